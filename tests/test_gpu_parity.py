@@ -1,0 +1,423 @@
+"""GPU parity: the CUDA path (through the Python mirror -> ctypes -> C ABI) against the numpy oracle and the committed
+golden vectors.  Bit-exact for indices / labels / IEEE-only arithmetic; <= 1e-5 relative where exp/log differ by ulps.
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+
+from oracle import boxpath_oracle as orc  # noqa: E402
+from tf_eager_object_detection_b200 import synthetic as syn  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # BASELINE.json north_star: "RoI features and decoded boxes within 1e-5 relative (fp32)"
+
+
+def close(a, b, scale=1.0):
+    """|a-b| <= 1e-5 * max(|a|,|b|, scale): relative, with `scale` as the magnitude floor of the tensor's own units."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    tol = RTOL * np.maximum(np.maximum(np.abs(a), np.abs(b)), scale)
+    bad = np.abs(a - b) > tol
+    assert not bad.any(), 'max err %g at %s' % (np.abs(a - b).max(), np.argwhere(bad)[:3].tolist())
+
+
+@pytest.fixture(scope='module')
+def bx():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import tf_eager_object_detection_b200.ops as ops
+    return ops
+
+
+def cu(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+@pytest.fixture(scope='module')
+def c4():
+    return syn.c4_image(1, 0, channels=8)
+
+
+@pytest.fixture(scope='module')
+def fpn():
+    return syn.fpn_image(3, 0, channels=8)
+
+
+# ------------------------------------------------------------------------------------------------ a1 / a2 / a12
+def test_decode_clip(bx, golden, c4):
+    out = bx.decode_clip(cu(c4['anchors']), cu(c4['deltas']), image_shape=(600, 1000)).cpu().numpy()
+    ref, _ = orc.bboxes_clip_filter(orc.decode_bbox(c4['anchors'], c4['deltas']), 0, 600, 1000)
+    close(out, ref, scale=1.0)
+    close(out[:2048], golden['c4_decoded_clipped_head'])
+    # known answer: zero delta on the first base anchor
+    one = bx.decode_clip(cu(np.float32([[-84, -40, 99, 55]])), cu(np.zeros((1, 4), np.float32)), image_shape=(600, 1000))
+    assert one.cpu().numpy().tolist() == [[0.0, 0.0, 100.0, 56.0]]
+    raw = bx.decode_clip(cu(np.float32([[-84, -40, 99, 55]])), cu(np.zeros((1, 4), np.float32)))
+    assert raw.cpu().numpy().tolist() == [[-84.0, -40.0, 100.0, 56.0]]
+
+
+def test_decode_with_stds_and_encode_roundtrip(bx):
+    rng = np.random.default_rng(5)
+    rois = syn.random_rois(rng, 1000, (600, 1000))
+    deltas = (rng.normal(0, 1, (1000, 4))).astype(np.float32)
+    means, stds = (0.0, 0.0, 0.0, 0.0), (0.1, 0.1, 0.2, 0.2)
+    dec = bx.decode_clip(cu(rois), cu(deltas), means, stds).cpu().numpy()
+    close(dec, orc.decode_bbox(rois, deltas, means, stds), scale=1.0)
+    gt, _ = syn.gt_boxes(rng, 1000, (600, 1000))
+    enc = bx.encode(cu(rois), cu(gt), means, stds).cpu().numpy()
+    close(enc, orc.encode_bbox(rois, gt, means, stds), scale=1.0)
+
+
+def test_clip_and_range_filters(bx, c4):
+    from tf_eager_object_detection_b200 import bbox_tf
+    dec = orc.decode_bbox(c4['anchors'], c4['deltas'])
+    b, idx = bbox_tf.bboxes_clip_filter(cu(dec), 0, 600, 1000, min_edge=16)
+    rb, ridx = orc.bboxes_clip_filter(dec, 0, 600, 1000, min_edge=16)
+    assert idx.dtype == torch.int64 and np.array_equal(idx.cpu().numpy(), ridx)
+    assert np.array_equal(b.cpu().numpy(), rb)
+    b2, idx2 = bbox_tf.bboxes_clip_filter(cu(dec), 0, 600, 1000)
+    assert np.array_equal(b2.cpu().numpy(), orc.bboxes_clip_filter(dec, 0, 600, 1000)[0])
+    assert idx2.dtype == torch.int32 and np.array_equal(idx2.cpu().numpy(), np.arange(dec.shape[0]))
+    inside = bbox_tf.bboxes_range_filter(cu(c4['anchors']), 600, 1000)
+    assert inside.shape[0] == 8151 and np.array_equal(inside.cpu().numpy(), orc.bboxes_range_filter(c4['anchors'], 600, 1000))
+
+
+# ------------------------------------------------------------------------------------------------ NMS (stage-wise)
+def test_nms_on_oracle_boxes_is_bit_exact(bx, golden, c4):
+    """SURVEY §7 mitigation (i): fed the oracle's decoded boxes, the kept indices must match without pre-screening."""
+    dec, _ = orc.bboxes_clip_filter(orc.decode_bbox(c4['anchors'], c4['deltas']), 0, 600, 1000)
+    for post, key in ((300, 'c4_eval_idx'), (2000, 'c4_train_idx')):
+        idx, cnt = bx.nms(cu(dec), cu(c4['scores']), post, 0.7)
+        assert int(cnt) == post
+        assert np.array_equal(idx.cpu().numpy(), golden[key])
+
+
+@pytest.mark.parametrize('n,max_out,thr', [(1, 5, 0.5), (37, 10, 0.3), (64, 64, 0.7), (65, 100, 0.5), (500, 500, 0.0),
+                                           (2049, 2048, 0.9), (5000, 300, 0.5), (30000, 2000, 0.6)])
+def test_nms_random_shapes(bx, n, max_out, thr):
+    rng = np.random.default_rng(n)
+    b = syn.random_rois(rng, n, (600, 1000))
+    s = ((rng.permutation(n) + 1) / (n + 1)).astype(np.float32)
+    idx, cnt = bx.nms(cu(b), cu(s), max_out, thr)
+    ref = orc.nms_tf(b, s, max_out, thr)
+    assert int(cnt) == ref.size
+    assert np.array_equal(idx.cpu().numpy()[:ref.size], ref)
+    assert (idx.cpu().numpy()[ref.size:] == -1).all()
+
+
+def test_nms_ties_degenerate_boxes_and_batch(bx):
+    rng = np.random.default_rng(11)
+    n = 3000
+    b = syn.random_rois(rng, n, (600, 1000))
+    b[::7, 2] = b[::7, 0]                       # zero-area boxes: never suppressed, never suppress
+    b[1::50] = b[1::50][:, [2, 3, 0, 1]]        # flipped corners: TF normalises with min/max
+    s = rng.integers(0, 40, n).astype(np.float32) / 40.0   # heavy score ties -> lower index first
+    s[5] = -0.0; s[6] = 0.0
+    batch_b = np.stack([b, b[::-1].copy(), np.roll(b, 17, axis=0)])
+    batch_s = np.stack([s, s[::-1].copy(), np.roll(s, 17)])
+    idx, cnt = bx.nms(cu(batch_b), cu(batch_s), 400, 0.5)
+    for i in range(3):
+        ref = orc.nms_tf(batch_b[i], batch_s[i], 400, 0.5)
+        assert int(cnt[i]) == ref.size
+        assert np.array_equal(idx[i].cpu().numpy()[:ref.size], ref)
+    # all scores equal: more ties than one selection chunk holds (exercises the index refinement of the select)
+    s_eq = np.full(n, 0.25, np.float32)
+    idx, cnt = bx.nms(cu(b), cu(s_eq), 2048, 0.3)
+    ref = orc.nms_tf(b, s_eq, 2048, 0.3)
+    assert int(cnt) == ref.size and np.array_equal(idx.cpu().numpy()[:ref.size], ref)
+
+
+def test_nms_argument_errors(bx):
+    b = cu(np.zeros((4, 4), np.float32)); s = cu(np.zeros(4, np.float32))
+    with pytest.raises(ValueError):
+        bx.nms(b, s, 10, 1.5)            # TF: iou_threshold must be in [0, 1]
+    with pytest.raises(NotImplementedError):
+        bx.nms(b, s, 5000, 0.5)          # documented limit: max_output_size <= 2048
+    from tf_eager_object_detection_b200._tensor import FLOAT32, INT32, Borrow
+    with pytest.raises(TypeError):       # wrong dtype is rejected by bx_dlpack_data, never silently converted
+        Borrow(0).ptr(b.to(torch.float64), FLOAT32, (4, 4))
+    with pytest.raises(TypeError):       # wrong shape
+        Borrow(0).ptr(b, FLOAT32, (4, 5))
+    with pytest.raises(TypeError):       # host memory is not accepted: there is no CPU path
+        Borrow(0).ptr(torch.zeros(4, 4), FLOAT32, (4, 4))
+    assert Borrow(0).ptr(s.to(torch.int32), INT32, (-1,)) != 0
+
+
+# ------------------------------------------------------------------------------------------------ a3 proposals
+def _margin(dec, scores, idx, thr):
+    """min |IoU - thr| over the pairs the greedy sweep compared decisively (kept x kept): pre-screen witness."""
+    k = dec[idx]
+    area = (k[:, 2] - k[:, 0]) * (k[:, 3] - k[:, 1])
+    iw = np.maximum(0, np.minimum(k[:, None, 2], k[None, :, 2]) - np.maximum(k[:, None, 0], k[None, :, 0]))
+    ih = np.maximum(0, np.minimum(k[:, None, 3], k[None, :, 3]) - np.maximum(k[:, None, 1], k[None, :, 1]))
+    inter = iw * ih
+    iou = inter / (area[:, None] + area[None, :] - inter)
+    np.fill_diagonal(iou, 0)
+    return np.abs(iou - thr).min()
+
+
+@pytest.mark.parametrize('mode,post', [('eval', 300), ('train', 2000)])
+def test_c4_region_proposal(bx, golden, c4, mode, post):
+    from tf_eager_object_detection_b200.region_proposal import RegionProposal
+    rp = RegionProposal()
+    rois = rp((cu(c4['deltas']), cu(c4['anchors']), cu(c4['scores']), c4['image_shape']), training=(mode == 'train'))
+    assert rois.shape == (post, 4)
+    close(rois.cpu().numpy(), golden['c4_%s_rois' % mode], scale=1.0)
+    ob, oi, oc = rp.call_batched((cu(c4['deltas'])[None], cu(c4['anchors']), cu(c4['scores'])[None], c4['image_shape']),
+                                 training=(mode == 'train'))
+    assert int(oc[0]) == post
+    assert np.array_equal(oi[0].cpu().numpy(), golden['c4_%s_idx' % mode])     # kept indices bit-exact
+    dec, _ = orc.bboxes_clip_filter(orc.decode_bbox(c4['anchors'], c4['deltas']), 0, 600, 1000)
+    assert _margin(dec, c4['scores'], golden['c4_%s_idx' % mode], 0.7) > 1e-5  # seed is decisively pre-screened
+
+
+def test_pre_nms_top_k_and_min_size(bx, golden, c4):
+    ob, oi, oc = bx.proposals(cu(c4['anchors']), cu(c4['deltas'])[None], cu(c4['scores'])[None], (600, 1000), 300,
+                              pre_nms_top_k=6000)
+    assert np.array_equal(oi[0].cpu().numpy(), golden['c4_eval_idx'])
+    # a top-k small enough to bite, and a min-size filter, against the oracle
+    for kw in (dict(pre_nms_top_k=200), dict(min_size=64.0), dict(pre_nms_top_k=3000, min_size=100.0)):
+        ob, oi, oc = bx.proposals(cu(c4['anchors']), cu(c4['deltas'])[None], cu(c4['scores'])[None], (600, 1000), 300, **kw)
+        rois, idx = orc.region_proposal(c4['deltas'], c4['anchors'], c4['scores'], (600, 1000), 300, **kw)
+        assert int(oc[0]) == idx.size
+        assert np.array_equal(oi[0].cpu().numpy()[:idx.size], idx)
+        close(ob[0].cpu().numpy()[:idx.size], rois, scale=1.0)
+        assert (oi[0].cpu().numpy()[idx.size:] == -1).all() and (ob[0].cpu().numpy()[idx.size:] == 0).all()
+
+
+def test_fpn_global_proposals(bx, golden, fpn):
+    """150 111 anchors (P2-P6), one global NMS, post 1000 — keys stream from global memory (no smem cache)."""
+    ob, oi, oc = bx.proposals(cu(fpn['anchors']), cu(fpn['deltas'])[None], cu(fpn['scores'])[None], (600, 1000), 1000)
+    assert int(oc[0]) == 1000
+    assert np.array_equal(oi[0].cpu().numpy(), golden['fpn_eval_idx'])
+    close(ob[0].cpu().numpy(), golden['fpn_eval_rois'], scale=1.0)
+
+
+def test_proposals_batch_of_images(bx):
+    imgs = [syn.c4_image(2, i, with_features=False) for i in range(4)]
+    deltas = np.stack([im['deltas'] for im in imgs]); scores = np.stack([im['scores'] for im in imgs])
+    ob, oi, oc = bx.proposals(cu(imgs[0]['anchors']), cu(deltas), cu(scores), (600, 1000), 300, pre_nms_top_k=6000)
+    for i, im in enumerate(imgs):
+        rois, idx = orc.region_proposal(im['deltas'], im['anchors'], im['scores'], (600, 1000), 300, pre_nms_top_k=6000)
+        assert int(oc[i]) == 300 and np.array_equal(oi[i].cpu().numpy(), idx)
+        close(ob[i].cpu().numpy(), rois, scale=1.0)
+
+
+def test_proposals_quota_not_filled(bx):
+    """few anchors, strong overlap: NMS exhausts every candidate before post_nms (multi-round path, padded output)."""
+    rng = np.random.default_rng(3)
+    anchors = syn.c4_anchors(6, 8, 16)
+    n = anchors.shape[0]
+    deltas, scores = syn.rpn_outputs(rng, n)
+    ob, oi, oc = bx.proposals(cu(anchors), cu(deltas)[None], cu(scores)[None], (96, 128), 300, iou_threshold=0.3)
+    rois, idx = orc.region_proposal(deltas, anchors, scores, (96, 128), 300, iou_threshold=0.3)
+    assert idx.size < 300 and int(oc[0]) == idx.size
+    assert np.array_equal(oi[0].cpu().numpy()[:idx.size], idx)
+
+
+# ------------------------------------------------------------------------------------------------ a4 / a5 / a8 RoI pooling
+def test_c4_roi_pooling_golden(bx, golden, c4):
+    from tf_eager_object_detection_b200.roi_pooling import RoiPoolingCropAndResize, RoiPoolingRoiAlign
+    rois = golden['c4_eval_rois'][:64]
+    feat = cu(c4['feat'][None])
+    out = RoiPoolingCropAndResize(7, False)((feat, cu(rois), 16)).cpu().numpy()
+    assert np.array_equal(out, golden['c4_pool_nomax'])          # IEEE-only arithmetic, same op order: bit-exact
+    out = RoiPoolingCropAndResize(7, True)((feat, cu(rois), 16)).cpu().numpy()
+    assert np.array_equal(out, golden['c4_pool_max'])
+    out = RoiPoolingRoiAlign(7)((feat, cu(rois), 16)).cpu().numpy()
+    close(out, golden['c4_roialign'], scale=1.0)
+
+
+def test_roi_pool_scalar_channel_path_and_box_ind(bx):
+    rng = np.random.default_rng(8)
+    feat = rng.standard_normal((3, 20, 30, 6), dtype=np.float32)       # C=6: not a multiple of 4 -> scalar kernel
+    rois = syn.random_rois(rng, 50, (320, 480))
+    bi = rng.integers(0, 3, 50).astype(np.int32)
+    from tf_eager_object_detection_b200 import _lib
+    out = bx.roi_pool(_lib.ROI_STRIDE_NORM, _lib.POOL_MAX2, 7, cu(feat), cu(rois), stride=16.0, box_ind=cu(bi)).cpu().numpy()
+    assert np.array_equal(out, orc.roi_pool_c4(feat, rois, 16, 7, True, box_ind=bi))
+    out = bx.roi_pool(_lib.ROI_IMAGE_NORM, _lib.POOL_MAX2, 7, cu(feat), cu(rois), image_shape=(320, 480), box_ind=cu(bi)).cpu().numpy()
+    assert np.array_equal(out, orc.roi_pool_fpn(feat, rois, (320, 480), 7, box_ind=bi))
+
+
+def test_crop_and_resize_raw_op(bx):
+    rng = np.random.default_rng(9)
+    img = rng.standard_normal((2, 11, 13, 4), dtype=np.float32)
+    boxes = np.float32([[0, 0, 1, 1], [0.1, 0.2, 1.3, 0.9], [-0.2, 0.0, 0.5, 0.5], [0.6, 0.6, 0.2, 0.1]])
+    bi = np.int32([0, 1, 1, 0])
+    from tf_eager_object_detection_b200.roi_pooling import crop_and_resize
+    out = crop_and_resize(cu(img), cu(boxes), cu(bi), [11, 11]).cpu().numpy()
+    ref = orc.crop_and_resize_tf(img, boxes, bi, 11, 11)
+    assert np.array_equal(out, ref)
+    # box [0,0,1,1] with crop == (square) feature size returns the map; y2n > 1 -> trailing rows exactly 0
+    sq = rng.standard_normal((1, 9, 9, 4), dtype=np.float32)
+    out = crop_and_resize(cu(sq), cu(np.float32([[0, 0, 1, 1], [0, 0, 1.5, 1]])), cu(np.int32([0, 0])), [9, 9]).cpu().numpy()
+    assert np.array_equal(out[0], sq[0])
+    assert (out[1][6:] == 0).all() and (out[1][:6] != 0).any()
+    with pytest.raises(ValueError):
+        crop_and_resize(cu(sq), cu(np.float32([[0, 0, 1, 1]])), cu(np.int32([0])), [0, 9])
+
+
+def test_fpn_levels_and_features(bx, golden, fpn):
+    from tf_eager_object_detection_b200 import fpn as fpn_mod
+    feats = [cu(f[None]) for f in fpn['feats']]
+    rois = golden['fpn_eval_rois']
+    assert orc.level_margin(rois).min() > 1e-5
+    rois_list, order = fpn_mod.assign_levels(cu(rois))
+    assert [r.shape[0] for r in rois_list] == golden['fpn_level_counts'].tolist()
+    assert order.dtype == torch.int64 and np.array_equal(order.cpu().numpy(), golden['fpn_level_order'])
+    out = fpn_mod.get_roi_features(rois_list, feats, fpn['image_shape'])
+    assert np.array_equal(out[:128].cpu().numpy(), golden['fpn_roi_features_head'])
+    fused, order2, lv, counts = fpn_mod.fpn_roi_features(cu(rois), feats, fpn['image_shape'])
+    assert torch.equal(fused, out) and np.array_equal(order2.cpu().numpy(), golden['fpn_level_order'])
+    assert counts.cpu().numpy().tolist() == golden['fpn_level_counts'].tolist()
+    # random rois: every level populated, borders extrapolated
+    rr = syn.random_rois(np.random.default_rng(syn.seed_for(3, 50)), 256, (600, 1000))
+    fused, order, lv, counts = fpn_mod.fpn_roi_features(cu(rr), feats, fpn['image_shape'])
+    assert np.array_equal(order.cpu().numpy(), golden['rand_level_order'])
+    assert np.array_equal(fused.cpu().numpy(), golden['rand_roi_features'])
+    # known answers, SURVEY A.8
+    sides = np.float32([300, 150, 500, 60, 20, 900])
+    b = np.stack([np.zeros(6, np.float32), np.zeros(6, np.float32), sides, sides], 1)
+    lv, _, _ = bx.fpn_assign_levels(cu(b))
+    assert lv.cpu().numpy().tolist() == [4, 3, 5, 2, 2, 5]
+
+
+# ------------------------------------------------------------------------------------------------ a9 - a11 targets
+def _targets_inputs():
+    rng = np.random.default_rng(syn.seed_for(4, 0))
+    gt, gl = syn.gt_boxes(rng, 100, (600, 1000))
+    anchors = syn.c4_anchors(38, 63)
+    perm = rng.permutation(anchors.shape[0])
+    return rng, gt, gl, anchors, perm
+
+
+def test_pairwise_iou(bx, golden):
+    from tf_eager_object_detection_b200.bbox_tf import pairwise_iou
+    _, gt, _, anchors, _ = _targets_inputs()
+    out = pairwise_iou(cu(anchors[:4096]), cu(gt)).cpu().numpy()
+    assert np.array_equal(out, golden['iou_anchors4096_gt100'])
+    full = pairwise_iou(cu(anchors), cu(gt)).cpu().numpy()           # BASELINE cfg 4: 21 546 x 100
+    assert np.array_equal(full, orc.pairwise_iou(anchors, gt))
+    ka = pairwise_iou(cu(np.float32([[0, 0, 9, 9], [5, 5, 14, 14]])), cu(np.float32([[0, 0, 9, 9]]))).cpu().numpy()
+    assert ka[0, 0] == 1.0 and ka[1, 0] == np.float32(25.0) / np.float32(175.0)
+
+
+@pytest.mark.parametrize('name,m', [('at', 100), ('at3', 3)])
+def test_anchor_target(bx, golden, name, m):
+    from tf_eager_object_detection_b200.anchor_target import AnchorTarget
+    _, gt, _, anchors, perm = _targets_inputs()
+    lab, tg, iw, ow = AnchorTarget()((cu(gt[:m]), [600, 1000], cu(anchors)), perm=perm.astype(np.int32))
+    assert np.array_equal(lab.cpu().numpy(), golden[name + '_labels'])        # sampled indices bit-exact
+    assert np.array_equal(iw.cpu().numpy(), golden[name + '_in_w'])
+    assert np.array_equal(ow.cpu().numpy(), golden[name + '_out_w'])
+    close(tg.cpu().numpy(), golden[name + '_targets'], scale=1.0)
+
+
+def test_anchor_target_batched_and_all_positive_quirk(bx):
+    from tf_eager_object_detection_b200.anchor_target import AnchorTarget
+    rng = np.random.default_rng(21)
+    anchors = syn.c4_anchors(38, 63)
+    gts, perms = [], []
+    for i in range(3):
+        g, _ = syn.gt_boxes(rng, 20, (600, 1000))
+        gts.append(g); perms.append(rng.permutation(anchors.shape[0]).astype(np.int32))
+    # image 2: one gt box no inside anchor overlaps -> column max 0 -> every inside anchor becomes fg (py-faster-rcnn quirk)
+    gts[2][0] = np.float32([0, 0, 1, 1])
+    lab, tg, iw, ow, cnt = AnchorTarget().call_batched((cu(np.stack(gts)), [600, 1000], cu(anchors)), perm=np.stack(perms))
+    for i in range(3):
+        rl, rt, ri, ro, info = orc.anchor_target(gts[i], [600, 1000], anchors, perms[i])
+        assert np.array_equal(lab[i].cpu().numpy(), rl), i
+        assert np.array_equal(iw[i].cpu().numpy(), ri) and np.array_equal(ow[i].cpu().numpy(), ro)
+        close(tg[i].cpu().numpy(), rt, scale=1.0)
+        assert cnt[i].cpu().numpy().tolist() == [int((rl == 1).sum()), int((rl == 0).sum())]
+
+
+@pytest.mark.parametrize('name,kw', [
+    ('pt', dict(total_num_samples=128, max_pos_samples=32, neg_iou_threshold=0.0)),
+    ('pt_fpn', dict(total_num_samples=256, max_pos_samples=64, neg_iou_threshold=0.0)),
+    ('pt_pad', dict(total_num_samples=2048, max_pos_samples=512, neg_iou_threshold=0.1)),
+])
+def test_proposal_target(bx, golden, name, kw):
+    from tf_eager_object_detection_b200.proposal_target import ProposalTarget
+    rng, gt, gl, _, _ = _targets_inputs()
+    rois = golden['c4_train_rois']
+    perm_r = rng.permutation(rois.shape[0]).astype(np.int32)
+    pt = ProposalTarget(num_classes=21, pos_iou_threshold=0.5, target_stds=[0.1, 0.1, 0.2, 0.2], **kw)
+    out = pt((cu(rois), cu(gt), cu(gl)), perm=perm_r)
+    names = ('rois', 'labels', 'targets', 'in_w', 'out_w')
+    for k, v in zip(names, out):
+        g = golden['%s_%s' % (name, k)]
+        if k == 'targets':
+            close(v.cpu().numpy(), g, scale=1.0)
+        else:
+            assert np.array_equal(v.cpu().numpy(), g), k
+
+
+def test_proposal_target_empty_background_raises(bx):
+    from tf_eager_object_detection_b200.proposal_target import ProposalTarget
+    gt = np.float32([[10, 10, 100, 100]])
+    rois = np.float32([[10, 10, 100, 100], [12, 11, 101, 99]])      # both fg, no bg: np.random.choice would raise
+    with pytest.raises(ValueError):
+        ProposalTarget(neg_iou_threshold=0.0)((cu(rois), cu(gt), cu(np.int32([3]))), perm=np.int32([0, 1]))
+
+
+# ------------------------------------------------------------------------------------------------ composite + host path
+def test_c4_composite_and_host_entry(bx):
+    imgs = [syn.c4_image(2, i, channels=32) for i in range(2)]
+    anchors = imgs[0]['anchors']
+    deltas = np.stack([im['deltas'] for im in imgs]); scores = np.stack([im['scores'] for im in imgs])
+    feat = np.stack([im['feat'] for im in imgs])
+    ob, oi, oc, of = bx.c4_proposal_roi(cu(anchors), cu(deltas), cu(scores), cu(feat), (600, 1000), 300,
+                                        pre_nms_top_k=6000)
+    of = of.reshape(2, 300, 7, 7, 32)
+    for i, im in enumerate(imgs):
+        rois, idx = orc.region_proposal(im['deltas'], anchors, im['scores'], (600, 1000), 300, pre_nms_top_k=6000)
+        assert np.array_equal(oi[i].cpu().numpy(), idx)
+        # stage-wise exactness: pooling the GPU's own rois with the oracle reproduces the GPU features bit for bit
+        assert np.array_equal(of[i].cpu().numpy(), orc.roi_pool_c4(im['feat'][None], ob[i].cpu().numpy(), 16, 7, False))
+        # end to end: within 1e-5 relative of the oracle chain (decode differs by exp ulps)
+        close(of[i].cpu().numpy(), orc.roi_pool_c4(im['feat'][None], rois, 16, 7, False), scale=1.0)
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    out_h = (torch.empty((2, 300, 4)).pin_memory(), torch.empty((2, 300), dtype=torch.int32).pin_memory(),
+             torch.empty((2,), dtype=torch.int32).pin_memory(), torch.empty((600, 7, 7, 32)).pin_memory())
+    bx.c4_proposal_roi_host(cu(anchors), pin(deltas), pin(scores), pin(feat), (600, 1000), 300, out_h, pre_nms_top_k=6000)
+    torch.cuda.synchronize()
+    assert torch.equal(out_h[0], ob.cpu()) and torch.equal(out_h[1], oi.cpu()) and torch.equal(out_h[2], oc.cpu())
+    assert torch.equal(out_h[3], of.reshape(600, 7, 7, 32).cpu())
+
+
+# ------------------------------------------------------------------------------------------------ full BASELINE sizes
+def test_full_size_cfg2_properties(bx):
+    """BASELINE cfg 2 at full size (batch 8, 38x63x1024, 6000 -> 300, 7x7x1024): size-independent properties."""
+    B, C = 8, 1024
+    imgs = [syn.c4_image(2, i, with_features=False) for i in range(B)]
+    anchors = cu(imgs[0]['anchors'])
+    deltas = cu(np.stack([im['deltas'] for im in imgs])); scores = cu(np.stack([im['scores'] for im in imgs]))
+    g = torch.Generator(device='cuda'); g.manual_seed(1)
+    f1 = torch.randn((B, 38, 63, C), device='cuda', generator=g)
+    f2 = torch.randn((B, 38, 63, C), device='cuda', generator=g)
+    ob, oi, oc, o1 = bx.c4_proposal_roi(anchors, deltas, scores, f1, (600, 1000), 300, pre_nms_top_k=6000)
+    assert (oc == 300).all()
+    s_kept = torch.gather(scores, 1, oi.long())
+    assert (s_kept[:, 1:] < s_kept[:, :-1]).all()                        # selection order = strictly descending score
+    # idempotence: NMS over the kept boxes keeps all of them, in order
+    idx2, cnt2 = bx.nms(ob, s_kept, 300, 0.7)
+    assert (cnt2 == 300).all() and (idx2 == torch.arange(300, device='cuda', dtype=torch.int32)[None]).all()
+    # kept indices match the oracle on every image
+    for i, im in enumerate(imgs):
+        _, idx = orc.region_proposal(im['deltas'], im['anchors'], im['scores'], (600, 1000), 300, pre_nms_top_k=6000)
+        assert np.array_equal(oi[i].cpu().numpy(), idx)
+    # linearity of crop_and_resize in the feature map: pool(f1 + f2) == pool(f1) + pool(f2) within fp32 rounding
+    _, _, _, o2 = bx.c4_proposal_roi(anchors, deltas, scores, f2, (600, 1000), 300, pre_nms_top_k=6000)
+    _, _, _, o12 = bx.c4_proposal_roi(anchors, deltas, scores, f1 + f2, (600, 1000), 300, pre_nms_top_k=6000)
+    assert torch.allclose(o12, o1 + o2, rtol=1e-5, atol=2e-5)
+    # spot-check rows against the oracle at full channel count
+    sel = [0, 299, 1200, 2399]
+    rows = o1.reshape(B, 300, 7, 7, C)
+    for j in sel:
+        i, r = divmod(j, 300)
+        ref = orc.roi_pool_c4(f1[i:i + 1].cpu().numpy(), ob[i, r:r + 1].cpu().numpy(), 16, 7, False)
+        assert np.array_equal(rows[i, r].cpu().numpy(), ref[0])

@@ -1,0 +1,131 @@
+"""The standalone numpy oracle (oracle/boxpath_oracle.py) against the committed golden vectors that
+`oracle/make_golden.py` produced by running the reference's own files on the numpy TF shim."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import boxpath_oracle as orc
+from tf_eager_object_detection_b200 import synthetic as syn
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+@pytest.fixture(scope='module')
+def c4():
+    return syn.c4_image(1, 0, channels=8)
+
+
+@pytest.fixture(scope='module')
+def fpn():
+    return syn.fpn_image(3, 0, channels=8)
+
+
+def test_anchor_generators_match_reference(golden):
+    assert np.array_equal(syn.anchor_base(16).astype(np.float32), golden['anchor_base'])
+    assert np.array_equal(sha(syn.c4_anchors(38, 63, 16)), golden['c4_anchors_sha'])
+    assert np.array_equal(sha(syn.fpn_anchors((600, 1000))), golden['fpn_anchors_sha'])
+    assert syn.c4_anchors(38, 63).shape[0] == 21546
+    assert syn.fpn_anchors((600, 1000)).shape[0] == 150111
+    assert syn.fpn_anchors((800, 1333)).shape[0] == 267069
+    a = syn.c4_anchors(38, 63)
+    assert orc.bboxes_range_filter(a, 600, 1000).shape[0] == int(golden['c4_inside_count']) == 8151
+
+
+def test_decode_clip(golden, c4):
+    dec = orc.decode_bbox(c4['anchors'], c4['deltas'])
+    dec, idx = orc.bboxes_clip_filter(dec, 0, 600, 1000)
+    assert np.array_equal(dec[:2048], golden['c4_decoded_clipped_head'])
+    assert np.array_equal(sha(dec), golden['c4_decoded_clipped_sha'])
+    assert idx.dtype == np.int32 and np.array_equal(idx, np.arange(21546))
+
+
+@pytest.mark.parametrize('mode,post', [('eval', 300), ('train', 2000)])
+def test_c4_region_proposal(golden, c4, mode, post):
+    rois, idx = orc.region_proposal(c4['deltas'], c4['anchors'], c4['scores'], c4['image_shape'], post)
+    assert np.array_equal(idx, golden['c4_%s_idx' % mode])
+    assert np.array_equal(rois, golden['c4_%s_rois' % mode])
+
+
+def test_pre_nms_top_k_is_a_noop_when_quota_fills(golden, c4):
+    """with unique scores, top-k(6000) + NMS == NMS over all anchors if 300 are reached."""
+    rois, idx, st = orc.region_proposal(c4['deltas'], c4['anchors'], c4['scores'], c4['image_shape'], 300,
+                                        pre_nms_top_k=6000, return_stats=True)
+    assert st['examined'] <= 6000
+    assert np.array_equal(idx, golden['c4_eval_idx'])
+
+
+def test_c4_roi_pooling(golden, c4):
+    rois = golden['c4_eval_rois'][:64]
+    feat = c4['feat'][None]
+    assert np.array_equal(orc.roi_pool_c4(feat, rois, 16, 7, False), golden['c4_pool_nomax'])
+    assert np.array_equal(orc.roi_pool_c4(feat, rois, 16, 7, True), golden['c4_pool_max'])
+    assert np.array_equal(orc.roi_align_pad(feat, rois, 16, 7), golden['c4_roialign'])
+
+
+def test_fpn_proposals_levels_features(golden, fpn):
+    rois, idx = orc.region_proposal(fpn['deltas'], fpn['anchors'], fpn['scores'], fpn['image_shape'], 1000)
+    assert np.array_equal(idx, golden['fpn_eval_idx'])
+    assert np.array_equal(rois, golden['fpn_eval_rois'])
+    lv, rois_list, order = orc.assign_levels(rois)
+    assert np.array_equal([r.shape[0] for r in rois_list], golden['fpn_level_counts'])
+    assert np.array_equal(order, golden['fpn_level_order'])
+    feats = [f[None] for f in fpn['feats']]
+    out = orc.fpn_roi_features(rois_list, feats, fpn['image_shape'])
+    assert out.shape == (1000, 7, 7, 8)
+    assert np.array_equal(out[:128], golden['fpn_roi_features_head'])
+
+
+def test_fpn_random_rois_cover_levels_and_borders(golden, fpn):
+    rr = syn.random_rois(np.random.default_rng(syn.seed_for(3, 50)), 256, (600, 1000))
+    lv, rois_list, order = orc.assign_levels(rr)
+    assert np.array_equal([r.shape[0] for r in rois_list], golden['rand_level_counts'])
+    assert (golden['rand_level_counts'] > 0).all()
+    assert np.array_equal(order, golden['rand_level_order'])
+    out = orc.fpn_roi_features(rois_list, [f[None] for f in fpn['feats']], fpn['image_shape'])
+    assert np.array_equal(out, golden['rand_roi_features'])
+
+
+def _targets_inputs():
+    rng = np.random.default_rng(syn.seed_for(4, 0))
+    gt, gl = syn.gt_boxes(rng, 100, (600, 1000))
+    anchors = syn.c4_anchors(38, 63)
+    perm = rng.permutation(anchors.shape[0])
+    return rng, gt, gl, anchors, perm
+
+
+def test_pairwise_iou(golden):
+    _, gt, _, anchors, _ = _targets_inputs()
+    assert np.array_equal(orc.pairwise_iou(anchors[:4096], gt), golden['iou_anchors4096_gt100'])
+    got = orc.pairwise_iou(np.float32([[0, 0, 9, 9], [5, 5, 14, 14]]), np.float32([[0, 0, 9, 9]]))
+    assert got[0, 0] == 1.0 and got[1, 0] == np.float32(25.0) / np.float32(175.0)
+
+
+@pytest.mark.parametrize('name,m', [('at', 100), ('at3', 3)])
+def test_anchor_target(golden, name, m):
+    _, gt, _, anchors, perm = _targets_inputs()
+    lab, tg, iw, ow, info = orc.anchor_target(gt[:m], [600, 1000], anchors, perm)
+    assert np.array_equal(lab, golden[name + '_labels'])
+    assert np.array_equal(iw, golden[name + '_in_w'])
+    assert np.array_equal(ow, golden[name + '_out_w'])
+    assert np.array_equal(tg, golden[name + '_targets'])
+    assert (lab == 1).sum() <= 128 and (lab >= 0).sum() <= 256
+
+
+@pytest.mark.parametrize('name,kw', [
+    ('pt', dict(total_num_samples=128, max_pos_samples=32, neg_iou_threshold=0.0)),
+    ('pt_fpn', dict(total_num_samples=256, max_pos_samples=64, neg_iou_threshold=0.0)),
+    ('pt_pad', dict(total_num_samples=2048, max_pos_samples=512, neg_iou_threshold=0.1)),
+])
+def test_proposal_target(golden, name, kw):
+    rng, gt, gl, anchors, _ = _targets_inputs()
+    rois = golden['c4_train_rois']
+    perm_r = rng.permutation(rois.shape[0])
+    out = orc.proposal_target(rois, gt, gl, perm_r, num_classes=21, pos_iou_threshold=0.5,
+                              stds=(0.1, 0.1, 0.2, 0.2), **kw)
+    for k, v in zip(('rois', 'labels', 'targets', 'in_w', 'out_w'), out[:5]):
+        assert np.array_equal(v, golden['%s_%s' % (name, k)]), k
+    if name == 'pt_pad':   # the np.random.choice(replace=True) branch really ran
+        assert len(np.unique(out[5]['keep'])) < 2048

@@ -1,0 +1,129 @@
+"""ctypes binding of include/boxpath.h (libboxpath.so).  No fallback: a missing library or a missing CUDA
+device raises — the product path never computes on the CPU."""
+import ctypes
+import os
+import threading
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libboxpath.so')
+
+BX_OK, BX_ERR_INVALID, BX_ERR_CUDA, BX_ERR_UNSUPPORTED, BX_ERR_DLPACK = 0, -1, -2, -3, -4
+ROI_STRIDE_NORM, ROI_IMAGE_NORM, ROI_ALIGN_PAD = 0, 1, 2
+POOL_NONE, POOL_MAX2, POOL_AVG2 = 0, 1, 2
+
+F4 = c_float * 4
+
+
+class ProposalParams(ctypes.Structure):
+    _fields_ = [('means', F4), ('stds', F4), ('image_h', c_int), ('image_w', c_int), ('pre_nms_top_k', c_int),
+                ('post_nms', c_int), ('iou_threshold', c_float), ('min_size', c_float)]
+
+
+class AnchorTargetParams(ctypes.Structure):
+    _fields_ = [('pos_iou_threshold', c_float), ('neg_iou_threshold', c_float), ('total_num_samples', c_int),
+                ('max_pos_samples', c_int), ('means', F4), ('stds', F4), ('image_h', c_int), ('image_w', c_int)]
+
+
+class ProposalTargetParams(ctypes.Structure):
+    _fields_ = [('num_classes', c_int), ('pos_iou_threshold', c_float), ('neg_iou_threshold', c_float),
+                ('total_num_samples', c_int), ('max_pos_samples', c_int), ('means', F4), ('stds', F4)]
+
+
+P = c_void_p  # device pointers travel as integers
+
+# name -> (restype, argtypes); every symbol include/boxpath.h declares
+SIGNATURES = {
+    'bx_version': (c_int, []),
+    'bx_last_error': (c_char_p, []),
+    'bx_create': (c_int, [c_int, POINTER(c_void_p)]),
+    'bx_destroy': (c_int, [c_void_p]),
+    'bx_launch_count': (c_longlong, [c_void_p]),
+    'bx_dlpack_data': (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_int64), c_int, POINTER(c_void_p)]),
+    'bx_decode_clip': (c_int, [c_void_p, P, c_int, P, c_int, c_int, F4, F4, c_int, c_int, P, c_void_p]),
+    'bx_encode': (c_int, [c_void_p, P, P, c_int, F4, F4, P, c_void_p]),
+    'bx_clip_filter': (c_int, [c_void_p, P, c_int, c_float, c_int, c_int, c_float, P, P, P, c_void_p]),
+    'bx_range_filter': (c_int, [c_void_p, P, c_int, c_int, c_int, P, P, c_void_p]),
+    'bx_nms': (c_int, [c_void_p, P, P, c_int, c_int, c_int, c_float, P, P, c_void_p]),
+    'bx_proposals': (c_int, [c_void_p, P, P, P, c_int, c_int, POINTER(ProposalParams), P, P, P, c_void_p]),
+    'bx_crop_and_resize': (c_int, [c_void_p, P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_float, P,
+                                   c_void_p]),
+    'bx_roi_pool': (c_int, [c_void_p, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float,
+                            c_int, c_int, P, c_void_p]),
+    'bx_fpn_assign_levels': (c_int, [c_void_p, P, c_int, c_int, c_int, P, P, P, c_void_p]),
+    'bx_fpn_roi_features': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_int, c_int, c_int,
+                                    c_int, P, P, c_int, c_int, c_int, c_int, P, P, P, P, c_void_p]),
+    'bx_pairwise_iou': (c_int, [c_void_p, P, c_int, P, c_int, P, c_void_p]),
+    'bx_anchor_target': (c_int, [c_void_p, P, c_int, P, P, c_int, c_int, P, POINTER(AnchorTargetParams), P, P, P, P,
+                                 P, c_void_p]),
+    'bx_proposal_target': (c_int, [c_void_p, P, P, c_int, P, P, P, c_int, c_int, P, POINTER(ProposalTargetParams), P,
+                                   P, P, P, P, P, P, c_void_p]),
+    'bx_c4_proposal_roi': (c_int, [c_void_p, P, P, P, P, c_int, c_int, c_int, c_int, c_int, POINTER(ProposalParams),
+                                   c_float, c_int, c_int, P, P, P, P, c_void_p]),
+    'bx_c4_proposal_roi_host': (c_int, [c_void_p, P, P, P, P, c_int, c_int, c_int, c_int, c_int,
+                                        POINTER(ProposalParams), c_float, c_int, c_int, P, P, P, P, c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_handles = {}
+
+
+class BoxpathError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libboxpath.so (once).  Raises ImportError if it has not been built — there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    'libboxpath.so not found at %s: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                    '(or ./build.sh).  tf_eager_object_detection_b200 has no CPU fallback.' % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().bx_last_error().decode('utf-8', 'replace')
+
+
+def check(rc):
+    if rc == BX_OK:
+        return
+    msg = last_error()
+    if rc == BX_ERR_INVALID:
+        raise ValueError(msg)                 # the reference raises ValueError / TF InvalidArgumentError here
+    if rc == BX_ERR_DLPACK:
+        raise TypeError(msg)
+    if rc == BX_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise BoxpathError(msg)
+
+
+def handle(device_index):
+    """bx_handle* for (device, calling thread) — SURVEY §8b: one handle per (device, host thread)."""
+    key = (int(device_index), threading.get_ident())
+    h = _handles.get(key)
+    if h is None:
+        lib = load()
+        out = c_void_p()
+        check(lib.bx_create(int(device_index), ctypes.byref(out)))
+        h = _handles[key] = out
+    return h
+
+
+def launch_count(device_index):
+    return int(load().bx_launch_count(handle(device_index)))
+
+
+def f4(values):
+    return F4(*[float(v) for v in values])

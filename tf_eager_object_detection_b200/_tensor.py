@@ -1,0 +1,74 @@
+"""Zero-copy tensor hand-off: any object exposing `__dlpack__` (torch CUDA tensors here; a TF>=2.2 EagerTensor through
+tf.experimental.dlpack in the reference's world) -> DLTensor* -> validated device pointer (bx_dlpack_data).
+
+torch is used for device memory (output allocation), streams and nothing else."""
+import ctypes
+from ctypes import c_char_p, c_int64, c_void_p, py_object
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_PyCapsule_GetPointer = ctypes.pythonapi.PyCapsule_GetPointer
+_PyCapsule_GetPointer.restype = c_void_p
+_PyCapsule_GetPointer.argtypes = [py_object, c_char_p]
+
+FLOAT32 = (2, 32)
+INT32 = (0, 32)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.BoxpathError('no CUDA device available: tf_eager_object_detection_b200 runs only on the GPU '
+                                '(hand-written sm_100a kernels; no CPU fallback)')
+
+
+def to_device(x, dtype, device=None):
+    """Inputs may arrive as torch tensors (kept as they are, zero-copy) or as numpy / lists (copied host->device,
+    as feeding a numpy array to a TF op would)."""
+    if isinstance(x, torch.Tensor):
+        if not x.is_cuda:
+            require_cuda()
+            x = x.cuda(device)
+        if x.dtype != dtype:
+            x = x.to(dtype)
+        return x.detach()
+    require_cuda()
+    np_dtype = {torch.float32: np.float32, torch.int32: np.int32}[dtype]
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np_dtype)), device=device or 'cuda')
+
+
+class Borrow:
+    """Holds the DLPack capsules of one call alive and resolves them to validated device pointers."""
+
+    def __init__(self, device_index):
+        self.device = device_index
+        self._caps = []
+        self._lib = _lib.load()
+
+    def ptr(self, t, kind, shape, align=4):
+        if t is None:
+            return None
+        if isinstance(t, torch.Tensor) and not t.is_contiguous():
+            t = t.contiguous()
+            self._caps.append(t)
+        cap = t.__dlpack__()
+        self._caps.append(cap)
+        dl = _PyCapsule_GetPointer(cap, b'dltensor')
+        shp = (c_int64 * len(shape))(*shape)
+        out = c_void_p()
+        _lib.check(self._lib.bx_dlpack_data(dl, self.device, kind[0], kind[1], len(shape), shp, align, ctypes.byref(out)))
+        return out.value if out.value else 0
+
+
+def device_index_of(t):
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def stream_ptr(device_index):
+    return c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+def empty(shape, dtype, device_index):
+    return torch.empty(shape, dtype=dtype, device=torch.device('cuda', device_index))

@@ -1,0 +1,150 @@
+// Handle, error reporting, workspace, DLPack validation and the composite C4 entry points of libboxpath.
+#include <stdarg.h>
+#include <string.h>
+
+#include "bx_common.cuh"
+#include "bx_dlpack.h"
+
+static thread_local char g_err[512] = "";
+
+void bx_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int reserve(void** p, size_t* cur, size_t bytes) {
+  if (*cur >= bytes) return BX_OK;
+  // growth only: happens on the first call of a given problem size, never in steady state
+  size_t want = bytes + (bytes >> 2);
+  want = (want + 0xFFFFF) & ~static_cast<size_t>(0xFFFFF);
+  if (*p) {
+    BX_CUDA(cudaDeviceSynchronize());  // the old block may still be in use by enqueued kernels
+    BX_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *cur = 0;
+  }
+  BX_CUDA(cudaMalloc(p, want));
+  *cur = want;
+  return BX_OK;
+}
+
+int bx_ws_reserve(bx_handle* h, size_t bytes) { return reserve(&h->ws, &h->ws_bytes, bytes); }
+int bx_stage_reserve(bx_handle* h, size_t bytes) { return reserve(&h->stage, &h->stage_bytes, bytes); }
+
+extern "C" int bx_version(void) { return BX_VERSION; }
+extern "C" const char* bx_last_error(void) { return g_err; }
+
+extern "C" int bx_create(int device, bx_handle** out) {
+  BX_REQUIRE(out, BX_ERR_INVALID, "bx_create: NULL out");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    bx_set_error("bx_create: no CUDA device available (%s); libboxpath has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return BX_ERR_CUDA;
+  }
+  BX_REQUIRE(device >= 0 && device < count, BX_ERR_INVALID, "bx_create: device %d not in [0, %d)", device, count);
+  BX_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BX_CUDA(cudaGetDeviceProperties(&prop, device));
+  BX_REQUIRE(prop.major >= 10, BX_ERR_UNSUPPORTED, "bx_create: device %d is sm_%d%d; libboxpath is built for sm_100a only",
+             device, prop.major, prop.minor);
+  bx_handle* h = new bx_handle();
+  memset(h, 0, sizeof(*h));
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = h;
+  return BX_OK;
+}
+
+extern "C" int bx_destroy(bx_handle* h) {
+  if (!h) return BX_OK;
+  cudaSetDevice(h->device);
+  if (h->ws) cudaFree(h->ws);
+  if (h->stage) cudaFree(h->stage);
+  delete h;
+  return BX_OK;
+}
+
+extern "C" long long bx_launch_count(const bx_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int bx_dlpack_data(const void* dltensor, int device, int dtype_code, int bits, int ndim,
+                              const int64_t* shape, int align_bytes, void** out_data) {
+  BX_REQUIRE(dltensor && out_data, BX_ERR_INVALID, "bx_dlpack_data: NULL argument");
+  const BxDLTensor* t = static_cast<const BxDLTensor*>(dltensor);
+  BX_REQUIRE(t->device.device_type == 2 /*kDLCUDA*/, BX_ERR_DLPACK,
+             "tensor is not on a CUDA device (DLDeviceType %d); libboxpath has no CPU path", t->device.device_type);
+  BX_REQUIRE(device < 0 || t->device.device_id == device, BX_ERR_DLPACK, "tensor is on cuda:%d, handle is on cuda:%d",
+             t->device.device_id, device);
+  BX_REQUIRE(t->dtype.code == dtype_code && t->dtype.bits == bits && t->dtype.lanes == 1, BX_ERR_DLPACK,
+             "tensor dtype (code %d, %d bits) != expected (code %d, %d bits)", t->dtype.code, t->dtype.bits, dtype_code, bits);
+  BX_REQUIRE(t->ndim == ndim, BX_ERR_DLPACK, "tensor has %d dims, expected %d", t->ndim, ndim);
+  int64_t expect_stride = 1;
+  for (int d = ndim - 1; d >= 0; --d) {
+    BX_REQUIRE(!shape || shape[d] < 0 || t->shape[d] == shape[d], BX_ERR_DLPACK, "tensor dim %d is %lld, expected %lld", d,
+               (long long)t->shape[d], (long long)(shape ? shape[d] : -1));
+    if (t->strides && t->shape[d] > 1)
+      BX_REQUIRE(t->strides[d] == expect_stride, BX_ERR_DLPACK, "tensor is not C-contiguous (dim %d stride %lld)", d,
+                 (long long)t->strides[d]);
+    expect_stride *= t->shape[d];
+  }
+  void* p = static_cast<char*>(t->data) + t->byte_offset;
+  BX_REQUIRE(align_bytes <= 1 || expect_stride == 0 || bx_aligned(p, align_bytes), BX_ERR_DLPACK,
+             "tensor data is not %d-byte aligned", align_bytes);
+  *out_data = p;
+  return BX_OK;
+}
+
+extern "C" int bx_c4_proposal_roi(bx_handle* h, const float* anchors, const float* deltas, const float* scores,
+                                  const float* feat, int batch, int n, int fh, int fw, int c,
+                                  const bx_proposal_params* p, float stride, int pool_size, int pool, float* out_rois,
+                                  int* out_idx, int* out_count, float* out_feat, void* stream) {
+  BX_REQUIRE(p, BX_ERR_INVALID, "bx_c4_proposal_roi: NULL params");
+  int rc = bx_proposals(h, anchors, deltas, scores, batch, n, p, out_rois, out_idx, out_count, stream);
+  if (rc) return rc;
+  return bx_roi_pool(h, BX_ROI_STRIDE_NORM, pool, pool_size, feat, batch, fh, fw, c, out_rois, nullptr, out_count,
+                     batch * p->post_nms, stride, p->image_h, p->image_w, out_feat, stream);
+}
+
+extern "C" int bx_c4_proposal_roi_host(bx_handle* h, const float* anchors_dev, const float* deltas_host,
+                                       const float* scores_host, const float* feat_host, int batch, int n, int fh,
+                                       int fw, int c, const bx_proposal_params* p, float stride, int pool_size,
+                                       int pool, float* out_rois_host, int* out_idx_host, int* out_count_host,
+                                       float* out_feat_host, void* stream) {
+  BX_REQUIRE(h && p && deltas_host && scores_host && feat_host && out_rois_host && out_idx_host && out_count_host &&
+                 out_feat_host, BX_ERR_INVALID, "bx_c4_proposal_roi_host: NULL argument");
+  BX_REQUIRE(batch > 0 && n > 0 && fh > 0 && fw > 0 && c > 0 && pool_size > 0, BX_ERR_INVALID,
+             "bx_c4_proposal_roi_host: bad size");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+  const size_t b_deltas = up(sizeof(float) * 4 * batch * (size_t)n), b_scores = up(sizeof(float) * batch * (size_t)n);
+  const size_t b_feat = up(sizeof(float) * (size_t)batch * fh * fw * c);
+  const size_t k = static_cast<size_t>(batch) * p->post_nms;
+  const size_t b_rois = up(sizeof(float) * 4 * k), b_idx = up(sizeof(int) * k), b_cnt = up(sizeof(int) * batch);
+  const size_t b_out = up(sizeof(float) * k * pool_size * pool_size * c);
+  int rc = bx_stage_reserve(h, b_deltas + b_scores + b_feat + b_rois + b_idx + b_cnt + b_out);
+  if (rc) return rc;
+  char* base = static_cast<char*>(h->stage);
+  float* d_deltas = reinterpret_cast<float*>(base); base += b_deltas;
+  float* d_scores = reinterpret_cast<float*>(base); base += b_scores;
+  float* d_feat = reinterpret_cast<float*>(base); base += b_feat;
+  float* d_rois = reinterpret_cast<float*>(base); base += b_rois;
+  int* d_idx = reinterpret_cast<int*>(base); base += b_idx;
+  int* d_cnt = reinterpret_cast<int*>(base); base += b_cnt;
+  float* d_out = reinterpret_cast<float*>(base);
+  BX_CUDA(cudaMemcpyAsync(d_deltas, deltas_host, sizeof(float) * 4 * batch * (size_t)n, cudaMemcpyHostToDevice, st));
+  BX_CUDA(cudaMemcpyAsync(d_scores, scores_host, sizeof(float) * batch * (size_t)n, cudaMemcpyHostToDevice, st));
+  BX_CUDA(cudaMemcpyAsync(d_feat, feat_host, sizeof(float) * (size_t)batch * fh * fw * c, cudaMemcpyHostToDevice, st));
+  rc = bx_c4_proposal_roi(h, anchors_dev, d_deltas, d_scores, d_feat, batch, n, fh, fw, c, p, stride, pool_size, pool,
+                          d_rois, d_idx, d_cnt, d_out, stream);
+  if (rc) return rc;
+  BX_CUDA(cudaMemcpyAsync(out_rois_host, d_rois, sizeof(float) * 4 * k, cudaMemcpyDeviceToHost, st));
+  BX_CUDA(cudaMemcpyAsync(out_idx_host, d_idx, sizeof(int) * k, cudaMemcpyDeviceToHost, st));
+  BX_CUDA(cudaMemcpyAsync(out_count_host, d_cnt, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+  BX_CUDA(cudaMemcpyAsync(out_feat_host, d_out, sizeof(float) * k * pool_size * pool_size * c, cudaMemcpyDeviceToHost, st));
+  return BX_OK;
+}

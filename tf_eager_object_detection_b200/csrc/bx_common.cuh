@@ -1,0 +1,123 @@
+// Shared host/device helpers for libboxpath (sm_100a).  Compiled with -fmad=false: every fp32 expression on the
+// path is evaluated in the reference's op order with IEEE add/mul/div, no FMA contraction (DESIGN.md "Numerics").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/boxpath.h"
+
+#define BX_NUM_SMS_B200 148
+
+struct bx_handle {
+  int device;
+  int num_sms;
+  size_t smem_optin;     // max dynamic shared memory per block
+  void* ws;              // device workspace (grown on demand, stream-ordered by the caller's stream)
+  size_t ws_bytes;
+  void* stage;           // device staging area of the *_host entry points
+  size_t stage_bytes;
+  long long launches;
+};
+
+void bx_set_error(const char* fmt, ...);
+int bx_ws_reserve(bx_handle* h, size_t bytes);       // ensure h->ws has >= bytes (may cudaMalloc; not in steady state)
+int bx_stage_reserve(bx_handle* h, size_t bytes);
+
+#define BX_REQUIRE(cond, code, ...)  \
+  do {                               \
+    if (!(cond)) {                   \
+      bx_set_error(__VA_ARGS__);     \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+#define BX_CUDA(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      bx_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+      return BX_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+#define BX_LAUNCH_CHECK(h)                                                                   \
+  do {                                                                                       \
+    (h)->launches++;                                                                         \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess) {                                                                \
+      bx_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return BX_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+static inline bool bx_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+static inline int bx_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline long long bx_min_ll(long long a, long long b) { return a < b ? a : b; }
+
+#ifdef __CUDACC__
+struct BoxCodec {
+  float m0, m1, m2, m3, s0, s1, s2, s3;
+  float max_x, max_y;  // W-1, H-1 (clip upper bounds)
+  int clip;
+};
+
+// utils/bbox_transform.py:32-55 followed by utils/bbox_tf.py:71-74, same fp32 op order.
+__device__ __forceinline__ float4 bx_decode_clip_one(const float4 a, const float4 t, const BoxCodec& k) {
+  const float dx = t.x * k.s0 + k.m0;
+  const float dy = t.y * k.s1 + k.m1;
+  const float dw = t.z * k.s2 + k.m2;
+  const float dh = t.w * k.s3 + k.m3;
+  float w = a.z - a.x + 1.0f;
+  float h = a.w - a.y + 1.0f;
+  float cx = a.x + 0.5f * w;
+  float cy = a.y + 0.5f * h;
+  cx = cx + dx * w;
+  cy = cy + dy * h;
+  w = w * expf(dw);
+  h = h * expf(dh);
+  float4 o;
+  o.x = cx - 0.5f * w;
+  o.y = cy - 0.5f * h;
+  o.z = o.x + w;
+  o.w = o.y + h;
+  if (k.clip) {
+    o.x = fmaxf(fminf(o.x, k.max_x), 0.0f);
+    o.y = fmaxf(fminf(o.y, k.max_y), 0.0f);
+    o.z = fmaxf(fminf(o.z, k.max_x), 0.0f);
+    o.w = fmaxf(fminf(o.w, k.max_y), 0.0f);
+  }
+  return o;
+}
+
+// utils/bbox_transform.py:4-29
+__device__ __forceinline__ float4 bx_encode_one(const float4 b, const float4 g, const BoxCodec& k) {
+  const float w = b.z - b.x + 1.0f, h = b.w - b.y + 1.0f;
+  const float cx = b.x + 0.5f * w, cy = b.y + 0.5f * h;
+  const float gw = g.z - g.x + 1.0f, gh = g.w - g.y + 1.0f;
+  const float gcx = g.x + 0.5f * gw, gcy = g.y + 0.5f * gh;
+  float4 d;
+  d.x = ((gcx - cx) / w - k.m0) / k.s0;
+  d.y = ((gcy - cy) / h - k.m1) / k.s1;
+  d.z = (logf(gw / w) - k.m2) / k.s2;
+  d.w = (logf(gh / h) - k.m3) / k.s3;
+  return d;
+}
+
+// utils/bbox_tf.py:7-56 for one pair ("+1" convention)
+__device__ __forceinline__ float bx_iou_plus1(const float4 a, const float area_a, const float4 b, const float area_b) {
+  const float ih = fmaxf(0.0f, fminf(a.w, b.w) - fmaxf(a.y, b.y) + 1.0f);
+  const float iw = fmaxf(0.0f, fminf(a.z, b.z) - fmaxf(a.x, b.x) + 1.0f);
+  const float inter = ih * iw;
+  const float uni = area_a + area_b - inter;
+  return inter == 0.0f ? 0.0f : inter / uni;
+}
+__device__ __forceinline__ float bx_area_plus1(const float4 a) { return (a.w - a.y + 1.0f) * (a.z - a.x + 1.0f); }
+
+// order-preserving map fp32 -> u32 (larger float -> larger key); 0 is reserved for "excluded"
+__device__ __forceinline__ uint32_t bx_score_key(float s) {
+  const uint32_t u = __float_as_uint(s);
+  const uint32_t k = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return k == 0u ? 1u : k;
+}
+#endif

@@ -1,0 +1,613 @@
+// Proposal stage: anchor decode + clip, candidate selection (adaptive radix select over 64-bit
+// (score,index) composites staged in shared memory), bitonic sort of the selected chunk, greedy IoU NMS with
+// 64-bit tile bitmasks and early exit at post_nms.  One CTA (1024 threads) per image; a batch is one launch.
+//
+// Replaces model/region_proposal.py:37-81 (RegionProposal.call): decode (utils/bbox_transform.py:32-55), clip
+// (utils/bbox_tf.py:59-78) and tf.image.non_max_suppression (TF r1.13 CPU kernel semantics).
+//
+// Why "lazy" chunks: greedy NMS visits candidates in descending score order and stops after post_nms keeps, so only a
+// prefix of the sorted order is ever needed.  Each round selects the next <= CHUNK best candidates (exact set, any
+// order), sorts just those, and sweeps them; with pre_nms_top_k = 0 (reference behaviour) rounds continue until the
+// quota is filled or every anchor was visited, so the result is identical to sorting all N.
+#include "bx_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr int kChunk = 2048;        // candidates sorted + swept per round
+constexpr int kBins = 2048;         // histogram bins per select level
+constexpr int kMaxPost = 2048;      // kept-box list capacity (post_nms limit)
+constexpr int kTile = 64;           // NMS tile: one 64-bit mask word
+constexpr int kKeyCacheMax = 24576; // keys cached in smem when n <= this (C4 600x1000: 21 546)
+
+struct ProposalArgs {
+  const float4* anchors;  // [n] (shared) — decode mode
+  const float4* deltas;   // [batch,n] — decode mode
+  const float4* boxes;    // [batch,n] precomputed boxes (bx_nms / min-size path); overrides decode when non-null
+  const float* scores;    // [batch,n]
+  const uint32_t* keys;   // [batch,n] precomputed keys (0 = excluded) or null -> derived from scores
+  int n;
+  BoxCodec codec;
+  int pre_nms_top_k;
+  int post_nms;
+  float thr;
+  float4* out_boxes;      // [batch,post_nms] or null
+  int* out_idx;           // [batch,post_nms]
+  int* out_count;         // [batch]
+  int cache_keys;         // 1: keys live in smem
+};
+
+__device__ __forceinline__ uint64_t composite(uint32_t key, uint32_t idx) {
+  return (static_cast<uint64_t>(key) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
+}
+
+// TF NonMaxSuppressionV3 IoU test on min/max-normalised corners (x=lo0,y=lo1,z=hi0,w=hi1).
+__device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const float4 b, const float thr) {
+  const float area_b = (b.z - b.x) * (b.w - b.y);
+  if (area_a <= 0.0f || area_b <= 0.0f) return false;
+  const float i0 = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.0f);
+  const float i1 = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.0f);
+  const float inter = i0 * i1;
+  if (inter <= 0.0f) return false;  // iou == 0, never > thr for thr in [0,1]
+  const float iou = inter / (area_a + area_b - inter);
+  return iou > thr;
+}
+
+__device__ __forceinline__ float4 normalise(const float4 b) {
+  return make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
+}
+
+struct Shared {
+  uint64_t lo, hi;        // current select range (inclusive)
+  uint64_t prev;          // exclusive upper bound: composites already consumed are >= prev
+  uint64_t thresh;        // selected threshold of this round
+  uint64_t sup;           // tile: candidates suppressed by the kept list
+  uint64_t keepmask;      // tile: candidates kept
+  uint32_t kmin, kmax;    // key range of the image
+  int n_valid;            // keys > 0
+  int cand_count;
+  int kept;
+  int state;
+  int shift;
+  int found_bin;
+  int suffix_count;
+};
+
+template <bool kCache>
+__device__ __forceinline__ uint32_t load_key(const ProposalArgs& a, const uint32_t* skeys, const float* scores,
+                                             const uint32_t* gkeys, int i) {
+  if (kCache) return skeys[i];
+  if (gkeys) return gkeys[i];
+  return bx_score_key(scores[i] + 0.0f);
+}
+
+template <bool kCache>
+__global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // carve-up (all 16B aligned)
+  float4* cand_box = reinterpret_cast<float4*>(smem_raw);                           // kChunk
+  float4* kept_box = cand_box + kChunk;                                             // kMaxPost
+  uint64_t* cand_key = reinterpret_cast<uint64_t*>(kept_box + kMaxPost);            // kChunk
+  uint64_t* rowmask = cand_key + kChunk;                                            // kTile
+  uint32_t* hist = reinterpret_cast<uint32_t*>(rowmask + kTile);                    // kBins
+  uint32_t* red = hist + kBins;                                                     // 64 (block reductions)
+  Shared* sh = reinterpret_cast<Shared*>(red + 64);
+  uint32_t* skeys = reinterpret_cast<uint32_t*>(sh + 1);                            // n (when cached)
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int img = blockIdx.x;
+  const int n = a.n;
+  const float* scores = a.scores ? a.scores + static_cast<size_t>(img) * n : nullptr;
+  const uint32_t* gkeys = a.keys ? a.keys + static_cast<size_t>(img) * n : nullptr;
+  const float4* deltas = a.deltas ? a.deltas + static_cast<size_t>(img) * n : nullptr;
+  const float4* boxes = a.boxes ? a.boxes + static_cast<size_t>(img) * n : nullptr;
+  float4* out_boxes = a.out_boxes ? a.out_boxes + static_cast<size_t>(img) * a.post_nms : nullptr;
+  int* out_idx = a.out_idx + static_cast<size_t>(img) * a.post_nms;
+
+  // ---- pass 0: keys -> smem (if cached), min / max / count of valid keys
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+  int nvalid = 0;
+  for (int i = tid; i < n; i += kThreads) {
+    const uint32_t k = gkeys ? gkeys[i] : bx_score_key(scores[i] + 0.0f);
+    if (kCache) skeys[i] = k;
+    if (k) {
+      kmin = min(kmin, k);
+      kmax = max(kmax, k);
+      ++nvalid;
+    }
+  }
+  kmin = __reduce_min_sync(0xFFFFFFFFu, kmin);
+  kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
+  nvalid = __reduce_add_sync(0xFFFFFFFFu, nvalid);
+  if (lane == 0) {
+    red[warp] = kmin;
+    red[32 + warp] = kmax;
+    hist[warp] = nvalid;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t mn = __reduce_min_sync(0xFFFFFFFFu, red[lane]);
+    uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, red[32 + lane]);
+    int nv = __reduce_add_sync(0xFFFFFFFFu, static_cast<int>(hist[lane]));
+    if (lane == 0) {
+      sh->kmin = mn;
+      sh->kmax = mx;
+      sh->n_valid = nv;
+      sh->prev = 0xFFFFFFFFFFFFFFFFull;
+      sh->kept = 0;
+    }
+  }
+  __syncthreads();
+
+  const int n_valid = sh->n_valid;
+  const int limit = (a.pre_nms_top_k > 0) ? min(a.pre_nms_top_k, n_valid) : n_valid;
+  const uint64_t global_lo = static_cast<uint64_t>(sh->kmin) << 32;
+  int consumed = 0;
+
+  while (consumed < limit && sh->kept < a.post_nms) {
+    const int want = min(kChunk, limit - consumed);
+    const uint64_t prev = sh->prev;
+
+    // ---- select: threshold T with  #{v : T <= v < prev} in [1, want]  (as large as the bins allow)
+    if (tid == 0) {
+      sh->lo = global_lo;
+      sh->hi = prev - 1;   // prev > global_lo while consumed < limit
+      if (prev == 0xFFFFFFFFFFFFFFFFull) sh->hi = (static_cast<uint64_t>(sh->kmax) << 32) | 0xFFFFFFFFull;
+    }
+    __syncthreads();
+    int above = 0;  // elements already known to be >= the upper edge of the current range (all selected)
+    for (;;) {
+      const uint64_t lo = sh->lo, hi = sh->hi;
+      const uint64_t span = hi - lo;  // inclusive span - 1
+      int shift = 0;
+      while ((span >> shift) >= static_cast<uint64_t>(kBins)) ++shift;
+      for (int i = tid; i < kBins; i += kThreads) hist[i] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += kThreads) {
+        const uint32_t k = load_key<kCache>(a, skeys, scores, gkeys, i);
+        if (!k) continue;
+        const uint64_t v = composite(k, static_cast<uint32_t>(i));
+        if (v >= lo && v <= hi) atomicAdd(&hist[static_cast<uint32_t>((v - lo) >> shift)], 1u);
+      }
+      __syncthreads();
+      // suffix scan from the top bin: largest suffix whose count (+above) <= want
+      if (warp == 0) {
+        // each lane owns kBins/32 consecutive bins, highest lane = highest bins
+        constexpr int per = kBins / 32;
+        uint32_t mine = 0;
+        for (int j = 0; j < per; ++j) mine += hist[lane * per + j];
+        // inclusive suffix sum over lanes (lane 31 first)
+        uint32_t suf = mine;
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_down_sync(0xFFFFFFFFu, suf, d);
+          if (lane + d < 32) suf += o;
+        }
+        const uint32_t higher = suf - mine;  // count in lanes above
+        // walk own bins from the top
+        int fit_bin = -1;         // lowest bin index such that suffix(bin..top)+above <= want
+        int over_bin = -1;        // first (highest) bin where the running count exceeds want
+        uint32_t run = higher + above;
+        uint32_t fit_count = 0;
+        if (run <= static_cast<uint32_t>(want)) {
+          for (int j = per - 1; j >= 0; --j) {
+            const uint32_t c = hist[lane * per + j];
+            if (run + c <= static_cast<uint32_t>(want)) {
+              run += c;
+              fit_bin = lane * per + j;
+              fit_count = run;
+            } else {
+              over_bin = lane * per + j;
+              break;
+            }
+          }
+        }
+        // the crossing happens in exactly one lane: the highest lane with over_bin >= 0 ... or nowhere (all fit)
+        const uint32_t has_over = __ballot_sync(0xFFFFFFFFu, over_bin >= 0);
+        if (has_over == 0u) {
+          // everything in [lo,hi] fits
+          if (lane == 0) {
+            sh->thresh = lo;
+            sh->state = 1;
+          }
+        } else {
+          const int src = 31 - __clz(has_over);
+          const int ob = __shfl_sync(0xFFFFFFFFu, over_bin, src);
+          // count of the suffix strictly above bin `ob` (+above): take it from the crossing lane's walk
+          uint32_t cnt_above = __shfl_sync(0xFFFFFFFFu, run, src);
+          if (lane == 0) {
+            if (cnt_above > 0) {
+              // a non-empty suffix fits: T = lower edge of bin ob+1
+              sh->thresh = lo + (static_cast<uint64_t>(ob + 1) << shift);
+              sh->state = 1;
+            } else {
+              // the top non-empty bin alone holds more than `want`: refine inside it
+              const uint64_t nlo = lo + (static_cast<uint64_t>(ob) << shift);
+              uint64_t nhi = nlo + ((1ull << shift) - 1ull);
+              if (nhi > hi) nhi = hi;
+              sh->lo = nlo;
+              sh->hi = nhi;
+              sh->state = 0;
+            }
+          }
+        }
+        (void)fit_bin;
+        (void)fit_count;
+      }
+      __syncthreads();
+      if (sh->state == 1) break;
+      // state 0 with shift == 0 cannot happen: a bin of width 1 holds exactly one composite (<= want since want >= 1)
+    }
+    const uint64_t T = sh->thresh;
+
+    // ---- compaction of {T <= v < prev} into cand_key (any order), then pad to a power of two
+    if (tid == 0) sh->cand_count = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += kThreads) {
+      const int i = base + tid;
+      uint64_t v = 0;
+      bool take = false;
+      if (i < n) {
+        const uint32_t k = load_key<kCache>(a, skeys, scores, gkeys, i);
+        if (k) {
+          v = composite(k, static_cast<uint32_t>(i));
+          take = (v >= T) && (v < prev);
+        }
+      }
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, take);
+      if (m) {
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(&sh->cand_count, __popc(m));
+        pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+        if (take) cand_key[pos + __popc(m & ((1u << lane) - 1u))] = v;
+      }
+    }
+    __syncthreads();
+    const int cnt = sh->cand_count;  // 1..want
+    int pow2 = 64;
+    while (pow2 < cnt) pow2 <<= 1;
+    for (int i = cnt + tid; i < pow2; i += kThreads) cand_key[i] = 0ull;
+    __syncthreads();
+
+    // ---- bitonic sort, descending
+    for (int k = 2; k <= pow2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < (pow2 >> 1); t += kThreads) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+          const int p = i | j;
+          const uint64_t x = cand_key[i], y = cand_key[p];
+          const bool desc = ((i & k) == 0);
+          if ((x < y) == desc) {
+            cand_key[i] = y;
+            cand_key[p] = x;
+          }
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---- decode + clip (or gather) the candidates' boxes, normalised corners for the IoU test
+    for (int i = tid; i < cnt; i += kThreads) {
+      const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(cand_key[i] & 0xFFFFFFFFull);
+      float4 b;
+      if (boxes) b = boxes[idx];
+      else b = bx_decode_clip_one(a.anchors[idx], deltas[idx], a.codec);
+      cand_box[i] = b;  // original orientation (written to out_boxes); normalised on load below
+    }
+    __syncthreads();
+
+    // ---- greedy sweep in tiles of 64
+    for (int t0 = 0; t0 < cnt && sh->kept < a.post_nms; t0 += kTile) {
+      const int tn = min(kTile, cnt - t0);
+      const int kept = sh->kept;
+      if (tid == 0) sh->sup = 0ull;
+      __syncthreads();
+      {
+        // (1) tile candidates vs kept list: candidate c = tid & 63, kept subset j = tid>>6 (mod 16)
+        const int c = tid & 63;
+        bool s = false;
+        if (c < tn) {
+          const float4 cb = normalise(cand_box[t0 + c]);
+          const float ca = (cb.z - cb.x) * (cb.w - cb.y);
+          for (int j = tid >> 6; j < kept && !s; j += 16) s = iou_gt(cb, ca, kept_box[j], a.thr);
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, s);
+        if (lane == 0 && m) atomicOr(reinterpret_cast<unsigned long long*>(&sh->sup),
+                                     static_cast<unsigned long long>(m) << ((warp & 1) * 32));
+        // (2) intra-tile masks: row i = tid>>4, columns part*4 .. part*4+3 ; bit j set iff j > i and IoU(i,j) > thr
+        const int i = tid >> 4, part = tid & 15;
+        uint64_t bits = 0ull;
+        if (i < tn) {
+          const float4 ib = normalise(cand_box[t0 + i]);
+          const float ia = (ib.z - ib.x) * (ib.w - ib.y);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = part * 4 + q;
+            if (j > i && j < tn) {
+              if (iou_gt(ib, ia, normalise(cand_box[t0 + j]), a.thr)) bits |= (1ull << j);
+            }
+          }
+        }
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, d);
+        if (part == 0) rowmask[i] = bits;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint64_t removed = sh->sup;
+        uint64_t keep = 0ull;
+        int room = a.post_nms - kept;
+        for (int i = 0; i < tn && room > 0; ++i) {
+          if (!((removed >> i) & 1ull)) {
+            keep |= (1ull << i);
+            removed |= rowmask[i];
+            --room;
+          }
+        }
+        sh->keepmask = keep;
+        sh->kept = kept + __popcll(keep);
+      }
+      __syncthreads();
+      if (tid < tn) {
+        const uint64_t keep = sh->keepmask;
+        if ((keep >> tid) & 1ull) {
+          const int pos = kept + __popcll(keep & ((1ull << tid) - 1ull));
+          const float4 b = cand_box[t0 + tid];
+          kept_box[pos] = normalise(b);
+          out_idx[pos] = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(cand_key[t0 + tid] & 0xFFFFFFFFull));
+          if (out_boxes) out_boxes[pos] = b;
+        }
+      }
+      __syncthreads();
+    }
+
+    consumed += cnt;
+    if (tid == 0) sh->prev = T;
+    __syncthreads();
+  }
+
+  // ---- pad the tail, publish the count
+  const int kept = sh->kept;
+  for (int i = kept + tid; i < a.post_nms; i += kThreads) {
+    out_idx[i] = -1;
+    if (out_boxes) out_boxes[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (tid == 0) a.out_count[img] = kept;
+}
+
+size_t proposals_smem_bytes(int n, bool cache) {
+  size_t b = sizeof(float4) * (kChunk + kMaxPost) + sizeof(uint64_t) * (kChunk + kTile) +
+             sizeof(uint32_t) * (kBins + 64) + sizeof(Shared);
+  if (cache) b += sizeof(uint32_t) * static_cast<size_t>(n);
+  return (b + 15) & ~static_cast<size_t>(15);
+}
+
+int launch_proposals(bx_handle* h, ProposalArgs& a, int batch, cudaStream_t st) {
+  const bool cache = a.n <= kKeyCacheMax;
+  a.cache_keys = cache ? 1 : 0;
+  const size_t smem = proposals_smem_bytes(a.n, cache);
+  BX_REQUIRE(smem <= h->smem_optin, BX_ERR_UNSUPPORTED, "proposals: %zu B shared memory > device limit %zu", smem,
+             h->smem_optin);
+  if (cache) {
+    BX_CUDA(cudaFuncSetAttribute(proposals_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    proposals_kernel<true><<<batch, kThreads, smem, st>>>(a);
+  } else {
+    BX_CUDA(cudaFuncSetAttribute(proposals_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    proposals_kernel<false><<<batch, kThreads, smem, st>>>(a);
+  }
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}
+
+// ------------------------------------------------------------------ elementwise helpers
+__global__ void __launch_bounds__(256) decode_clip_kernel(const float4* __restrict__ anchors, int anchors_batched,
+                                                          const float4* __restrict__ deltas, int batch, int n,
+                                                          BoxCodec codec, float4* __restrict__ out) {
+  const long long total = static_cast<long long>(batch) * n;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int j = static_cast<int>(i % n);
+    const float4 a = anchors_batched ? anchors[i] : anchors[j];
+    out[i] = bx_decode_clip_one(a, deltas[i], codec);
+  }
+}
+
+// decode + clip + min-size key masking for the min_size > 0 path (boxes kept for the later gather)
+__global__ void __launch_bounds__(256) decode_filter_keys_kernel(const float4* __restrict__ anchors,
+                                                                 const float4* __restrict__ deltas,
+                                                                 const float* __restrict__ scores, int batch, int n,
+                                                                 BoxCodec codec, float min_size,
+                                                                 float4* __restrict__ boxes,
+                                                                 uint32_t* __restrict__ keys) {
+  const long long total = static_cast<long long>(batch) * n;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const float4 b = bx_decode_clip_one(anchors[i % n], deltas[i], codec);
+    boxes[i] = b;
+    const bool ok = ((b.z - b.x + 1.0f) >= min_size) && ((b.w - b.y + 1.0f) >= min_size);  // utils/bbox_tf.py:80-83
+    keys[i] = ok ? bx_score_key(scores[i] + 0.0f) : 0u;
+  }
+}
+
+__global__ void __launch_bounds__(256) encode_kernel(const float4* __restrict__ src, const float4* __restrict__ dst,
+                                                     int n, BoxCodec codec, float4* __restrict__ out) {
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += 256 * gridDim.x) out[i] = bx_encode_one(src[i], dst[i], codec);
+}
+
+// single-CTA ordered compaction (clip + min-edge filter, or inside-image filter); n is small on these call sites
+__global__ void __launch_bounds__(1024) filter_compact_kernel(const float4* __restrict__ in, int n, int mode,
+                                                              float lo, float max_x, float max_y, float min_edge,
+                                                              float4* __restrict__ out_boxes, int* __restrict__ out_idx,
+                                                              int* __restrict__ out_count) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) base_s = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < n; b0 += 1024) {
+    const int i = b0 + tid;
+    bool keep = false;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (i < n) {
+      v = in[i];
+      if (mode == 0) {  // bboxes_clip_filter with min_edge
+        v.x = fmaxf(fminf(v.x, max_x), lo);
+        v.y = fmaxf(fminf(v.y, max_y), lo);
+        v.z = fmaxf(fminf(v.z, max_x), lo);
+        v.w = fmaxf(fminf(v.w, max_y), lo);
+        keep = ((v.z - v.x + 1.0f) >= min_edge) && ((v.w - v.y + 1.0f) >= min_edge);
+      } else {          // bboxes_range_filter
+        keep = (v.x >= 0.0f) && (v.y >= 0.0f) && (v.z <= max_x) && (v.w <= max_y);
+      }
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int c = warp_tot[w];
+      if (w < warp) off += c;
+      tot += c;
+    }
+    const int base = base_s;
+    if (keep) {
+      const int pos = base + off + __popc(m & ((1u << lane) - 1u));
+      if (out_boxes) out_boxes[pos] = v;
+      out_idx[pos] = i;
+    }
+    __syncthreads();
+    if (tid == 0) base_s = base + tot;
+    __syncthreads();
+  }
+  if (tid == 0) *out_count = base_s;
+}
+
+BoxCodec make_codec(const float means[4], const float stds[4], int image_h, int image_w) {
+  BoxCodec k;
+  k.m0 = means[0]; k.m1 = means[1]; k.m2 = means[2]; k.m3 = means[3];
+  k.s0 = stds[0]; k.s1 = stds[1]; k.s2 = stds[2]; k.s3 = stds[3];
+  k.clip = (image_h > 0 && image_w > 0) ? 1 : 0;
+  k.max_x = static_cast<float>(image_w - 1);
+  k.max_y = static_cast<float>(image_h - 1);
+  return k;
+}
+
+}  // namespace
+
+extern "C" int bx_decode_clip(bx_handle* h, const float* anchors, int anchors_batched, const float* deltas,
+                              int batch, int n, const float means[4], const float stds[4], int image_h, int image_w,
+                              float* out_boxes, void* stream) {
+  BX_REQUIRE(h && anchors && deltas && out_boxes && means && stds, BX_ERR_INVALID, "bx_decode_clip: NULL argument");
+  BX_REQUIRE(batch >= 0 && n >= 0, BX_ERR_INVALID, "bx_decode_clip: negative size");
+  BX_REQUIRE(bx_aligned(anchors, 16) && bx_aligned(deltas, 16) && bx_aligned(out_boxes, 16), BX_ERR_INVALID,
+             "bx_decode_clip: box tensors must be 16-byte aligned");
+  if (batch == 0 || n == 0) return BX_OK;
+  const long long total = static_cast<long long>(batch) * n;
+  const int grid = static_cast<int>(bx_min_ll(bx_div_up(total, 256), 8ll * h->num_sms));
+  decode_clip_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(anchors), anchors_batched, reinterpret_cast<const float4*>(deltas), batch, n,
+      make_codec(means, stds, image_h, image_w), reinterpret_cast<float4*>(out_boxes));
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}
+
+extern "C" int bx_encode(bx_handle* h, const float* src, const float* dst, int n, const float means[4],
+                         const float stds[4], float* out, void* stream) {
+  BX_REQUIRE(h && src && dst && out && means && stds, BX_ERR_INVALID, "bx_encode: NULL argument");
+  BX_REQUIRE(bx_aligned(src, 16) && bx_aligned(dst, 16) && bx_aligned(out, 16), BX_ERR_INVALID,
+             "bx_encode: box tensors must be 16-byte aligned");
+  if (n <= 0) return BX_OK;
+  encode_kernel<<<min(bx_div_up(n, 256), 8 * h->num_sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(src), reinterpret_cast<const float4*>(dst), n, make_codec(means, stds, 0, 0),
+      reinterpret_cast<float4*>(out));
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}
+
+extern "C" int bx_clip_filter(bx_handle* h, const float* boxes, int n, float min_value, int image_h, int image_w,
+                              float min_edge, float* out_boxes, int* out_idx, int* out_count, void* stream) {
+  BX_REQUIRE(h && boxes && out_boxes && out_idx && out_count, BX_ERR_INVALID, "bx_clip_filter: NULL argument");
+  BX_REQUIRE(n >= 0, BX_ERR_INVALID, "bx_clip_filter: negative size");
+  BX_REQUIRE(bx_aligned(boxes, 16) && bx_aligned(out_boxes, 16), BX_ERR_INVALID, "bx_clip_filter: alignment");
+  filter_compact_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(boxes), n, 0, min_value, static_cast<float>(image_w - 1),
+      static_cast<float>(image_h - 1), min_edge, reinterpret_cast<float4*>(out_boxes), out_idx, out_count);
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}
+
+extern "C" int bx_range_filter(bx_handle* h, const float* anchors, int n, int image_h, int image_w, int* out_idx,
+                               int* out_count, void* stream) {
+  BX_REQUIRE(h && anchors && out_idx && out_count, BX_ERR_INVALID, "bx_range_filter: NULL argument");
+  BX_REQUIRE(n >= 0 && bx_aligned(anchors, 16), BX_ERR_INVALID, "bx_range_filter: bad size/alignment");
+  filter_compact_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(anchors), n, 1, 0.0f, static_cast<float>(image_w - 1),
+      static_cast<float>(image_h - 1), 0.0f, nullptr, out_idx, out_count);
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}
+
+extern "C" int bx_nms(bx_handle* h, const float* boxes, const float* scores, int batch, int n, int max_out,
+                      float iou_threshold, int* out_idx, int* out_count, void* stream) {
+  BX_REQUIRE(h && boxes && scores && out_idx && out_count, BX_ERR_INVALID, "bx_nms: NULL argument");
+  BX_REQUIRE(batch >= 0 && n >= 0 && max_out >= 0, BX_ERR_INVALID, "bx_nms: negative size");
+  BX_REQUIRE(iou_threshold >= 0.0f && iou_threshold <= 1.0f, BX_ERR_INVALID,
+             "bx_nms: iou_threshold must be in [0, 1]");  // TF: InvalidArgument
+  BX_REQUIRE(max_out <= kMaxPost, BX_ERR_UNSUPPORTED, "bx_nms: max_output_size %d > %d", max_out, kMaxPost);
+  BX_REQUIRE(n < (1 << 22), BX_ERR_UNSUPPORTED, "bx_nms: n must be < 2^22");
+  BX_REQUIRE(bx_aligned(boxes, 16), BX_ERR_INVALID, "bx_nms: boxes must be 16-byte aligned");
+  if (batch == 0) return BX_OK;
+  ProposalArgs a = {};
+  a.boxes = reinterpret_cast<const float4*>(boxes);
+  a.scores = scores;
+  a.n = n;
+  a.post_nms = max_out;
+  a.thr = iou_threshold;
+  a.out_idx = out_idx;
+  a.out_count = out_count;
+  return launch_proposals(h, a, batch, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bx_proposals(bx_handle* h, const float* anchors, const float* deltas, const float* scores, int batch,
+                            int n, const bx_proposal_params* p, float* out_boxes, int* out_idx, int* out_count,
+                            void* stream) {
+  BX_REQUIRE(h && anchors && deltas && scores && p && out_boxes && out_idx && out_count, BX_ERR_INVALID,
+             "bx_proposals: NULL argument");
+  BX_REQUIRE(batch >= 0 && n >= 0, BX_ERR_INVALID, "bx_proposals: negative size");
+  BX_REQUIRE(p->iou_threshold >= 0.0f && p->iou_threshold <= 1.0f, BX_ERR_INVALID,
+             "bx_proposals: iou_threshold must be in [0, 1]");
+  BX_REQUIRE(p->post_nms >= 0 && p->post_nms <= kMaxPost, BX_ERR_UNSUPPORTED, "bx_proposals: post_nms %d not in [0, %d]",
+             p->post_nms, kMaxPost);
+  BX_REQUIRE(p->image_h > 0 && p->image_w > 0, BX_ERR_INVALID, "bx_proposals: image shape must be positive");
+  BX_REQUIRE(n < (1 << 22), BX_ERR_UNSUPPORTED, "bx_proposals: n must be < 2^22");
+  BX_REQUIRE(bx_aligned(anchors, 16) && bx_aligned(deltas, 16) && bx_aligned(out_boxes, 16), BX_ERR_INVALID,
+             "bx_proposals: box tensors must be 16-byte aligned");
+  if (batch == 0) return BX_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProposalArgs a = {};
+  a.anchors = reinterpret_cast<const float4*>(anchors);
+  a.deltas = reinterpret_cast<const float4*>(deltas);
+  a.scores = scores;
+  a.n = n;
+  a.codec = make_codec(p->means, p->stds, p->image_h, p->image_w);
+  a.pre_nms_top_k = p->pre_nms_top_k;
+  a.post_nms = p->post_nms;
+  a.thr = p->iou_threshold;
+  a.out_boxes = reinterpret_cast<float4*>(out_boxes);
+  a.out_idx = out_idx;
+  a.out_count = out_count;
+  if (p->min_size > 0.0f) {
+    // filter -> top-k -> NMS: decode everything once, mask the keys of undersized boxes
+    const size_t total = static_cast<size_t>(batch) * n;
+    int rc = bx_ws_reserve(h, total * (sizeof(float4) + sizeof(uint32_t)));
+    if (rc) return rc;
+    float4* wboxes = reinterpret_cast<float4*>(h->ws);
+    uint32_t* wkeys = reinterpret_cast<uint32_t*>(wboxes + total);
+    const int grid = static_cast<int>(bx_min_ll(bx_div_up((long long)total, 256), 8ll * h->num_sms));
+    decode_filter_keys_kernel<<<grid, 256, 0, st>>>(a.anchors, a.deltas, scores, batch, n, a.codec, p->min_size,
+                                                    wboxes, wkeys);
+    BX_LAUNCH_CHECK(h);
+    a.boxes = wboxes;
+    a.keys = wkeys;
+  }
+  return launch_proposals(h, a, batch, st);
+}

@@ -1,0 +1,383 @@
+// RoI feature extraction: tf.image.crop_and_resize (bilinear, extrapolation 0) fused with the 2x2 max / avg pool and
+// with FPN level routing.  Replaces model/roi_pooling.py:8-42 (RoiPoolingCropAndResize2), :45-90
+// (RoiPoolingCropAndResize), :93-176 (crop_and_resize(pad_border)/roi_align/RoiPoolingRoiAlign) and
+// model/fpn/base_fpn_model.py:152-161,303-324 (_get_roi_features, _assign_levels).
+//
+// Layout: features NHWC fp32, so the channel axis is the coalesced / float4 axis; one CTA produces one output row
+// (roi, py): P pixels x C channels, written once, contiguous.  Sample coordinates follow the TF r1.13 kernel's fp32
+// op order: in_y = y1*(h-1) + y*((y2-y1)*(h-1)/(Q-1)); a sample outside [0,h-1]x[0,w-1] is 0.
+#include "bx_common.cuh"
+
+namespace {
+
+constexpr int kMaxLevels = 8;
+constexpr int kMaxQ = 64;  // max crop size (2*pool_size)
+
+struct LevelFeat {
+  const float* feat;  // [b,fh,fw,c]
+  int fh, fw;
+};
+
+struct RoiArgs {
+  LevelFeat lv[kMaxLevels];
+  int n_levels;
+  const float4* rois;     // [r] image coordinates (or normalised y1,x1,y2,x2 for mode RAW)
+  const int* box_ind;     // [r] or null
+  const int* roi_counts;  // [b] or null
+  const int* order;       // [r] output row j reads roi order[j] (FPN level-major) or null (identity)
+  const int* level;       // [r] absolute level per roi or null (level 0)
+  int level_base;         // min_level: level[src] - level_base indexes lv[]
+  int r, b, c;
+  int rois_per_image;     // r / b when roi_counts is given
+  int mode;               // bx_roi_mode or 3 = RAW normalised boxes
+  int P;                  // output size
+  int Q;                  // crop size (P or 2P)
+  float stride;
+  float image_h, image_w;
+  float extrapolation;
+  float* out;             // [r,P,P,c]
+};
+
+struct Axis {
+  int lo, hi;   // tap indices (already mapped to the un-padded map)
+  float lerp;
+  int valid;
+};
+
+// coordinate of crop sample `s` along one axis, TF op order.  n1,n2: normalised box ends; dim: (padded) map size.
+__device__ __forceinline__ Axis sample_axis(float n1, float n2, int s, int Q, int dim, int pad) {
+  Axis a;
+  const float dm1 = static_cast<float>(dim - 1);
+  float in;
+  if (Q > 1) {
+    const float scale = (n2 - n1) * dm1 / static_cast<float>(Q - 1);
+    in = n1 * dm1 + static_cast<float>(s) * scale;
+  } else {
+    in = 0.5f * (n1 + n2) * dm1;
+  }
+  a.valid = !(in < 0.0f || in > dm1);
+  const float lo = floorf(in), hi = ceilf(in);
+  a.lerp = in - lo;
+  int ilo = static_cast<int>(lo), ihi = static_cast<int>(hi);
+  if (pad) {  // SYMMETRIC pad by 1 (roi_pooling.py:100): padded index p -> original clamp(p-1, 0, dim-3)
+    ilo = min(max(ilo - 1, 0), dim - 3);
+    ihi = min(max(ihi - 1, 0), dim - 3);
+  }
+  a.lo = ilo;
+  a.hi = ihi;
+  return a;
+}
+
+template <int POOL, typename VecT>
+__global__ void __launch_bounds__(256) roi_pool_kernel(const RoiArgs a) {
+  constexpr int S = (POOL == BX_POOL_NONE) ? 1 : 2;  // crop samples per output pixel per axis
+  constexpr int V = sizeof(VecT) / sizeof(float);
+  __shared__ Axis ax_y[2];
+  __shared__ Axis ax_x[kMaxQ];
+  __shared__ int s_meta[4];  // image index, level, zero-fill flag
+
+  const int P = a.P, Q = a.Q;
+  const int j = blockIdx.x / P;   // output roi row
+  const int py = blockIdx.x % P;
+  const int tid = threadIdx.x;
+  const int cv = a.c / V;
+  VecT* out_row = reinterpret_cast<VecT*>(a.out + (static_cast<size_t>(j) * P + py) * P * a.c);
+
+  if (tid < Q + 2) {
+    const int src = a.order ? a.order[j] : j;
+    const int lvl = a.level ? a.level[src] - a.level_base : 0;
+    int img = a.box_ind ? a.box_ind[src] : 0;
+    int zero = 0;
+    if (a.roi_counts) {
+      img = src / a.rois_per_image;
+      zero = (src % a.rois_per_image) >= a.roi_counts[img];
+    }
+    if (tid == 0) {
+      s_meta[0] = img;
+      s_meta[1] = lvl;
+      s_meta[2] = zero || img < 0 || img >= a.b;
+    }
+    const float4 roi = a.rois[src];
+    const int fh = a.lv[lvl].fh, fw = a.lv[lvl].fw;
+    float y1n, x1n, y2n, x2n;
+    int dimy = fh, dimx = fw, pad = 0;
+    if (a.mode == BX_ROI_STRIDE_NORM) {           // roi_pooling.py:64-74
+      const float fy = static_cast<float>(fh - 1), fx = static_cast<float>(fw - 1);
+      y1n = (roi.y / a.stride) / fy;
+      x1n = (roi.x / a.stride) / fx;
+      y2n = (roi.w / a.stride) / fy;
+      x2n = (roi.z / a.stride) / fx;
+    } else if (a.mode == BX_ROI_IMAGE_NORM) {     // roi_pooling.py:26-35
+      y1n = roi.y / a.image_h;
+      x1n = roi.x / a.image_w;
+      y2n = roi.w / a.image_h;
+      x2n = roi.z / a.image_w;
+    } else if (a.mode == BX_ROI_ALIGN_PAD) {      // roi_pooling.py:175,101,103-130
+      pad = 1;
+      dimy = fh + 2;
+      dimx = fw + 2;
+      const float x0 = roi.x / a.stride + 1.0f, y0 = roi.y / a.stride + 1.0f;
+      const float x1 = roi.z / a.stride + 1.0f, y1 = roi.w / a.stride + 1.0f;
+      const float qf = static_cast<float>(Q);
+      const float sw = (x1 - x0) / qf, sh = (y1 - y0) / qf;
+      const float ih = static_cast<float>(dimy - 1), iw = static_cast<float>(dimx - 1);
+      x1n = (x0 + sw / 2.0f - 0.5f) / iw;
+      y1n = (y0 + sh / 2.0f - 0.5f) / ih;
+      const float nw = sw * static_cast<float>(Q - 1) / iw;
+      const float nh = sh * static_cast<float>(Q - 1) / ih;
+      x2n = x1n + nw;
+      y2n = y1n + nh;
+    } else {                                      // RAW: boxes are (y1,x1,y2,x2) normalised
+      y1n = roi.x; x1n = roi.y; y2n = roi.z; x2n = roi.w;
+    }
+    if (tid < Q) ax_x[tid] = sample_axis(x1n, x2n, tid, Q, dimx, pad);
+    else if (tid - Q < S) ax_y[tid - Q] = sample_axis(y1n, y2n, py * S + (tid - Q), Q, dimy, pad);
+  }
+  __syncthreads();
+
+  const int items = P * cv;
+  if (s_meta[2]) {
+    VecT z;
+    float* zp = reinterpret_cast<float*>(&z);
+#pragma unroll
+    for (int v = 0; v < V; ++v) zp[v] = 0.0f;
+    for (int it = tid; it < items; it += 256) out_row[it] = z;
+    return;
+  }
+  const LevelFeat lf = a.lv[s_meta[1]];
+  const VecT* feat = reinterpret_cast<const VecT*>(lf.feat + static_cast<size_t>(s_meta[0]) * lf.fh * lf.fw * a.c);
+  const float ext = a.extrapolation;
+
+  for (int it = tid; it < items; it += 256) {
+    const int px = it / cv, cg = it % cv;
+    float acc[V];
+#pragma unroll
+    for (int sy = 0; sy < S; ++sy) {
+      const Axis ay = ax_y[sy];
+#pragma unroll
+      for (int sx = 0; sx < S; ++sx) {
+        const Axis axx = ax_x[px * S + sx];
+        float val[V];
+        if (ay.valid && axx.valid) {
+          const VecT tl = __ldg(feat + (static_cast<size_t>(ay.lo) * lf.fw + axx.lo) * cv + cg);
+          const VecT tr = __ldg(feat + (static_cast<size_t>(ay.lo) * lf.fw + axx.hi) * cv + cg);
+          const VecT bl = __ldg(feat + (static_cast<size_t>(ay.hi) * lf.fw + axx.lo) * cv + cg);
+          const VecT br = __ldg(feat + (static_cast<size_t>(ay.hi) * lf.fw + axx.hi) * cv + cg);
+          const float* ptl = reinterpret_cast<const float*>(&tl);
+          const float* ptr = reinterpret_cast<const float*>(&tr);
+          const float* pbl = reinterpret_cast<const float*>(&bl);
+          const float* pbr = reinterpret_cast<const float*>(&br);
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float top = ptl[v] + (ptr[v] - ptl[v]) * axx.lerp;
+            const float bot = pbl[v] + (pbr[v] - pbl[v]) * axx.lerp;
+            val[v] = top + (bot - top) * ay.lerp;
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) val[v] = ext;
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          if (sy == 0 && sx == 0) acc[v] = val[v];
+          else if (POOL == BX_POOL_MAX2) acc[v] = fmaxf(acc[v], val[v]);
+          else acc[v] = acc[v] + val[v];  // AVG2: ((s00+s01)+s10)+s11
+        }
+      }
+    }
+    VecT o;
+    float* po = reinterpret_cast<float*>(&o);
+#pragma unroll
+    for (int v = 0; v < V; ++v) po[v] = (POOL == BX_POOL_AVG2) ? acc[v] / 4.0f : acc[v];
+    out_row[it] = o;
+  }
+}
+
+template <typename VecT>
+int launch_roi_v(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
+  const int grid = a.r * a.P;
+  if (pool == BX_POOL_NONE) roi_pool_kernel<BX_POOL_NONE, VecT><<<grid, 256, 0, st>>>(a);
+  else if (pool == BX_POOL_MAX2) roi_pool_kernel<BX_POOL_MAX2, VecT><<<grid, 256, 0, st>>>(a);
+  else roi_pool_kernel<BX_POOL_AVG2, VecT><<<grid, 256, 0, st>>>(a);
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}
+
+int launch_roi(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
+  if (a.r == 0) return BX_OK;
+  bool vec = (a.c % 4 == 0) && bx_aligned(a.out, 16);
+  for (int l = 0; l < a.n_levels; ++l) vec = vec && bx_aligned(a.lv[l].feat, 16);
+  return vec ? launch_roi_v<float4>(h, a, pool, st) : launch_roi_v<float>(h, a, pool, st);
+}
+
+// ---- FPN level assignment (base_fpn_model.py:303-324): single CTA, stable level-major order
+__device__ __forceinline__ int roi_level(const float4 roi, int min_level, int max_level) {
+  const float hh = fmaxf(0.0f, roi.w - roi.y);
+  const float ww = fmaxf(0.0f, roi.z - roi.x);
+  float lv = floorf(4.0f + logf(sqrtf(ww * hh + 1e-8f) / 224.0f) / logf(2.0f));
+  lv = fmaxf(lv, static_cast<float>(min_level));
+  lv = fminf(lv, static_cast<float>(max_level));
+  return static_cast<int>(lv) - min_level;
+}
+
+__global__ void __launch_bounds__(1024) assign_levels_kernel(const float4* __restrict__ rois, int r, int min_level,
+                                                             int max_level, int* __restrict__ out_level,
+                                                             int* __restrict__ out_order, int* __restrict__ out_counts) {
+  __shared__ int warp_cnt[kMaxLevels][32];
+  __shared__ int base[kMaxLevels];
+  __shared__ int total[kMaxLevels];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nl = max_level - min_level + 1;
+  // pass 1: counts per level
+  if (tid < kMaxLevels) total[tid] = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < r; b0 += 1024) {
+    const int i = b0 + tid;
+    const int lv = (i < r) ? roi_level(rois[i], min_level, max_level) : -1;
+    if (i < r && out_level) out_level[i] = lv + min_level;
+    for (int l = 0; l < nl; ++l) {
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, lv == l);
+      if (lane == 0 && m) atomicAdd(&total[l], __popc(m));
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int l = 0; l < nl; ++l) {
+      base[l] = run;
+      run += total[l];
+      if (out_counts) out_counts[l] = total[l];
+    }
+  }
+  __syncthreads();
+  // pass 2: stable positions
+  for (int b0 = 0; b0 < r; b0 += 1024) {
+    const int i = b0 + tid;
+    const int lv = (i < r) ? roi_level(rois[i], min_level, max_level) : -1;
+    uint32_t my_mask = 0;
+    for (int l = 0; l < nl; ++l) {
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, lv == l);
+      if (lane == 0) warp_cnt[l][warp] = __popc(m);
+      if (lv == l) my_mask = m;
+    }
+    __syncthreads();
+    if (lv >= 0) {
+      int off = 0;
+      for (int w = 0; w < warp; ++w) off += warp_cnt[lv][w];
+      out_order[base[lv] + off + __popc(my_mask & ((1u << lane) - 1u))] = i;
+    }
+    __syncthreads();
+    if (tid < nl) {
+      int t = 0;
+      for (int w = 0; w < 32; ++w) t += warp_cnt[tid][w];
+      base[tid] += t;
+    }
+    __syncthreads();
+  }
+}
+
+int check_roi_common(const char* fn, bx_handle* h, int pool_size, int c, int r, const void* rois, const void* out) {
+  BX_REQUIRE(h && out && (rois || r == 0), BX_ERR_INVALID, "%s: NULL argument", fn);
+  BX_REQUIRE(r >= 0 && c > 0, BX_ERR_INVALID, "%s: bad size", fn);
+  BX_REQUIRE(pool_size > 0 && 2 * pool_size <= kMaxQ, BX_ERR_UNSUPPORTED, "%s: pool_size must be in [1, %d]", fn, kMaxQ / 2);
+  BX_REQUIRE(bx_aligned(rois, 16), BX_ERR_INVALID, "%s: rois must be 16-byte aligned", fn);
+  return BX_OK;
+}
+
+}  // namespace
+
+extern "C" int bx_crop_and_resize(bx_handle* h, const float* image, int b, int ih, int iw, int c, const float* boxes,
+                                  const int* box_ind, int r, int crop_h, int crop_w, float extrapolation_value,
+                                  float* out, void* stream) {
+  BX_REQUIRE(h && image && out && (boxes || r == 0), BX_ERR_INVALID, "bx_crop_and_resize: NULL argument");
+  BX_REQUIRE(crop_h > 0 && crop_w > 0, BX_ERR_INVALID, "bx_crop_and_resize: crop_size must be 2 positive ints");
+  BX_REQUIRE(crop_h == crop_w && crop_h <= kMaxQ, BX_ERR_UNSUPPORTED,
+             "bx_crop_and_resize: only square crops up to %d are built (the reference uses 7 and 14)", kMaxQ);
+  BX_REQUIRE(b > 0 && ih > 0 && iw > 0 && c > 0 && r >= 0, BX_ERR_INVALID, "bx_crop_and_resize: bad size");
+  BX_REQUIRE(bx_aligned(boxes, 16), BX_ERR_INVALID, "bx_crop_and_resize: boxes must be 16-byte aligned");
+  RoiArgs a = {};
+  a.lv[0] = {image, ih, iw};
+  a.n_levels = 1;
+  a.rois = reinterpret_cast<const float4*>(boxes);
+  a.box_ind = box_ind;
+  a.r = r; a.b = b; a.c = c;
+  a.mode = 3;
+  a.P = crop_h; a.Q = crop_h;
+  a.extrapolation = extrapolation_value;
+  a.out = out;
+  return launch_roi(h, a, BX_POOL_NONE, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bx_roi_pool(bx_handle* h, int mode, int pool, int pool_size, const float* feat, int b, int fh, int fw,
+                           int c, const float* rois, const int* box_ind, const int* roi_counts, int r, float stride,
+                           int image_h, int image_w, float* out, void* stream) {
+  int rc = check_roi_common("bx_roi_pool", h, pool_size, c, r, rois, out);
+  if (rc) return rc;
+  BX_REQUIRE(feat && b > 0 && fh > 1 && fw > 1, BX_ERR_INVALID, "bx_roi_pool: bad feature map");
+  BX_REQUIRE(mode >= 0 && mode <= 2 && pool >= 0 && pool <= 2, BX_ERR_INVALID, "bx_roi_pool: bad mode/pool enum");
+  BX_REQUIRE(mode == BX_ROI_IMAGE_NORM ? (image_h > 0 && image_w > 0) : (stride > 0.0f), BX_ERR_INVALID,
+             "bx_roi_pool: stride (or image shape) must be positive");
+  BX_REQUIRE(!roi_counts || (r % b == 0), BX_ERR_INVALID, "bx_roi_pool: with roi_counts, r must be batch * rois_per_image");
+  RoiArgs a = {};
+  a.lv[0] = {feat, fh, fw};
+  a.n_levels = 1;
+  a.rois = reinterpret_cast<const float4*>(rois);
+  a.box_ind = box_ind;
+  a.roi_counts = roi_counts;
+  a.rois_per_image = roi_counts ? r / b : 0;
+  a.r = r; a.b = b; a.c = c;
+  a.mode = mode;
+  a.P = pool_size;
+  a.Q = (pool == BX_POOL_NONE) ? pool_size : 2 * pool_size;
+  a.stride = stride;
+  a.image_h = static_cast<float>(image_h);
+  a.image_w = static_cast<float>(image_w);
+  a.extrapolation = 0.0f;
+  a.out = out;
+  return launch_roi(h, a, pool, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bx_fpn_assign_levels(bx_handle* h, const float* rois, int r, int min_level, int max_level,
+                                    int* out_level, int* out_order, int* out_counts, void* stream) {
+  BX_REQUIRE(h && out_order && (rois || r == 0), BX_ERR_INVALID, "bx_fpn_assign_levels: NULL argument");
+  BX_REQUIRE(r >= 0 && max_level >= min_level && max_level - min_level < kMaxLevels, BX_ERR_INVALID,
+             "bx_fpn_assign_levels: bad level range");
+  BX_REQUIRE(bx_aligned(rois, 16), BX_ERR_INVALID, "bx_fpn_assign_levels: rois must be 16-byte aligned");
+  assign_levels_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(rois), r,
+                                                                          min_level, max_level, out_level, out_order,
+                                                                          out_counts);
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}
+
+extern "C" int bx_fpn_roi_features(bx_handle* h, const float* const* feats, const int* fh, const int* fw,
+                                   int n_levels, int min_level, int b, int c, const float* rois, const int* box_ind,
+                                   int r, int image_h, int image_w, int pool_size, float* out, int* out_level,
+                                   int* out_order, int* out_counts, void* stream) {
+  int rc = check_roi_common("bx_fpn_roi_features", h, pool_size, c, r, rois, out);
+  if (rc) return rc;
+  BX_REQUIRE(feats && fh && fw && out_level && out_order, BX_ERR_INVALID, "bx_fpn_roi_features: NULL argument");
+  BX_REQUIRE(n_levels > 0 && n_levels <= kMaxLevels && b > 0, BX_ERR_INVALID, "bx_fpn_roi_features: bad level count");
+  BX_REQUIRE(image_h > 0 && image_w > 0, BX_ERR_INVALID, "bx_fpn_roi_features: image shape must be positive");
+  rc = bx_fpn_assign_levels(h, rois, r, min_level, min_level + n_levels - 1, out_level, out_order, out_counts, stream);
+  if (rc) return rc;
+  RoiArgs a = {};
+  for (int l = 0; l < n_levels; ++l) {
+    BX_REQUIRE(feats[l] && fh[l] > 1 && fw[l] > 1, BX_ERR_INVALID, "bx_fpn_roi_features: bad feature map %d", l);
+    a.lv[l] = {feats[l], fh[l], fw[l]};
+  }
+  a.n_levels = n_levels;
+  a.rois = reinterpret_cast<const float4*>(rois);
+  a.box_ind = box_ind;
+  a.order = out_order;
+  a.level = out_level;
+  a.r = r; a.b = b; a.c = c;
+  a.mode = BX_ROI_IMAGE_NORM;
+  a.P = pool_size;
+  a.Q = 2 * pool_size;
+  a.image_h = static_cast<float>(image_h);
+  a.image_w = static_cast<float>(image_w);
+  a.out = out;
+  a.level_base = min_level;
+  return launch_roi(h, a, BX_POOL_MAX2, static_cast<cudaStream_t>(stream));
+}

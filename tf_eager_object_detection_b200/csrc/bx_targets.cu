@@ -1,0 +1,537 @@
+// Training-target stage: pairwise IoU ("+1" convention) and the fused AnchorTarget / ProposalTarget built on it.
+// Replaces utils/bbox_tf.py:7-56 (pairwise_iou), model/anchor_target.py:29-125 (AnchorTarget.call, _unmap) and
+// model/proposal_target.py:32-124 (ProposalTarget.call).  The [N,M] matrix is materialised only by bx_pairwise_iou
+// (its contract); the fused targets recompute rows from gt boxes staged in shared memory.
+//
+// Sampling: the reference's unseeded tf.random_shuffle / np.random.choice are replaced by an injected priority array
+// `perm`: shuffle(idx) := idx sorted ascending by (perm[idx], idx)  (DESIGN.md "Sampling").
+#include "bx_common.cuh"
+
+namespace {
+
+constexpr int kMaxGt = 1024;     // gt boxes staged in shared memory
+constexpr int kSelBins = 1024;
+constexpr int kMaxRois = 2048;   // ProposalTarget: rois per image (== bx_proposals post_nms limit)
+
+// ------------------------------------------------------------------------------------------- pairwise IoU
+__global__ void __launch_bounds__(256) pairwise_iou_kernel(const float4* __restrict__ a, int n,
+                                                           const float4* __restrict__ b, int m,
+                                                           float* __restrict__ out) {
+  const long long total = static_cast<long long>(n) * m;
+  for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += 256ll * gridDim.x) {
+    const int i = static_cast<int>(e / m), j = static_cast<int>(e % m);
+    const float4 x = __ldg(a + i), y = __ldg(b + j);
+    out[e] = bx_iou_plus1(x, bx_area_plus1(x), y, bx_area_plus1(y));
+  }
+}
+
+// ------------------------------------------------------------------------------------------- exact k-smallest select
+// Block-wide: among elements i in [0,n) with flag(i) true, find the threshold composite T such that exactly k elements
+// have comp(i) <= T, comp(i) = (prio[i] << 32) | i  (all distinct).  Adaptive 1024-bin radix refinement.
+// All threads of the block must call; `hist` has kSelBins entries, `sc` 8 uint64 scratch words.  Requires 1 <= k <= #flagged.
+template <typename FlagFn>
+__device__ uint64_t block_select_k_smallest(int n, const int* __restrict__ prio, FlagFn flag, int k, uint32_t* hist,
+                                            uint64_t* sc) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  uint64_t lo = 0ull, hi = 0xFFFFFFFFFFFFFFFFull;
+  // tighten the range to [min,max] of the flagged composites
+  {
+    uint64_t mn = 0xFFFFFFFFFFFFFFFFull, mx = 0ull;
+    for (int i = tid; i < n; i += nt)
+      if (flag(i)) {
+        const uint64_t v = (static_cast<uint64_t>(static_cast<uint32_t>(prio[i])) << 32) | static_cast<uint32_t>(i);
+        mn = min(mn, v);
+        mx = max(mx, v);
+      }
+    if (tid == 0) { sc[0] = 0xFFFFFFFFFFFFFFFFull; sc[1] = 0ull; }
+    __syncthreads();
+    atomicMin(reinterpret_cast<unsigned long long*>(&sc[0]), static_cast<unsigned long long>(mn));
+    atomicMax(reinterpret_cast<unsigned long long*>(&sc[1]), static_cast<unsigned long long>(mx));
+    __syncthreads();
+    lo = sc[0];
+    hi = sc[1];
+    __syncthreads();
+  }
+  int need = k;
+  for (;;) {
+    const uint64_t span = hi - lo;
+    int shift = 0;
+    while ((span >> shift) >= static_cast<uint64_t>(kSelBins)) ++shift;
+    for (int i = tid; i < kSelBins; i += nt) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt)
+      if (flag(i)) {
+        const uint64_t v = (static_cast<uint64_t>(static_cast<uint32_t>(prio[i])) << 32) | static_cast<uint32_t>(i);
+        if (v >= lo && v <= hi) atomicAdd(&hist[static_cast<uint32_t>((v - lo) >> shift)], 1u);
+      }
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0, b = 0;
+      for (; b < kSelBins; ++b) {
+        const int c = static_cast<int>(hist[b]);
+        if (run + c > need) break;
+        run += c;
+      }
+      // b: first bin that does not fit entirely (b == kSelBins: everything fits, then run == need by the precondition)
+      if (run == need) {
+        sc[2] = 1ull;                                              // done
+        sc[3] = (b == 0) ? (lo - 1ull) : (lo + (static_cast<uint64_t>(b) << shift) - 1ull);  // T = last value below bin b
+        if (b == kSelBins) sc[3] = hi;
+      } else {
+        sc[2] = 0ull;
+        sc[4] = lo + (static_cast<uint64_t>(b) << shift);
+        uint64_t nhi = sc[4] + ((1ull << shift) - 1ull);
+        sc[5] = nhi > hi ? hi : nhi;
+        sc[6] = static_cast<uint64_t>(need - run);
+      }
+    }
+    __syncthreads();
+    const bool done = sc[2] != 0ull;
+    const uint64_t T = sc[3];
+    if (!done) {
+      lo = sc[4];
+      hi = sc[5];
+      need = static_cast<int>(sc[6]);
+    }
+    __syncthreads();
+    if (done) return T;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- anchor target
+struct ATArgs {
+  const float4* anchors;  // [n]
+  const float4* gt;       // [batch,max_gt]
+  const int* gt_counts;   // [batch] or null
+  const int* perm;        // [batch,n]
+  int n, max_gt;
+  bx_anchor_target_params p;
+  BoxCodec codec;
+  // workspace
+  float* row_max;         // [batch,n]
+  int* row_arg;           // [batch,n]
+  int* col_max;           // [batch,max_gt] (fp32 bits, iou >= 0 so int order == float order)
+  int* label;             // [batch,n] pre-sampling then final label (-1/0/1), -2 = outside image
+  int* counts;            // [batch,4] = #fg, #bg before sampling; after sampling: fg_final, bg_final
+  // outputs
+  float* out_labels;
+  float4* out_targets;
+  float4* out_in_w;
+  float4* out_out_w;
+  int* out_counts;        // [batch,2]
+};
+
+__device__ __forceinline__ bool anchor_inside(const float4 a, float max_x, float max_y) {
+  return (a.x >= 0.0f) && (a.y >= 0.0f) && (a.z <= max_x) && (a.w <= max_y);  // utils/bbox_tf.py:95-100
+}
+
+// pass A: row max / argmax per inside anchor, column max per gt over inside anchors
+__global__ void __launch_bounds__(256) at_rowstats_kernel(const ATArgs a) {
+  __shared__ float4 s_gt[kMaxGt];
+  __shared__ float s_area[kMaxGt];
+  __shared__ int s_col[kMaxGt];
+  const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int m = a.gt_counts ? a.gt_counts[img] : a.max_gt;
+  for (int j = tid; j < m; j += 256) {
+    const float4 g = a.gt[static_cast<size_t>(img) * a.max_gt + j];
+    s_gt[j] = g;
+    s_area[j] = bx_area_plus1(g);
+    s_col[j] = 0;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * 256 + tid;
+  const bool live = i < a.n;
+  const float4 anc = live ? a.anchors[i] : make_float4(0, 0, 0, 0);
+  const bool inside = live && anchor_inside(anc, static_cast<float>(a.p.image_w - 1), static_cast<float>(a.p.image_h - 1));
+  const float area = bx_area_plus1(anc);
+  float best = -1.0f;
+  int arg = 0;
+  for (int j = 0; j < m; ++j) {
+    float v = inside ? bx_iou_plus1(anc, area, s_gt[j], s_area[j]) : 0.0f;
+    if (inside && v > best) { best = v; arg = j; }        // first max, like tf.argmax
+    const int wmax = __reduce_max_sync(0xFFFFFFFFu, __float_as_int(v));  // int order == float order for v >= 0
+    if (lane == 0) atomicMax(&s_col[j], wmax);
+  }
+  if (live) {
+    const size_t o = static_cast<size_t>(img) * a.n + i;
+    a.row_max[o] = inside ? best : 0.0f;
+    a.row_arg[o] = arg;
+  }
+  __syncthreads();
+  for (int j = tid; j < m; j += 256) atomicMax(&a.col_max[static_cast<size_t>(img) * a.max_gt + j], s_col[j]);
+}
+
+// pass B: labels before subsampling (anchor_target.py:59-69) + fg/bg counts
+__global__ void __launch_bounds__(256) at_label_kernel(const ATArgs a) {
+  __shared__ float4 s_gt[kMaxGt];
+  __shared__ float s_area[kMaxGt];
+  __shared__ float s_col[kMaxGt];
+  const int img = blockIdx.y, tid = threadIdx.x;
+  const int m = a.gt_counts ? a.gt_counts[img] : a.max_gt;
+  for (int j = tid; j < m; j += 256) {
+    const float4 g = a.gt[static_cast<size_t>(img) * a.max_gt + j];
+    s_gt[j] = g;
+    s_area[j] = bx_area_plus1(g);
+    s_col[j] = __int_as_float(a.col_max[static_cast<size_t>(img) * a.max_gt + j]);
+  }
+  __syncthreads();
+  const int i = blockIdx.x * 256 + tid;
+  int lab = -2;
+  if (i < a.n) {
+    const float4 anc = a.anchors[i];
+    if (anchor_inside(anc, static_cast<float>(a.p.image_w - 1), static_cast<float>(a.p.image_h - 1))) {
+      const size_t o = static_cast<size_t>(img) * a.n + i;
+      const float mx = a.row_max[o];
+      const float area = bx_area_plus1(anc);
+      bool is_gt_arg = false;
+      for (int j = 0; j < m; ++j) is_gt_arg |= (bx_iou_plus1(anc, area, s_gt[j], s_area[j]) == s_col[j]);  // :64
+      lab = -1;
+      if (m > 0) {
+        if (mx < a.p.neg_iou_threshold) lab = 0;      // :67
+        if (is_gt_arg) lab = 1;                       // :68
+        if (mx >= a.p.pos_iou_threshold) lab = 1;     // :69
+      }
+    }
+    a.label[static_cast<size_t>(img) * a.n + i] = lab;
+  }
+  const uint32_t fg = __ballot_sync(0xFFFFFFFFu, lab == 1), bg = __ballot_sync(0xFFFFFFFFu, lab == 0);
+  if ((tid & 31) == 0) {
+    if (fg) atomicAdd(&a.counts[img * 4 + 0], __popc(fg));
+    if (bg) atomicAdd(&a.counts[img * 4 + 1], __popc(bg));
+  }
+}
+
+// pass C: subsample fg then bg by priority (anchor_target.py:72-84); one CTA per image
+__global__ void __launch_bounds__(1024) at_sample_kernel(const ATArgs a) {
+  __shared__ uint32_t hist[kSelBins];
+  __shared__ uint64_t sc[8];
+  const int img = blockIdx.x, tid = threadIdx.x;
+  int* label = a.label + static_cast<size_t>(img) * a.n;
+  const int* perm = a.perm + static_cast<size_t>(img) * a.n;
+  const int nfg = a.counts[img * 4 + 0], nbg = a.counts[img * 4 + 1];
+  int fg_final = nfg;
+  if (nfg > a.p.max_pos_samples) {
+    fg_final = a.p.max_pos_samples;
+    uint64_t T = 0ull;
+    if (fg_final > 0) T = block_select_k_smallest(a.n, perm, [&](int i) { return label[i] == 1; }, fg_final, hist, sc);
+    for (int i = tid; i < a.n; i += 1024)
+      if (label[i] == 1) {
+        const uint64_t v = (static_cast<uint64_t>(static_cast<uint32_t>(perm[i])) << 32) | static_cast<uint32_t>(i);
+        if (fg_final == 0 || v > T) label[i] = -1;
+      }
+    __syncthreads();
+  }
+  const int num_bg = a.p.total_num_samples - fg_final;   // :78
+  int bg_final = nbg;
+  if (nbg > num_bg) {
+    bg_final = max(num_bg, 0);
+    uint64_t T = 0ull;
+    if (bg_final > 0) T = block_select_k_smallest(a.n, perm, [&](int i) { return label[i] == 0; }, bg_final, hist, sc);
+    for (int i = tid; i < a.n; i += 1024)
+      if (label[i] == 0) {
+        const uint64_t v = (static_cast<uint64_t>(static_cast<uint32_t>(perm[i])) << 32) | static_cast<uint32_t>(i);
+        if (bg_final == 0 || v > T) label[i] = -1;
+      }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    a.counts[img * 4 + 2] = fg_final;
+    a.counts[img * 4 + 3] = bg_final;
+    if (a.out_counts) {
+      a.out_counts[img * 2 + 0] = fg_final;
+      a.out_counts[img * 2 + 1] = bg_final;
+    }
+  }
+}
+
+// pass D: targets / weights / unmap (anchor_target.py:88-125)
+__global__ void __launch_bounds__(256) at_finalize_kernel(const ATArgs a) {
+  const int img = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.n) return;
+  const size_t o = static_cast<size_t>(img) * a.n + i;
+  const int lab = a.label[o];
+  float4 tg = make_float4(0, 0, 0, 0), iw = tg, ow = tg;
+  float fl = -1.0f;
+  if (lab != -2) {
+    fl = static_cast<float>(lab);
+    const int m = a.gt_counts ? a.gt_counts[img] : a.max_gt;
+    if (m > 0) tg = bx_encode_one(a.anchors[i], a.gt[static_cast<size_t>(img) * a.max_gt + a.row_arg[o]], a.codec);
+    if (lab == 1) iw = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (lab >= 0) {
+      const float num_examples = static_cast<float>(a.counts[img * 4 + 2] + a.counts[img * 4 + 3]);  // :99
+      const float w = 1.0f / num_examples;
+      ow = make_float4(w, w, w, w);
+    }
+  }
+  a.out_labels[o] = fl;
+  a.out_targets[o] = tg;
+  a.out_in_w[o] = iw;
+  a.out_out_w[o] = ow;
+}
+
+// ------------------------------------------------------------------------------------------- proposal target
+struct PTArgs {
+  const float4* rois;      // [batch,k]
+  const int* roi_counts;   // [batch] or null
+  const float4* gt;        // [batch,max_gt]
+  const int* gt_labels;    // [batch,max_gt]
+  const int* gt_counts;    // [batch] or null
+  const int* perm;         // [batch,k]
+  int k, max_gt;
+  bx_proposal_target_params p;
+  BoxCodec codec;
+  float4* out_rois;        // [batch,S]
+  int* out_labels;         // [batch,S]
+  float* out_targets;      // [batch,S,4C]
+  float* out_in_w;
+  float* out_out_w;
+  int* out_keep;           // [batch,S]
+  int* out_counts;         // [batch,2]
+};
+
+__device__ void bitonic_sort_asc(uint64_t* v, int pow2) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int k = 2; k <= pow2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (pow2 >> 1); t += nt) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int q = i | j;
+        const uint64_t x = v[i], y = v[q];
+        const bool asc = ((i & k) == 0);
+        if ((x > y) == asc) { v[i] = y; v[q] = x; }
+      }
+      __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) proposal_target_kernel(const PTArgs a) {
+  extern __shared__ __align__(16) unsigned char pt_smem[];
+  float4* s_gt = reinterpret_cast<float4*>(pt_smem);                       // kMaxGt
+  uint64_t* s_fg = reinterpret_cast<uint64_t*>(s_gt + kMaxGt);             // kMaxRois
+  uint64_t* s_bg = s_fg + kMaxRois;                                        // kMaxRois
+  float* s_area = reinterpret_cast<float*>(s_bg + kMaxRois);               // kMaxGt
+  unsigned short* s_assign = reinterpret_cast<unsigned short*>(s_area + kMaxGt);  // kMaxRois
+  __shared__ int s_cnt[2];
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int m = a.gt_counts ? a.gt_counts[img] : a.max_gt;
+  const int k = a.roi_counts ? min(a.roi_counts[img], a.k) : a.k;
+  const float4* rois = a.rois + static_cast<size_t>(img) * a.k;
+  const float4* gt = a.gt + static_cast<size_t>(img) * a.max_gt;
+  const int* gt_labels = a.gt_labels + static_cast<size_t>(img) * a.max_gt;
+  const int* perm = a.perm + static_cast<size_t>(img) * a.k;
+  const int S = a.p.total_num_samples, C = a.p.num_classes;
+
+  for (int j = tid; j < m; j += 1024) {
+    s_gt[j] = gt[j];
+    s_area[j] = bx_area_plus1(gt[j]);
+  }
+  if (tid < 2) s_cnt[tid] = 0;
+  __syncthreads();
+
+  // (1) max / argmax over gt, fg / bg membership (proposal_target.py:56-64)
+  int pow2 = 64;
+  while (pow2 < k) pow2 <<= 1;
+  for (int i0 = 0; i0 < pow2; i0 += 1024) {
+    const int i = i0 + tid;
+    bool fg = false, bg = false;
+    if (i < k) {
+      const float4 r = rois[i];
+      const float ar = bx_area_plus1(r);
+      float best = -1.0f;
+      int arg = 0;
+      for (int j = 0; j < m; ++j) {
+        const float v = bx_iou_plus1(r, ar, s_gt[j], s_area[j]);
+        if (v > best) { best = v; arg = j; }
+      }
+      s_assign[i] = static_cast<unsigned short>(arg);
+      if (m > 0) {
+        fg = best >= a.p.pos_iou_threshold;
+        bg = (best < a.p.pos_iou_threshold) && (best >= a.p.neg_iou_threshold);
+      }
+    }
+    if (i < pow2) {
+      // provisional keys by index; re-keyed by priority below when a set has to be shuffled
+      s_fg[i] = fg ? static_cast<uint64_t>(i) : 0xFFFFFFFFFFFFFFFFull;
+      s_bg[i] = bg ? static_cast<uint64_t>(i) : 0xFFFFFFFFFFFFFFFFull;
+    }
+    const uint32_t mf = __ballot_sync(0xFFFFFFFFu, fg), mb = __ballot_sync(0xFFFFFFFFu, bg);
+    if (lane == 0) {
+      if (mf) atomicAdd(&s_cnt[0], __popc(mf));
+      if (mb) atomicAdd(&s_cnt[1], __popc(mb));
+    }
+  }
+  __syncthreads();
+  const int nfg_all = s_cnt[0], nbg_all = s_cnt[1];
+  const bool shuffle_fg = nfg_all > a.p.max_pos_samples;                      // :67
+  const int nfg = shuffle_fg ? a.p.max_pos_samples : nfg_all;
+  const int want = S - nfg;
+  const bool shuffle_bg = (nbg_all != want);                                  // :69-77 (> : subsample, < : padded cycle)
+  // (2) order the two sets: ascending index (tf.where order) or ascending (perm, index) when shuffled
+  for (int i = tid; i < pow2; i += 1024) {
+    if (shuffle_fg && s_fg[i] != 0xFFFFFFFFFFFFFFFFull)
+      s_fg[i] = (static_cast<uint64_t>(static_cast<uint32_t>(perm[i])) << 32) | static_cast<uint32_t>(i);
+    if (shuffle_bg && s_bg[i] != 0xFFFFFFFFFFFFFFFFull)
+      s_bg[i] = (static_cast<uint64_t>(static_cast<uint32_t>(perm[i])) << 32) | static_cast<uint32_t>(i);
+  }
+  __syncthreads();
+  bitonic_sort_asc(s_fg, pow2);
+  bitonic_sort_asc(s_bg, pow2);
+
+  const int status = (want > 0 && nbg_all == 0) ? 1 : 0;   // np.random.choice on an empty set raises (:77)
+  if (tid == 0) {
+    a.out_counts[img * 2 + 0] = nfg;
+    a.out_counts[img * 2 + 1] = status;
+  }
+  // (3) outputs
+  float4* out_rois = a.out_rois + static_cast<size_t>(img) * S;
+  int* out_labels = a.out_labels + static_cast<size_t>(img) * S;
+  int* out_keep = a.out_keep + static_cast<size_t>(img) * S;
+  const size_t row = static_cast<size_t>(4) * C;
+  float* out_t = a.out_targets + static_cast<size_t>(img) * S * row;
+  float* out_i = a.out_in_w + static_cast<size_t>(img) * S * row;
+  float* out_o = a.out_out_w + static_cast<size_t>(img) * S * row;
+  for (size_t e = tid; e < static_cast<size_t>(S) * row; e += 1024) {
+    out_t[e] = 0.0f;
+    out_i[e] = 0.0f;
+    out_o[e] = 1.0f;                                                          // :122
+  }
+  __syncthreads();
+  for (int s = tid; s < S; s += 1024) {
+    int src = -1;
+    if (s < nfg) src = static_cast<int>(s_fg[s] & 0xFFFFFFFFull);
+    else if (nbg_all > 0) src = static_cast<int>(s_bg[(s - nfg) % nbg_all] & 0xFFFFFFFFull);
+    out_keep[s] = src;
+    if (src < 0) {
+      out_rois[s] = make_float4(0, 0, 0, 0);
+      out_labels[s] = 0;
+      continue;
+    }
+    const float4 r = rois[src];
+    out_rois[s] = r;                                                          // :82
+    out_labels[s] = (s < nfg) ? gt_labels[s_assign[src]] : 0;                 // :83-86
+    if (s < nfg) {
+      const int cls = gt_labels[s_assign[s]];                                 // :99,117 `labels[idx]` quirk: roi #s, not roi fg[s]
+      if (cls >= 0 && cls < C) {
+        const float4 t = bx_encode_one(r, s_gt[s_assign[src]], a.codec);      // :105-108
+        float* pt = out_t + static_cast<size_t>(s) * row + 4 * cls;
+        float* pi = out_i + static_cast<size_t>(s) * row + 4 * cls;
+        pt[0] = t.x; pt[1] = t.y; pt[2] = t.z; pt[3] = t.w;
+        pi[0] = 1.f; pi[1] = 1.f; pi[2] = 1.f; pi[3] = 1.f;
+      }
+    }
+  }
+}
+
+BoxCodec codec_of(const float means[4], const float stds[4]) {
+  BoxCodec k = {};
+  k.m0 = means[0]; k.m1 = means[1]; k.m2 = means[2]; k.m3 = means[3];
+  k.s0 = stds[0]; k.s1 = stds[1]; k.s2 = stds[2]; k.s3 = stds[3];
+  return k;
+}
+
+}  // namespace
+
+extern "C" int bx_pairwise_iou(bx_handle* h, const float* a, int n, const float* b, int m, float* out, void* stream) {
+  BX_REQUIRE(h && out && (a || n == 0) && (b || m == 0), BX_ERR_INVALID, "bx_pairwise_iou: NULL argument");
+  BX_REQUIRE(n >= 0 && m >= 0, BX_ERR_INVALID, "bx_pairwise_iou: negative size");
+  BX_REQUIRE(bx_aligned(a, 16) && bx_aligned(b, 16), BX_ERR_INVALID, "bx_pairwise_iou: boxes must be 16-byte aligned");
+  const long long total = static_cast<long long>(n) * m;
+  if (total == 0) return BX_OK;
+  const int grid = static_cast<int>(bx_min_ll(bx_div_up(total, 256), 16ll * h->num_sms));
+  pairwise_iou_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(a), n, reinterpret_cast<const float4*>(b), m, out);
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}
+
+extern "C" int bx_anchor_target(bx_handle* h, const float* anchors, int n, const float* gt, const int* gt_counts,
+                                int batch, int max_gt, const int* perm, const bx_anchor_target_params* p,
+                                float* out_labels, float* out_targets, float* out_in_w, float* out_out_w,
+                                int* out_counts, void* stream) {
+  BX_REQUIRE(h && anchors && gt && perm && p && out_labels && out_targets && out_in_w && out_out_w, BX_ERR_INVALID,
+             "bx_anchor_target: NULL argument");
+  BX_REQUIRE(n > 0 && batch >= 0 && max_gt >= 0, BX_ERR_INVALID, "bx_anchor_target: bad size");
+  BX_REQUIRE(max_gt <= kMaxGt, BX_ERR_UNSUPPORTED, "bx_anchor_target: max_gt %d > %d", max_gt, kMaxGt);
+  BX_REQUIRE(p->max_pos_samples >= 0 && p->total_num_samples >= p->max_pos_samples, BX_ERR_INVALID,
+             "bx_anchor_target: need 0 <= max_pos_samples <= total_num_samples");
+  BX_REQUIRE(bx_aligned(anchors, 16) && bx_aligned(gt, 16) && bx_aligned(out_targets, 16) && bx_aligned(out_in_w, 16) &&
+                 bx_aligned(out_out_w, 16), BX_ERR_INVALID, "bx_anchor_target: box tensors must be 16-byte aligned");
+  if (batch == 0) return BX_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bn = static_cast<size_t>(batch) * n;
+  const size_t ws = bn * (sizeof(float) + 2 * sizeof(int)) + static_cast<size_t>(batch) * (max_gt + 4) * sizeof(int);
+  int rc = bx_ws_reserve(h, ws);
+  if (rc) return rc;
+  ATArgs a = {};
+  a.anchors = reinterpret_cast<const float4*>(anchors);
+  a.gt = reinterpret_cast<const float4*>(gt);
+  a.gt_counts = gt_counts;
+  a.perm = perm;
+  a.n = n;
+  a.max_gt = max_gt;
+  a.p = *p;
+  a.codec = codec_of(p->means, p->stds);
+  a.row_max = reinterpret_cast<float*>(h->ws);
+  a.row_arg = reinterpret_cast<int*>(a.row_max + bn);
+  a.label = a.row_arg + bn;
+  a.col_max = a.label + bn;
+  a.counts = a.col_max + static_cast<size_t>(batch) * max_gt;
+  a.out_labels = out_labels;
+  a.out_targets = reinterpret_cast<float4*>(out_targets);
+  a.out_in_w = reinterpret_cast<float4*>(out_in_w);
+  a.out_out_w = reinterpret_cast<float4*>(out_out_w);
+  a.out_counts = out_counts;
+  BX_CUDA(cudaMemsetAsync(a.col_max, 0, static_cast<size_t>(batch) * (max_gt + 4) * sizeof(int), st));
+  const dim3 grid(bx_div_up(n, 256), batch);
+  at_rowstats_kernel<<<grid, 256, 0, st>>>(a);
+  BX_LAUNCH_CHECK(h);
+  at_label_kernel<<<grid, 256, 0, st>>>(a);
+  BX_LAUNCH_CHECK(h);
+  at_sample_kernel<<<batch, 1024, 0, st>>>(a);
+  BX_LAUNCH_CHECK(h);
+  at_finalize_kernel<<<grid, 256, 0, st>>>(a);
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}
+
+extern "C" int bx_proposal_target(bx_handle* h, const float* rois, const int* roi_counts, int k, const float* gt,
+                                  const int* gt_labels, const int* gt_counts, int batch, int max_gt, const int* perm,
+                                  const bx_proposal_target_params* p, float* out_rois, int* out_labels,
+                                  float* out_targets, float* out_in_w, float* out_out_w, int* out_keep,
+                                  int* out_counts, void* stream) {
+  BX_REQUIRE(h && rois && gt && gt_labels && perm && p && out_rois && out_labels && out_targets && out_in_w &&
+                 out_out_w && out_keep && out_counts, BX_ERR_INVALID, "bx_proposal_target: NULL argument");
+  BX_REQUIRE(k >= 0 && batch >= 0 && max_gt >= 0, BX_ERR_INVALID, "bx_proposal_target: negative size");
+  BX_REQUIRE(k <= kMaxRois, BX_ERR_UNSUPPORTED, "bx_proposal_target: %d rois per image > %d", k, kMaxRois);
+  BX_REQUIRE(max_gt <= kMaxGt, BX_ERR_UNSUPPORTED, "bx_proposal_target: max_gt %d > %d", max_gt, kMaxGt);
+  BX_REQUIRE(p->num_classes > 0 && p->total_num_samples > 0 && p->max_pos_samples >= 0 &&
+                 p->max_pos_samples <= p->total_num_samples, BX_ERR_INVALID, "bx_proposal_target: bad sampling parameters");
+  BX_REQUIRE(bx_aligned(rois, 16) && bx_aligned(gt, 16) && bx_aligned(out_rois, 16), BX_ERR_INVALID,
+             "bx_proposal_target: box tensors must be 16-byte aligned");
+  if (batch == 0) return BX_OK;
+  PTArgs a = {};
+  a.rois = reinterpret_cast<const float4*>(rois);
+  a.roi_counts = roi_counts;
+  a.gt = reinterpret_cast<const float4*>(gt);
+  a.gt_labels = gt_labels;
+  a.gt_counts = gt_counts;
+  a.perm = perm;
+  a.k = k;
+  a.max_gt = max_gt;
+  a.p = *p;
+  a.codec = codec_of(p->means, p->stds);
+  a.out_rois = reinterpret_cast<float4*>(out_rois);
+  a.out_labels = out_labels;
+  a.out_targets = out_targets;
+  a.out_in_w = out_in_w;
+  a.out_out_w = out_out_w;
+  a.out_keep = out_keep;
+  a.out_counts = out_counts;
+  const size_t smem = sizeof(float4) * kMaxGt + 2 * sizeof(uint64_t) * kMaxRois + sizeof(float) * kMaxGt +
+                      sizeof(unsigned short) * kMaxRois;
+  BX_CUDA(cudaFuncSetAttribute(proposal_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  proposal_target_kernel<<<batch, 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}

@@ -1,0 +1,312 @@
+"""Functional layer over the C ABI: one Python function per `bx_*` entry point, torch CUDA tensors in and out.
+
+Every function is asynchronous on torch's current stream and performs no host synchronisation; the class layer
+(region_proposal.py, roi_pooling.py, ...) adds the reference's ragged Python views where its signatures need them."""
+import ctypes
+from ctypes import c_int, c_void_p
+
+import torch
+
+from . import _lib
+from ._tensor import FLOAT32, INT32, Borrow, device_index_of, empty, stream_ptr, to_device
+
+f32, i32 = torch.float32, torch.int32
+
+
+def _ctx(t):
+    dev = device_index_of(t)
+    return dev, _lib.handle(dev), Borrow(dev), stream_ptr(dev), _lib.load()
+
+
+def decode_clip(anchors, deltas, means=(0, 0, 0, 0), stds=(1, 1, 1, 1), image_shape=None):
+    """a1 (+a2 clip when image_shape is given).  anchors [n,4] or [b,n,4]; deltas [n,4] or [b,n,4]."""
+    deltas = to_device(deltas, f32)
+    anchors = to_device(anchors, f32, deltas.device)
+    squeeze = deltas.dim() == 2
+    d3 = deltas.unsqueeze(0) if squeeze else deltas
+    b, n = d3.shape[0], d3.shape[1]
+    batched_anchors = anchors.dim() == 3
+    dev, h, bw, st, lib = _ctx(d3)
+    out = empty((b, n, 4), f32, dev)
+    if b * n:
+        H, W = (int(image_shape[0]), int(image_shape[1])) if image_shape is not None else (0, 0)
+        _lib.check(lib.bx_decode_clip(h, bw.ptr(anchors, FLOAT32, (b, n, 4) if batched_anchors else (n, 4), 16),
+                                      1 if batched_anchors else 0, bw.ptr(d3, FLOAT32, (b, n, 4), 16), b, n,
+                                      _lib.f4(means), _lib.f4(stds), H, W, bw.ptr(out, FLOAT32, (b, n, 4), 16), st))
+    return out[0] if squeeze else out
+
+
+def encode(src, dst, means=(0, 0, 0, 0), stds=(1, 1, 1, 1)):
+    """a12: utils/bbox_transform.py:4-29."""
+    src = to_device(src, f32)
+    dst = to_device(dst, f32, src.device)
+    n = src.shape[0]
+    dev, h, bw, st, lib = _ctx(src)
+    out = empty((n, 4), f32, dev)
+    if n:
+        _lib.check(lib.bx_encode(h, bw.ptr(src, FLOAT32, (n, 4), 16), bw.ptr(dst, FLOAT32, (n, 4), 16), n,
+                                 _lib.f4(means), _lib.f4(stds), bw.ptr(out, FLOAT32, (n, 4), 16), st))
+    return out
+
+
+def clip_filter(boxes, min_value, max_height, max_width, min_edge):
+    """a2 with min_edge: returns (boxes_padded [n,4], idx_padded [n] int32, count [1] int32) — device-resident."""
+    boxes = to_device(boxes, f32)
+    n = boxes.shape[0]
+    dev, h, bw, st, lib = _ctx(boxes)
+    ob, oi, oc = empty((n, 4), f32, dev), empty((n,), i32, dev), torch.zeros((1,), dtype=i32, device=boxes.device)
+    if n:
+        _lib.check(lib.bx_clip_filter(h, bw.ptr(boxes, FLOAT32, (n, 4), 16), n, float(min_value), int(max_height),
+                                      int(max_width), float(min_edge), bw.ptr(ob, FLOAT32, (n, 4), 16),
+                                      bw.ptr(oi, INT32, (n,)), bw.ptr(oc, INT32, (1,)), st))
+    return ob, oi, oc
+
+
+def range_filter(anchors, max_height, max_width):
+    """utils/bbox_tf.py:87-101: (idx_padded [n] int32, count [1])."""
+    anchors = to_device(anchors, f32)
+    n = anchors.shape[0]
+    dev, h, bw, st, lib = _ctx(anchors)
+    oi, oc = empty((n,), i32, dev), torch.zeros((1,), dtype=i32, device=anchors.device)
+    if n:
+        _lib.check(lib.bx_range_filter(h, bw.ptr(anchors, FLOAT32, (n, 4), 16), n, int(max_height), int(max_width),
+                                       bw.ptr(oi, INT32, (n,)), bw.ptr(oc, INT32, (1,)), st))
+    return oi, oc
+
+
+def nms(boxes, scores, max_output_size, iou_threshold):
+    """tf.image.non_max_suppression, batched: boxes [b,n,4], scores [b,n] -> (idx [b,max_out] int32 (-1 pad), count [b])."""
+    boxes = to_device(boxes, f32)
+    scores = to_device(scores, f32, boxes.device)
+    squeeze = boxes.dim() == 2
+    b3 = boxes.unsqueeze(0) if squeeze else boxes
+    s2 = scores.unsqueeze(0) if squeeze else scores
+    b, n = b3.shape[0], b3.shape[1]
+    dev, h, bw, st, lib = _ctx(b3)
+    oi, oc = empty((b, int(max_output_size)), i32, dev), empty((b,), i32, dev)
+    if n == 0 or max_output_size == 0:
+        oi.fill_(-1)
+        oc.zero_()
+        if not (0.0 <= iou_threshold <= 1.0):
+            raise ValueError('iou_threshold must be in [0, 1]')
+    else:
+        _lib.check(lib.bx_nms(h, bw.ptr(b3, FLOAT32, (b, n, 4), 16), bw.ptr(s2, FLOAT32, (b, n)), b, n,
+                              int(max_output_size), float(iou_threshold), bw.ptr(oi, INT32, (b, int(max_output_size))),
+                              bw.ptr(oc, INT32, (b,)), st))
+    return (oi[0], oc[0]) if squeeze else (oi, oc)
+
+
+def proposal_params(image_shape, post_nms, iou_threshold=0.7, means=(0, 0, 0, 0), stds=(1, 1, 1, 1),
+                    pre_nms_top_k=0, min_size=0.0):
+    return _lib.ProposalParams(_lib.f4(means), _lib.f4(stds), int(image_shape[0]), int(image_shape[1]),
+                               int(pre_nms_top_k), int(post_nms), float(iou_threshold), float(min_size))
+
+
+def proposals(anchors, deltas, scores, image_shape, post_nms, iou_threshold=0.7, means=(0, 0, 0, 0),
+              stds=(1, 1, 1, 1), pre_nms_top_k=0, min_size=0.0):
+    """a3 batched: anchors [n,4]; deltas [b,n,4]; scores [b,n] -> (boxes [b,post,4], idx [b,post], count [b])."""
+    deltas = to_device(deltas, f32)
+    anchors = to_device(anchors, f32, deltas.device)
+    scores = to_device(scores, f32, deltas.device)
+    b, n = deltas.shape[0], deltas.shape[1]
+    dev, h, bw, st, lib = _ctx(deltas)
+    p = proposal_params(image_shape, post_nms, iou_threshold, means, stds, pre_nms_top_k, min_size)
+    ob, oi, oc = empty((b, post_nms, 4), f32, dev), empty((b, post_nms), i32, dev), empty((b,), i32, dev)
+    if n == 0:
+        ob.zero_(); oi.fill_(-1); oc.zero_()
+        return ob, oi, oc
+    _lib.check(lib.bx_proposals(h, bw.ptr(anchors, FLOAT32, (n, 4), 16), bw.ptr(deltas, FLOAT32, (b, n, 4), 16),
+                                bw.ptr(scores, FLOAT32, (b, n)), b, n, ctypes.byref(p),
+                                bw.ptr(ob, FLOAT32, (b, post_nms, 4), 16), bw.ptr(oi, INT32, (b, post_nms)),
+                                bw.ptr(oc, INT32, (b,)), st))
+    return ob, oi, oc
+
+
+def crop_and_resize(image, boxes, box_ind, crop_size, extrapolation_value=0.0):
+    """tf.image.crop_and_resize (bilinear): image [b,h,w,c]; boxes [r,4] (y1,x1,y2,x2) normalised; box_ind [r]."""
+    image = to_device(image, f32)
+    boxes = to_device(boxes, f32, image.device)
+    box_ind = to_device(box_ind, i32, image.device)
+    ch, cw = int(crop_size[0]), int(crop_size[1])
+    b, ih, iw, c = image.shape
+    r = boxes.shape[0]
+    dev, h, bw, st, lib = _ctx(image)
+    out = empty((r, ch, cw, c), f32, dev)
+    if ch <= 0 or cw <= 0:
+        raise ValueError('crop_size must be 2 positive ints')
+    if r:
+        _lib.check(lib.bx_crop_and_resize(h, bw.ptr(image, FLOAT32, (b, ih, iw, c)), b, ih, iw, c,
+                                          bw.ptr(boxes, FLOAT32, (r, 4), 16), bw.ptr(box_ind, INT32, (r,)), r, ch, cw,
+                                          float(extrapolation_value), bw.ptr(out, FLOAT32, (r, ch, cw, c)), st))
+    return out
+
+
+def roi_pool(mode, pool, pool_size, feat, rois, stride=16.0, image_shape=(0, 0), box_ind=None, roi_counts=None):
+    """a4/a5/a8: feat [b,fh,fw,c]; rois [r,4] (or [b,k,4] with roi_counts [b]) -> [r,P,P,c]."""
+    feat = to_device(feat, f32)
+    rois = to_device(rois, f32, feat.device).reshape(-1, 4)
+    b, fh, fw, c = feat.shape
+    r = rois.shape[0]
+    dev, h, bw, st, lib = _ctx(feat)
+    out = empty((r, pool_size, pool_size, c), f32, dev)
+    if r:
+        bi = bw.ptr(to_device(box_ind, i32, feat.device), INT32, (r,)) if box_ind is not None else None
+        rc = bw.ptr(to_device(roi_counts, i32, feat.device), INT32, (b,)) if roi_counts is not None else None
+        _lib.check(lib.bx_roi_pool(h, mode, pool, int(pool_size), bw.ptr(feat, FLOAT32, (b, fh, fw, c)), b, fh, fw, c,
+                                   bw.ptr(rois, FLOAT32, (r, 4), 16), bi, rc, r, float(stride), int(image_shape[0]),
+                                   int(image_shape[1]), bw.ptr(out, FLOAT32, (r, pool_size, pool_size, c)), st))
+    return out
+
+
+def fpn_assign_levels(rois, min_level=2, max_level=5):
+    """a6: rois [r,4] -> (level [r] int32, order [r] int32 level-major stable, counts [L] int32)."""
+    rois = to_device(rois, f32)
+    r = rois.shape[0]
+    nl = max_level - min_level + 1
+    dev, h, bw, st, lib = _ctx(rois)
+    lv, order, counts = empty((r,), i32, dev), empty((r,), i32, dev), torch.zeros((nl,), dtype=i32, device=rois.device)
+    if r:
+        _lib.check(lib.bx_fpn_assign_levels(h, bw.ptr(rois, FLOAT32, (r, 4), 16), r, min_level, max_level,
+                                            bw.ptr(lv, INT32, (r,)), bw.ptr(order, INT32, (r,)),
+                                            bw.ptr(counts, INT32, (nl,)), st))
+    return lv, order, counts
+
+
+def fpn_roi_features(feats, rois, image_shape, pool_size=7, min_level=2, box_ind=None):
+    """a6+a7 fused: feats = [P2..P5] each [b,fh,fw,c]; rois [r,4] -> (features [r,P,P,c] level-major, level, order, counts)."""
+    feats = [to_device(f, f32) for f in feats]
+    rois = to_device(rois, f32, feats[0].device)
+    r = rois.shape[0]
+    nl = len(feats)
+    b, c = feats[0].shape[0], feats[0].shape[3]
+    dev, h, bw, st, lib = _ctx(feats[0])
+    out = empty((r, pool_size, pool_size, c), f32, dev)
+    lv, order, counts = empty((r,), i32, dev), empty((r,), i32, dev), torch.zeros((nl,), dtype=i32, device=rois.device)
+    if r:
+        ptrs = (c_void_p * nl)(*[bw.ptr(f, FLOAT32, (b, f.shape[1], f.shape[2], c)) for f in feats])
+        fh = (c_int * nl)(*[f.shape[1] for f in feats])
+        fw = (c_int * nl)(*[f.shape[2] for f in feats])
+        bi = bw.ptr(to_device(box_ind, i32, rois.device), INT32, (r,)) if box_ind is not None else None
+        _lib.check(lib.bx_fpn_roi_features(h, ptrs, fh, fw, nl, min_level, b, c, bw.ptr(rois, FLOAT32, (r, 4), 16), bi,
+                                           r, int(image_shape[0]), int(image_shape[1]), int(pool_size),
+                                           bw.ptr(out, FLOAT32, (r, pool_size, pool_size, c)), bw.ptr(lv, INT32, (r,)),
+                                           bw.ptr(order, INT32, (r,)), bw.ptr(counts, INT32, (nl,)), st))
+    return out, lv, order, counts
+
+
+def pairwise_iou(b1, b2):
+    """a9: utils/bbox_tf.py:37-56 -> [n,m] fp32."""
+    b1 = to_device(b1, f32)
+    b2 = to_device(b2, f32, b1.device)
+    n, m = b1.shape[0], b2.shape[0]
+    dev, h, bw, st, lib = _ctx(b1)
+    out = empty((n, m), f32, dev)
+    if n * m:
+        _lib.check(lib.bx_pairwise_iou(h, bw.ptr(b1, FLOAT32, (n, 4), 16), n, bw.ptr(b2, FLOAT32, (m, 4), 16), m,
+                                       bw.ptr(out, FLOAT32, (n, m)), st))
+    return out
+
+
+def anchor_target(anchors, gt, perm, image_shape, pos_iou_threshold=0.7, neg_iou_threshold=0.3,
+                  total_num_samples=256, max_pos_samples=128, means=(0, 0, 0, 0), stds=(1, 1, 1, 1), gt_counts=None):
+    """a10 batched: anchors [n,4]; gt [b,m,4]; perm [b,n] int32 -> labels [b,n], targets/in_w/out_w [b,n,4], counts [b,2]."""
+    anchors = to_device(anchors, f32)
+    gt = to_device(gt, f32, anchors.device)
+    perm = to_device(perm, i32, anchors.device)
+    n = anchors.shape[0]
+    b, m = gt.shape[0], gt.shape[1]
+    dev, h, bw, st, lib = _ctx(anchors)
+    p = _lib.AnchorTargetParams(float(pos_iou_threshold), float(neg_iou_threshold), int(total_num_samples),
+                                int(max_pos_samples), _lib.f4(means), _lib.f4(stds), int(image_shape[0]),
+                                int(image_shape[1]))
+    lab = empty((b, n), f32, dev)
+    tg, iw, ow = empty((b, n, 4), f32, dev), empty((b, n, 4), f32, dev), empty((b, n, 4), f32, dev)
+    cnt = empty((b, 2), i32, dev)
+    gc = bw.ptr(to_device(gt_counts, i32, anchors.device), INT32, (b,)) if gt_counts is not None else None
+    _lib.check(lib.bx_anchor_target(h, bw.ptr(anchors, FLOAT32, (n, 4), 16), n,
+                                    bw.ptr(gt, FLOAT32, (b, m, 4), 16) if m else 0, gc, b, m,
+                                    bw.ptr(perm, INT32, (b, n)), ctypes.byref(p), bw.ptr(lab, FLOAT32, (b, n)),
+                                    bw.ptr(tg, FLOAT32, (b, n, 4), 16), bw.ptr(iw, FLOAT32, (b, n, 4), 16),
+                                    bw.ptr(ow, FLOAT32, (b, n, 4), 16), bw.ptr(cnt, INT32, (b, 2)), st))
+    return lab, tg, iw, ow, cnt
+
+
+def proposal_target(rois, gt, gt_labels, perm, num_classes=21, pos_iou_threshold=0.5, neg_iou_threshold=0.5,
+                    total_num_samples=128, max_pos_samples=32, means=(0, 0, 0, 0), stds=(1, 1, 1, 1),
+                    roi_counts=None, gt_counts=None):
+    """a11 batched: rois [b,k,4]; gt [b,m,4]; gt_labels [b,m] int32; perm [b,k] int32 ->
+    (rois [b,S,4], labels [b,S] int32, targets, in_w, out_w [b,S,4C], keep [b,S] int32, counts [b,2])."""
+    rois = to_device(rois, f32)
+    gt = to_device(gt, f32, rois.device)
+    gt_labels = to_device(gt_labels, i32, rois.device)
+    perm = to_device(perm, i32, rois.device)
+    b, k = rois.shape[0], rois.shape[1]
+    m = gt.shape[1]
+    S, C = int(total_num_samples), int(num_classes)
+    dev, h, bw, st, lib = _ctx(rois)
+    p = _lib.ProposalTargetParams(C, float(pos_iou_threshold), float(neg_iou_threshold), S, int(max_pos_samples),
+                                  _lib.f4(means), _lib.f4(stds))
+    o_rois, o_lab = empty((b, S, 4), f32, dev), empty((b, S), i32, dev)
+    o_t, o_i, o_o = empty((b, S, 4 * C), f32, dev), empty((b, S, 4 * C), f32, dev), empty((b, S, 4 * C), f32, dev)
+    o_keep, o_cnt = empty((b, S), i32, dev), empty((b, 2), i32, dev)
+    rc = bw.ptr(to_device(roi_counts, i32, rois.device), INT32, (b,)) if roi_counts is not None else None
+    gc = bw.ptr(to_device(gt_counts, i32, rois.device), INT32, (b,)) if gt_counts is not None else None
+    _lib.check(lib.bx_proposal_target(h, bw.ptr(rois, FLOAT32, (b, k, 4), 16) if k else 0, rc, k,
+                                      bw.ptr(gt, FLOAT32, (b, m, 4), 16) if m else 0,
+                                      bw.ptr(gt_labels, INT32, (b, m)) if m else 0, gc, b, m,
+                                      bw.ptr(perm, INT32, (b, k)) if k else 0, ctypes.byref(p),
+                                      bw.ptr(o_rois, FLOAT32, (b, S, 4), 16), bw.ptr(o_lab, INT32, (b, S)),
+                                      bw.ptr(o_t, FLOAT32, (b, S, 4 * C)), bw.ptr(o_i, FLOAT32, (b, S, 4 * C)),
+                                      bw.ptr(o_o, FLOAT32, (b, S, 4 * C)), bw.ptr(o_keep, INT32, (b, S)),
+                                      bw.ptr(o_cnt, INT32, (b, 2)), st))
+    return o_rois, o_lab, o_t, o_i, o_o, o_keep, o_cnt
+
+
+def c4_proposal_roi(anchors, deltas, scores, feat, image_shape, post_nms, stride=16.0, pool_size=7,
+                    max_pooling_flag=False, iou_threshold=0.7, means=(0, 0, 0, 0), stds=(1, 1, 1, 1), pre_nms_top_k=0,
+                    min_size=0.0, out=None):
+    """Composite used by BaseFasterRcnn eval (base_faster_rcnn_model.py:153,182) and the benchmark, batched:
+    -> (rois [b,post,4], idx [b,post], count [b], roi_features [b*post,P,P,c])."""
+    deltas = to_device(deltas, f32)
+    anchors = to_device(anchors, f32, deltas.device)
+    scores = to_device(scores, f32, deltas.device)
+    feat = to_device(feat, f32, deltas.device)
+    b, n = deltas.shape[0], deltas.shape[1]
+    _, fh, fw, c = feat.shape
+    dev, h, bw, st, lib = _ctx(deltas)
+    p = proposal_params(image_shape, post_nms, iou_threshold, means, stds, pre_nms_top_k, min_size)
+    if out is None:
+        out = (empty((b, post_nms, 4), f32, dev), empty((b, post_nms), i32, dev), empty((b,), i32, dev),
+               empty((b * post_nms, pool_size, pool_size, c), f32, dev))
+    ob, oi, oc, of = out
+    _lib.check(lib.bx_c4_proposal_roi(h, bw.ptr(anchors, FLOAT32, (n, 4), 16), bw.ptr(deltas, FLOAT32, (b, n, 4), 16),
+                                      bw.ptr(scores, FLOAT32, (b, n)), bw.ptr(feat, FLOAT32, (b, fh, fw, c)), b, n, fh,
+                                      fw, c, ctypes.byref(p), float(stride), int(pool_size),
+                                      _lib.POOL_MAX2 if max_pooling_flag else _lib.POOL_NONE,
+                                      bw.ptr(ob, FLOAT32, (b, post_nms, 4), 16), bw.ptr(oi, INT32, (b, post_nms)),
+                                      bw.ptr(oc, INT32, (b,)),
+                                      bw.ptr(of, FLOAT32, (b * post_nms, pool_size, pool_size, c)), st))
+    return ob, oi, oc, of
+
+
+def c4_proposal_roi_host(anchors_dev, deltas_h, scores_h, feat_h, image_shape, post_nms, out_h, stride=16.0,
+                         pool_size=7, max_pooling_flag=False, iou_threshold=0.7, means=(0, 0, 0, 0),
+                         stds=(1, 1, 1, 1), pre_nms_top_k=0, min_size=0.0):
+    """Same composite through HOST buffers (bx_c4_proposal_roi_host): deltas/scores/feat and the four outputs are CPU
+    torch tensors (pinned for full PCIe rate); copies are enqueued on torch's current stream around the kernels.
+    out_h = (rois [b,post,4] f32, idx [b,post] i32, count [b] i32, feat [b*post,P,P,c] f32) CPU tensors."""
+    anchors_dev = to_device(anchors_dev, f32)
+    for t in (deltas_h, scores_h, feat_h) + tuple(out_h):
+        if t.is_cuda or not t.is_contiguous():
+            raise ValueError('c4_proposal_roi_host expects contiguous CPU tensors')
+    b, n = deltas_h.shape[0], deltas_h.shape[1]
+    _, fh, fw, c = feat_h.shape
+    dev, h, bw, st, lib = _ctx(anchors_dev)
+    p = proposal_params(image_shape, post_nms, iou_threshold, means, stds, pre_nms_top_k, min_size)
+    ob, oi, oc, of = out_h
+    _lib.check(lib.bx_c4_proposal_roi_host(h, bw.ptr(anchors_dev, FLOAT32, (n, 4), 16), deltas_h.data_ptr(),
+                                           scores_h.data_ptr(), feat_h.data_ptr(), b, n, fh, fw, c, ctypes.byref(p),
+                                           float(stride), int(pool_size),
+                                           _lib.POOL_MAX2 if max_pooling_flag else _lib.POOL_NONE, ob.data_ptr(),
+                                           oi.data_ptr(), oc.data_ptr(), of.data_ptr(), st))
+    return out_h
