@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — proposal + NMS + RoI pooling throughput (BASELINE.json metric) on N B200s, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one pass of the hot path over one batch of synthetic images (workload cfg2 of BASELINE.json: ResNet-50 C4,
+600x1000, 21 546 anchors, pre-NMS 6000 -> post-NMS 300, crop 7x7x1024, batch 8 per GPU).  Prints ONE JSON line (rank 0).
+Device-resident `value`, host-buffer `e2e`, `roofline` of the dominant kernel (RoI pooling), `cpu_baseline` (oracle C
+twin on the host cores), clocks.  `--impl reference` times the CPU restatement of the reference path instead.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tf_eager_object_detection_b200 import synthetic as syn  # noqa: E402
+
+WORKLOAD = dict(name='cfg2: ResNet-50 C4 600x1000, 21546 anchors, pre-NMS 6000 -> post-NMS 300, crop 7x7x1024, batch 8/GPU',
+                cfg=2, batch=8, image_hw=(600, 1000), stride=16, channels=1024, pre_nms=6000, post_nms=300, pool=7,
+                iou_thr=0.7)
+METRIC = 'proposal+NMS+RoIAlign images/s'
+UNIT = 'images/s'
+FALLBACK_HBM_GBS = 6650.0
+
+
+def algorithmic_bytes(w, n, fh, fw):
+    """B_prop = 36N + 20K ; B_roi = 4*C*h*w + 16R + 4*R*P^2*C (per image, K = R = post_nms)."""
+    K = R = w['post_nms']
+    b_prop = 36 * n + 20 * K
+    b_roi = 4 * w['channels'] * fh * fw + 16 * R + 4 * R * w['pool'] ** 2 * w['channels']
+    return b_prop, b_roi
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured'
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, 'fallback'
+
+
+def make_batch(w, first_index, with_features=True):
+    imgs = [syn.c4_image(w['cfg'], first_index + i, w['image_hw'], w['stride'], w['channels'], with_features)
+            for i in range(w['batch'])]
+    out = dict(anchors=imgs[0]['anchors'], deltas=np.stack([im['deltas'] for im in imgs]),
+               scores=np.stack([im['scores'] for im in imgs]), feat_hw=imgs[0]['feat_hw'])
+    if with_features:
+        out['feat'] = np.stack([im['feat'] for im in imgs])
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arm
+def load_cpu_oracle():
+    """The oracle's C twin (oracle/c): allowed here only for the cpu_baseline / --impl reference legs."""
+    so = os.path.join(ROOT, 'oracle', 'c', 'libboxpath_ref.so')
+    if not os.path.exists(so):
+        import subprocess
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle', 'c')])
+    lib = ctypes.CDLL(so)
+    lib.orc_c4_proposal_roi.restype = ctypes.c_int
+    lib.orc_c4_proposal_roi.argtypes = ([ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_void_p] * 2 +
+                                        [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                              ctypes.c_int] + [ctypes.c_void_p] * 4)
+    lib.orc_max_threads.restype = ctypes.c_int
+    return lib
+
+
+def cpu_step_fn(w, batch_np, n_images):
+    lib = load_cpu_oracle()
+    n = batch_np['anchors'].shape[0]
+    fh, fw = batch_np['feat_hw']
+    post, P, c = w['post_nms'], w['pool'], w['channels']
+    b = n_images
+    means, stds = np.zeros(4, np.float32), np.ones(4, np.float32)
+    o_rois = np.zeros((b, post, 4), np.float32); o_idx = np.zeros((b, post), np.int32)
+    o_cnt = np.zeros(b, np.int32); o_feat = np.zeros((b * post, P, P, c), np.float32)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    deltas = np.ascontiguousarray(batch_np['deltas'][:b]); scores = np.ascontiguousarray(batch_np['scores'][:b])
+    feat = np.ascontiguousarray(batch_np['feat'][:b])
+
+    def step():
+        rc = lib.orc_c4_proposal_roi(ptr(batch_np['anchors']), ptr(deltas), ptr(scores), ptr(feat), b, n, fh, fw, c,
+                                     ptr(means), ptr(stds), w['image_hw'][0], w['image_hw'][1], w['pre_nms'], post,
+                                     w['iou_thr'], float(w['stride']), P, 0, ptr(o_rois), ptr(o_idx), ptr(o_cnt), ptr(o_feat))
+        assert rc == 0
+    return step, lib.orc_max_threads(), (o_rois, o_idx, o_cnt, o_feat)
+
+
+def run_cpu_baseline(w, batch_np, budget_s=12.0):
+    step, cores, _ = cpu_step_fn(w, batch_np, w['batch'])
+    step()  # warm
+    t0 = time.perf_counter(); reps = 0
+    while True:
+        step(); reps += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or reps >= 50:
+            break
+    return dict(value=round(reps * w['batch'] / el, 2), unit=UNIT, cores=cores, kind='port',
+                sample='%d passes over one %d-image batch of the same workload (%.1f s), oracle C twin: '
+                       'single-thread NMS per image, crop_and_resize sharded over boxes with OpenMP'
+                       % (reps, w['batch'], el))
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the CPU restatement of the reference's path (the real TF path is not installable: SURVEY §8c),
+    all host threads, same workload/metric.  Rank 0 only."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    w = WORKLOAD
+    batch_np = make_batch(w, 0)
+    n_img = w['batch']
+    step, cores, _ = cpu_step_fn(w, batch_np, n_img)
+    t0 = time.perf_counter(); step(); one = time.perf_counter() - t0
+    if one * (args.steps + args.warmup) > 240.0:          # keep the whole run within a few minutes
+        n_img = max(1, int(n_img * 240.0 / (one * (args.steps + args.warmup))))
+        step, cores, _ = cpu_step_fn(w, batch_np, n_img)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    val = args.steps * n_img / el
+    sample = '%d steps x %d images of the workload batch per step' % (args.steps, n_img)
+    line = dict(metric=METRIC, value=round(val, 2), unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=round(1e3 * el / args.steps, 3), higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic', impl='reference',
+                config=dict(workload=w['name'], images_per_step=n_img,
+                            note='CPU restatement of the reference TF ops (oracle C twin); TensorFlow itself is not installable here'),
+                cpu_baseline=dict(value=round(val, 2), unit=UNIT, cores=cores, kind='port', sample=sample),
+                e2e=dict(value=round(val, 2), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.stop_flag = index, period, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: 'hw_slowdown',
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonSwPowerCap: 'sw_power_cap',
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: 'hw_power_brake'}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=[], samples=0)
+        return dict(sm_mhz=int(statistics.median(self.samples)), sm_max_mhz=self.max_mhz,
+                    reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+# ----------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tf_eager_object_detection_b200 import _lib, ops
+
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    w = WORKLOAD
+    B, post, P, C = w['batch'], w['post_nms'], w['pool'], w['channels']
+    lib = _lib.load()
+
+    # ---- inputs: NBUF distinct batches resident in HBM, rotated so no step re-reads the previous step's inputs from L2
+    NBUF = 4
+    host_batches = [make_batch(w, rank * 10000 + k * B) for k in range(NBUF)]
+    n = host_batches[0]['anchors'].shape[0]
+    fh, fw = host_batches[0]['feat_hw']
+    anchors = torch.as_tensor(host_batches[0]['anchors']).to(dev)
+    d_in = [dict(deltas=torch.as_tensor(hb['deltas']).to(dev), scores=torch.as_tensor(hb['scores']).to(dev),
+                 feat=torch.as_tensor(hb['feat']).to(dev)) for hb in host_batches]
+    NSTREAM = max(1, args.streams)
+    outs = [(torch.empty((B, post, 4), device=dev), torch.empty((B, post), dtype=torch.int32, device=dev),
+             torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B * post, P, P, C), device=dev))
+            for _ in range(NSTREAM)]
+    params = ops.proposal_params(w['image_hw'], post, w['iou_thr'], pre_nms_top_k=w['pre_nms'])
+    streams = [torch.cuda.Stream(dev) for _ in range(NSTREAM)]
+    handles = []
+    for _ in range(NSTREAM):
+        hh = ctypes.c_void_p()
+        _lib.check(lib.bx_create(local, ctypes.byref(hh)))
+        handles.append(hh)
+
+    def launch(step):
+        s = step % NSTREAM
+        din, o = d_in[step % NBUF], outs[s]
+        _lib.check(lib.bx_c4_proposal_roi(handles[s], anchors.data_ptr(), din['deltas'].data_ptr(),
+                                          din['scores'].data_ptr(), din['feat'].data_ptr(), B, n, fh, fw, C,
+                                          ctypes.byref(params), float(w['stride']), P, _lib.POOL_NONE, o[0].data_ptr(),
+                                          o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(),
+                                          ctypes.c_void_p(streams[s].cuda_stream)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    main = torch.cuda.current_stream(dev)
+
+    def timed(nsteps, first):
+        """K steps round-robin over the streams; device time from a start event (main stream, all streams wait on it)
+        to an end event recorded after every stream has been joined back into the main stream."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(main)
+        for s in streams:
+            s.wait_event(e0)
+        for k in range(nsteps):
+            launch(first + k)
+        for s in streams:
+            ev = torch.cuda.Event(); ev.record(s); main.wait_event(ev)
+        e1.record(main)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    launches0 = [int(lib.bx_launch_count(hh)) for hh in handles]
+    timed(max(3, args.warmup), 0)                       # warm-up (>= 3 steps)
+    launches_w = [int(lib.bx_launch_count(hh)) for hh in handles]
+    for hh in handles:
+        _lib.check(lib.bx_profile_roi(hh, 1, args.steps // NSTREAM + 2))
+    sampler = ClockSampler(local); sampler.start()
+    ms = timed(args.steps, max(3, args.warmup))
+    sampler.stop_flag = True; sampler.join()
+    launches_t = [int(lib.bx_launch_count(hh)) for hh in handles]
+    gpu_launches = sum(launches_t) - sum(launches_w)
+    # dominant kernel: per-launch CUDA-event durations recorded on the launch streams inside the timed region
+    roi_ms = []
+    for hh in handles:
+        buf = (ctypes.c_float * (args.steps + 4))(); cnt = ctypes.c_int()
+        _lib.check(lib.bx_profile_read(hh, buf, args.steps + 4, ctypes.byref(cnt)))
+        roi_ms += list(buf[:cnt.value])
+        _lib.check(lib.bx_profile_roi(hh, 0, 0))
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.steps * B / (ms_max * 1e-3)
+
+    # ---- sanity inside the bench: every image filled its quota (otherwise the work measured is not the workload)
+    for o in outs:
+        assert bool((o[2] == post).all()), 'a step kept fewer than post_nms proposals'
+
+    # ---- e2e: the public Python API with HOST (pinned) buffers; H2D inputs + D2H outputs inside the timed region
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    hb = host_batches[0]
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    h_in = [dict(deltas=pin(b_['deltas']), scores=pin(b_['scores']), feat=pin(b_['feat'])) for b_ in host_batches[:2]]
+    h_out = (torch.empty((B, post, 4)).pin_memory(), torch.empty((B, post), dtype=torch.int32).pin_memory(),
+             torch.empty((B,), dtype=torch.int32).pin_memory(), torch.empty((B * post, P, P, C)).pin_memory())
+    h2d = sum(t_.numel() * t_.element_size() for t_ in h_in[0].values())
+    d2h = sum(t_.numel() * t_.element_size() for t_ in h_out)
+
+    def e2e_step(k):
+        hi = h_in[k % 2]
+        ops.c4_proposal_roi_host(anchors, hi['deltas'], hi['scores'], hi['feat'], w['image_hw'], post, h_out,
+                                 stride=float(w['stride']), pool_size=P, pre_nms_top_k=w['pre_nms'],
+                                 iou_threshold=w['iou_thr'])
+    for k in range(2):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    assert int(h_out[2].min()) == post
+    t = torch.tensor([max(e2e_ms, 0.0)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps * B / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        b_prop, b_roi = algorithmic_bytes(w, n, fh, fw)
+        peak, which = hbm_peak()
+        roi_avg_ms = sum(roi_ms) / max(1, len(roi_ms))
+        roi_bytes = B * b_roi                           # one launch pools the whole batch
+        achieved = roi_bytes / (roi_avg_ms * 1e-3) / 1e9 if roi_avg_ms > 0 else 0.0
+        step_bytes = B * (b_prop + b_roi)
+        cpu = run_cpu_baseline(w, host_batches[0])
+        line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps,
+                    warmup=max(3, args.warmup), ms_per_step=round(ms_max / args.steps, 5), higher_is_better=True,
+                    scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                    config=dict(workload=w['name'], images_per_step_per_gpu=B, streams=NSTREAM,
+                                l2='working set %.0f MB/step (inputs rotate over %d batches, outputs %.0f MB) > 126 MB L2'
+                                   % (step_bytes / 1e6, NBUF, B * post * P * P * C * 4 / 1e6),
+                                algorithmic_bytes_per_image=b_prop + b_roi,
+                                composite_hbm_frac=round(step_bytes * args.steps / (ms_max * 1e-3) / 1e9 / peak, 4)),
+                    roofline=dict(bound='hbm', kernel='roi_pool_kernel', achieved=round(achieved, 1), peak=peak,
+                                  peak_source=which, unit='GB/s', frac=round(achieved / peak, 4), traffic=None,
+                                  launches_timed=len(roi_ms), avg_launch_ms=round(roi_avg_ms, 5),
+                                  algorithmic_bytes_per_launch=roi_bytes),
+                    cpu_baseline=cpu,
+                    e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             steps=e2e_steps, ms_per_step=round(e2e_ms / e2e_steps, 3), wall_ms_per_step=round(wall_ms / e2e_steps, 3),
+                             api='ops.c4_proposal_roi_host -> bx_c4_proposal_roi_host (pinned host buffers)'),
+                    gpu_launches=gpu_launches, clocks=sampler.summary())
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=1000)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--streams', type=int, default=2, help='steps are issued round-robin over this many CUDA streams')
+    ap.add_argument('--e2e-steps', type=int, default=20)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

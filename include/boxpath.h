@@ -195,6 +195,12 @@ int bx_c4_proposal_roi_host(bx_handle* h, const float* anchors_dev, const float*
 /* number of kernels launched by this handle since creation (bench.py "gpu_launches") */
 long long bx_launch_count(const bx_handle* h);
 
+/* Measurement support (bench.py roofline leg): when enabled, every RoI-pooling launch of this handle is bracketed by a
+ * cudaEvent pair recorded on the launch stream (up to `capacity` launches, then recording stops).
+ * bx_profile_read synchronises the recorded events and returns their durations in milliseconds. */
+int bx_profile_roi(bx_handle* h, int enable, int capacity);
+int bx_profile_read(bx_handle* h, float* ms_out, int max_records, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,8 @@ SIGNATURES = {
     'bx_create': (c_int, [c_int, POINTER(c_void_p)]),
     'bx_destroy': (c_int, [c_void_p]),
     'bx_launch_count': (c_longlong, [c_void_p]),
+    'bx_profile_roi': (c_int, [c_void_p, c_int, c_int]),
+    'bx_profile_read': (c_int, [c_void_p, POINTER(c_float), c_int, POINTER(c_int)]),
     'bx_dlpack_data': (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_int64), c_int, POINTER(c_void_p)]),
     'bx_decode_clip': (c_int, [c_void_p, P, c_int, P, c_int, c_int, F4, F4, c_int, c_int, P, c_void_p]),
     'bx_encode': (c_int, [c_void_p, P, P, c_int, F4, F4, P, c_void_p]),

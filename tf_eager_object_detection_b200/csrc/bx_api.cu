@@ -66,11 +66,41 @@ extern "C" int bx_destroy(bx_handle* h) {
   cudaSetDevice(h->device);
   if (h->ws) cudaFree(h->ws);
   if (h->stage) cudaFree(h->stage);
+  bx_profile_roi(h, 0, 0);
   delete h;
   return BX_OK;
 }
 
 extern "C" long long bx_launch_count(const bx_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int bx_profile_roi(bx_handle* h, int enable, int capacity) {
+  BX_REQUIRE(h, BX_ERR_INVALID, "bx_profile_roi: NULL handle");
+  if (h->prof_ev) {
+    for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
+    delete[] h->prof_ev;
+    h->prof_ev = nullptr;
+  }
+  h->prof_cap = h->prof_n = h->prof_on = 0;
+  if (!enable || capacity <= 0) return BX_OK;
+  BX_CUDA(cudaSetDevice(h->device));
+  h->prof_ev = new cudaEvent_t[2 * capacity];
+  for (int i = 0; i < 2 * capacity; ++i) BX_CUDA(cudaEventCreate(&h->prof_ev[i]));
+  h->prof_cap = capacity;
+  h->prof_on = 1;
+  return BX_OK;
+}
+
+extern "C" int bx_profile_read(bx_handle* h, float* ms_out, int max_records, int* n_out) {
+  BX_REQUIRE(h && ms_out && n_out, BX_ERR_INVALID, "bx_profile_read: NULL argument");
+  const int n = h->prof_n < max_records ? h->prof_n : max_records;
+  for (int i = 0; i < n; ++i) {
+    BX_CUDA(cudaEventSynchronize(h->prof_ev[2 * i + 1]));
+    BX_CUDA(cudaEventElapsedTime(&ms_out[i], h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+  }
+  *n_out = n;
+  h->prof_n = 0;
+  return BX_OK;
+}
 
 extern "C" int bx_dlpack_data(const void* dltensor, int device, int dtype_code, int bits, int ndim,
                               const int64_t* shape, int align_bytes, void** out_data) {

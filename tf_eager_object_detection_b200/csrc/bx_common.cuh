@@ -18,6 +18,11 @@ struct bx_handle {
   void* stage;           // device staging area of the *_host entry points
   size_t stage_bytes;
   long long launches;
+  // optional event bracketing of the RoI-pooling kernel (bx_profile_roi)
+  cudaEvent_t* prof_ev;   // 2 * prof_cap events
+  int prof_cap;
+  int prof_n;
+  int prof_on;
 };
 
 void bx_set_error(const char* fmt, ...);

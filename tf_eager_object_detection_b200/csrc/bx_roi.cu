@@ -6,67 +6,11 @@
 // Layout: features NHWC fp32, so the channel axis is the coalesced / float4 axis; one CTA produces one output row
 // (roi, py): P pixels x C channels, written once, contiguous.  Sample coordinates follow the TF r1.13 kernel's fp32
 // op order: in_y = y1*(h-1) + y*((y2-y1)*(h-1)/(Q-1)); a sample outside [0,h-1]x[0,w-1] is 0.
-#include "bx_common.cuh"
+#include "bx_roi.cuh"
+
+using namespace bxroi;
 
 namespace {
-
-constexpr int kMaxLevels = 8;
-constexpr int kMaxQ = 64;  // max crop size (2*pool_size)
-
-struct LevelFeat {
-  const float* feat;  // [b,fh,fw,c]
-  int fh, fw;
-};
-
-struct RoiArgs {
-  LevelFeat lv[kMaxLevels];
-  int n_levels;
-  const float4* rois;     // [r] image coordinates (or normalised y1,x1,y2,x2 for mode RAW)
-  const int* box_ind;     // [r] or null
-  const int* roi_counts;  // [b] or null
-  const int* order;       // [r] output row j reads roi order[j] (FPN level-major) or null (identity)
-  const int* level;       // [r] absolute level per roi or null (level 0)
-  int level_base;         // min_level: level[src] - level_base indexes lv[]
-  int r, b, c;
-  int rois_per_image;     // r / b when roi_counts is given
-  int mode;               // bx_roi_mode or 3 = RAW normalised boxes
-  int P;                  // output size
-  int Q;                  // crop size (P or 2P)
-  float stride;
-  float image_h, image_w;
-  float extrapolation;
-  float* out;             // [r,P,P,c]
-};
-
-struct Axis {
-  int lo, hi;   // tap indices (already mapped to the un-padded map)
-  float lerp;
-  int valid;
-};
-
-// coordinate of crop sample `s` along one axis, TF op order.  n1,n2: normalised box ends; dim: (padded) map size.
-__device__ __forceinline__ Axis sample_axis(float n1, float n2, int s, int Q, int dim, int pad) {
-  Axis a;
-  const float dm1 = static_cast<float>(dim - 1);
-  float in;
-  if (Q > 1) {
-    const float scale = (n2 - n1) * dm1 / static_cast<float>(Q - 1);
-    in = n1 * dm1 + static_cast<float>(s) * scale;
-  } else {
-    in = 0.5f * (n1 + n2) * dm1;
-  }
-  a.valid = !(in < 0.0f || in > dm1);
-  const float lo = floorf(in), hi = ceilf(in);
-  a.lerp = in - lo;
-  int ilo = static_cast<int>(lo), ihi = static_cast<int>(hi);
-  if (pad) {  // SYMMETRIC pad by 1 (roi_pooling.py:100): padded index p -> original clamp(p-1, 0, dim-3)
-    ilo = min(max(ilo - 1, 0), dim - 3);
-    ihi = min(max(ihi - 1, 0), dim - 3);
-  }
-  a.lo = ilo;
-  a.hi = ihi;
-  return a;
-}
 
 template <int POOL, typename VecT>
 __global__ void __launch_bounds__(256) roi_pool_kernel(const RoiArgs a) {
@@ -99,37 +43,9 @@ __global__ void __launch_bounds__(256) roi_pool_kernel(const RoiArgs a) {
     }
     const float4 roi = a.rois[src];
     const int fh = a.lv[lvl].fh, fw = a.lv[lvl].fw;
-    float y1n, x1n, y2n, x2n;
-    int dimy = fh, dimx = fw, pad = 0;
-    if (a.mode == BX_ROI_STRIDE_NORM) {           // roi_pooling.py:64-74
-      const float fy = static_cast<float>(fh - 1), fx = static_cast<float>(fw - 1);
-      y1n = (roi.y / a.stride) / fy;
-      x1n = (roi.x / a.stride) / fx;
-      y2n = (roi.w / a.stride) / fy;
-      x2n = (roi.z / a.stride) / fx;
-    } else if (a.mode == BX_ROI_IMAGE_NORM) {     // roi_pooling.py:26-35
-      y1n = roi.y / a.image_h;
-      x1n = roi.x / a.image_w;
-      y2n = roi.w / a.image_h;
-      x2n = roi.z / a.image_w;
-    } else if (a.mode == BX_ROI_ALIGN_PAD) {      // roi_pooling.py:175,101,103-130
-      pad = 1;
-      dimy = fh + 2;
-      dimx = fw + 2;
-      const float x0 = roi.x / a.stride + 1.0f, y0 = roi.y / a.stride + 1.0f;
-      const float x1 = roi.z / a.stride + 1.0f, y1 = roi.w / a.stride + 1.0f;
-      const float qf = static_cast<float>(Q);
-      const float sw = (x1 - x0) / qf, sh = (y1 - y0) / qf;
-      const float ih = static_cast<float>(dimy - 1), iw = static_cast<float>(dimx - 1);
-      x1n = (x0 + sw / 2.0f - 0.5f) / iw;
-      y1n = (y0 + sh / 2.0f - 0.5f) / ih;
-      const float nw = sw * static_cast<float>(Q - 1) / iw;
-      const float nh = sh * static_cast<float>(Q - 1) / ih;
-      x2n = x1n + nw;
-      y2n = y1n + nh;
-    } else {                                      // RAW: boxes are (y1,x1,y2,x2) normalised
-      y1n = roi.x; x1n = roi.y; y2n = roi.z; x2n = roi.w;
-    }
+    const NormBox nb = roi_norm_box(a, roi, fh, fw);
+    const float y1n = nb.y1, x1n = nb.x1, y2n = nb.y2, x2n = nb.x2;
+    const int dimy = nb.dimy, dimx = nb.dimx, pad = nb.pad;
     if (tid < Q) ax_x[tid] = sample_axis(x1n, x2n, tid, Q, dimx, pad);
     else if (tid - Q < S) ax_y[tid - Q] = sample_axis(y1n, y2n, py * S + (tid - Q), Q, dimy, pad);
   }
@@ -205,9 +121,22 @@ int launch_roi_v(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
 
 int launch_roi(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
   if (a.r == 0) return BX_OK;
-  bool vec = (a.c % 4 == 0) && bx_aligned(a.out, 16);
-  for (int l = 0; l < a.n_levels; ++l) vec = vec && bx_aligned(a.lv[l].feat, 16);
-  return vec ? launch_roi_v<float4>(h, a, pool, st) : launch_roi_v<float>(h, a, pool, st);
+  const bool prof = h->prof_on && h->prof_n < h->prof_cap;
+  if (prof) BX_CUDA(cudaEventRecord(h->prof_ev[2 * h->prof_n], st));
+  int used = 0;
+  int rc = roi_band_launch(h, a, pool, st, &used);   // TMA band-stationary kernel when the shape allows it
+  if (rc) return rc;
+  if (!used) {
+    bool vec = (a.c % 4 == 0) && bx_aligned(a.out, 16);
+    for (int l = 0; l < a.n_levels; ++l) vec = vec && bx_aligned(a.lv[l].feat, 16);
+    rc = vec ? launch_roi_v<float4>(h, a, pool, st) : launch_roi_v<float>(h, a, pool, st);
+    if (rc) return rc;
+  }
+  if (prof) {
+    BX_CUDA(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], st));
+    h->prof_n++;
+  }
+  return BX_OK;
 }
 
 // ---- FPN level assignment (base_fpn_model.py:303-324): single CTA, stable level-major order
