@@ -32,6 +32,7 @@ static int reserve(void** p, size_t* cur, size_t bytes) {
 
 int bx_ws_reserve(bx_handle* h, size_t bytes) { return reserve(&h->ws, &h->ws_bytes, bytes); }
 int bx_stage_reserve(bx_handle* h, size_t bytes) { return reserve(&h->stage, &h->stage_bytes, bytes); }
+int bx_plan_reserve(bx_handle* h, size_t bytes) { return reserve(&h->plan, &h->plan_bytes, bytes); }
 
 extern "C" int bx_version(void) { return BX_VERSION; }
 extern "C" const char* bx_last_error(void) { return g_err; }
@@ -66,6 +67,7 @@ extern "C" int bx_destroy(bx_handle* h) {
   cudaSetDevice(h->device);
   if (h->ws) cudaFree(h->ws);
   if (h->stage) cudaFree(h->stage);
+  if (h->plan) cudaFree(h->plan);
   bx_profile_roi(h, 0, 0);
   delete h;
   return BX_OK;

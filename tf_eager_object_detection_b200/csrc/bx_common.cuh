@@ -17,6 +17,8 @@ struct bx_handle {
   size_t ws_bytes;
   void* stage;           // device staging area of the *_host entry points
   size_t stage_bytes;
+  void* plan;            // RoI-pooling plan blocks (bx_roi_band.cu)
+  size_t plan_bytes;
   long long launches;
   // optional event bracketing of the RoI-pooling kernel (bx_profile_roi)
   cudaEvent_t* prof_ev;   // 2 * prof_cap events
@@ -28,6 +30,7 @@ struct bx_handle {
 void bx_set_error(const char* fmt, ...);
 int bx_ws_reserve(bx_handle* h, size_t bytes);       // ensure h->ws has >= bytes (may cudaMalloc; not in steady state)
 int bx_stage_reserve(bx_handle* h, size_t bytes);
+int bx_plan_reserve(bx_handle* h, size_t bytes);
 
 #define BX_REQUIRE(cond, code, ...)  \
   do {                               \
