@@ -223,6 +223,10 @@ def run_ours(args):
         _lib.check(lib.bx_create(local, ctypes.byref(hh)))
         handles.append(hh)
 
+    # N > 1: the only collective of the path — all-gather of the per-image detection records (kept boxes + counts)
+    gathered = [(torch.empty((world * B, post, 4), device=dev), torch.empty((world * B,), dtype=torch.int32, device=dev))
+                for _ in range(NSTREAM)] if world > 1 else None
+
     def launch(step):
         s = step % NSTREAM
         din, o = d_in[step % NBUF], outs[s]
@@ -231,6 +235,10 @@ def run_ours(args):
                                           ctypes.byref(params), float(w['stride']), P, _lib.POOL_NONE, o[0].data_ptr(),
                                           o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(),
                                           ctypes.c_void_p(streams[s].cuda_stream)))
+        if world > 1:
+            with torch.cuda.stream(streams[s]):
+                dist.all_gather_into_tensor(gathered[s][0], o[0])
+                dist.all_gather_into_tensor(gathered[s][1], o[2])
 
     def barrier():
         if world > 1:
@@ -327,6 +335,8 @@ def run_ours(args):
                     warmup=max(3, args.warmup), ms_per_step=round(ms_max / args.steps, 5), higher_is_better=True,
                     scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                     config=dict(workload=w['name'], images_per_step_per_gpu=B, streams=NSTREAM,
+                                parallelism='images sharded over GPUs, no data-path collective; NCCL all-gather of the '
+                                            'per-image detection records each step' if world > 1 else 'single GPU',
                                 l2='working set %.0f MB/step (inputs rotate over %d batches, outputs %.0f MB) > 126 MB L2'
                                    % (step_bytes / 1e6, NBUF, B * post * P * P * C * 4 / 1e6),
                                 algorithmic_bytes_per_image=b_prop + b_roi,
