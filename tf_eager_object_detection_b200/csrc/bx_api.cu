@@ -58,6 +58,7 @@ extern "C" int bx_create(int device, bx_handle** out) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   h->smem_optin = prop.sharedMemPerBlockOptin;
+  h->smem_sm = prop.sharedMemPerMultiprocessor;
   *out = h;
   return BX_OK;
 }
@@ -74,6 +75,16 @@ extern "C" int bx_destroy(bx_handle* h) {
 }
 
 extern "C" long long bx_launch_count(const bx_handle* h) { return h ? h->launches : 0; }
+
+// measurement aid (not in the public header): copy the BX_BAND_DEBUG timestamps of the last band launch to the host
+extern "C" long long bx_debug_band_dump(bx_handle* h, unsigned long long* out, long long max_ctas, int* info) {
+  if (!h || !h->dbg_ptr) return 0;
+  const long long n = h->dbg_count < max_ctas ? h->dbg_count : max_ctas;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, h->dbg_ptr, static_cast<size_t>(n) * 32, cudaMemcpyDeviceToHost);
+  for (int i = 0; i < 4; ++i) info[i] = h->dbg_info[i];
+  return n;
+}
 
 extern "C" int bx_profile_roi(bx_handle* h, int enable, int capacity) {
   BX_REQUIRE(h, BX_ERR_INVALID, "bx_profile_roi: NULL handle");

@@ -13,12 +13,16 @@ struct bx_handle {
   int device;
   int num_sms;
   size_t smem_optin;     // max dynamic shared memory per block
+  size_t smem_sm;        // shared memory per SM
   void* ws;              // device workspace (grown on demand, stream-ordered by the caller's stream)
   size_t ws_bytes;
   void* stage;           // device staging area of the *_host entry points
   size_t stage_bytes;
   void* plan;            // RoI-pooling plan blocks (bx_roi_band.cu)
   size_t plan_bytes;
+  unsigned long long* dbg_ptr;   // BX_BAND_DEBUG: device timestamps of the last band launch
+  long long dbg_count;
+  int dbg_info[4];
   long long launches;
   // optional event bracketing of the RoI-pooling kernel (bx_profile_roi)
   cudaEvent_t* prof_ev;   // 2 * prof_cap events

@@ -49,8 +49,13 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const
   const float i1 = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.0f);
   const float inter = i0 * i1;
   if (inter <= 0.0f) return false;  // iou == 0, never > thr for thr in [0,1]
-  const float iou = inter / (area_a + area_b - inter);
-  return iou > thr;
+  const float uni = area_a + area_b - inter;
+  // decide `inter / uni > thr` without the division when the quotient is at least 2e-6 (relative) away from thr: the
+  // correctly rounded quotient lies within 2^-24 of inter/uni, and thr*uni, *(1 +- 2e-6) round within 2^-23 each
+  const float p = thr * uni;
+  if (inter > p * 1.000002f) return true;
+  if (inter < p * 0.999998f) return false;
+  return inter / uni > thr;         // TF's exact test (fp32 division, strict >)
 }
 
 __device__ __forceinline__ float4 normalise(const float4 b) {
@@ -146,8 +151,12 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   const uint64_t global_lo = static_cast<uint64_t>(sh->kmin) << 32;
   int consumed = 0;
 
+  // first round: a chunk about 1.5x the quota (NMS usually fills it from there); later rounds take full chunks
+  int round_cap = 512;
+  while (round_cap < kChunk && round_cap < a.post_nms + (a.post_nms >> 1)) round_cap <<= 1;
   while (consumed < limit && sh->kept < a.post_nms) {
-    const int want = min(kChunk, limit - consumed);
+    const int want = min(round_cap, limit - consumed);
+    round_cap = kChunk;
     const uint64_t prev = sh->prev;
 
     // ---- select: threshold T with  #{v : T <= v < prev} in [1, want]  (as large as the bins allow)
@@ -334,19 +343,37 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         if (part == 0) rowmask[i] = bits;
       }
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
+        // greedy resolve of the tile by warp 0, every lane redundantly: the 64 mask rows are transposed into registers
+        // with independent shuffles (rows 0-31 then 32-63, 32 columns at a time), so the dependent chain is register-only
+        const uint64_t my_lo = rowmask[lane], my_hi = rowmask[lane + 32];
         uint64_t removed = sh->sup;
-        uint64_t keep = 0ull;
+        if (tn < 64) removed |= ~((1ull << tn) - 1ull);
         int room = a.post_nms - kept;
-        for (int i = 0; i < tn && room > 0; ++i) {
-          if (!((removed >> i) & 1ull)) {
-            keep |= (1ull << i);
-            removed |= rowmask[i];
-            --room;
-          }
+        uint32_t rem = static_cast<uint32_t>(removed), keep_lo = 0u, keep_hi = 0u;
+        uint32_t rows[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rows[i] = __shfl_sync(0xFFFFFFFFu, static_cast<uint32_t>(my_lo), i);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool k = !((rem >> i) & 1u) && room > 0;
+          if (k) { keep_lo |= 1u << i; rem |= rows[i]; --room; }
         }
-        sh->keepmask = keep;
-        sh->kept = kept + __popcll(keep);
+        // columns 32-63 suppressed by the kept rows 0-31
+        const uint32_t contrib = ((keep_lo >> lane) & 1u) ? static_cast<uint32_t>(my_lo >> 32) : 0u;
+        rem = static_cast<uint32_t>(removed >> 32) | __reduce_or_sync(0xFFFFFFFFu, contrib);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rows[i] = __shfl_sync(0xFFFFFFFFu, static_cast<uint32_t>(my_hi >> 32), i);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool k = !((rem >> i) & 1u) && room > 0;
+          if (k) { keep_hi |= 1u << i; rem |= rows[i]; --room; }
+        }
+        if (lane == 0) {
+          const uint64_t keep = static_cast<uint64_t>(keep_lo) | (static_cast<uint64_t>(keep_hi) << 32);
+          sh->keepmask = keep;
+          sh->kept = kept + __popcll(keep);
+        }
       }
       __syncthreads();
       if (tid < tn) {

@@ -16,20 +16,21 @@
 namespace bxroi {
 namespace {
 
-constexpr int kThreads = 1024;
 constexpr int kSlice = 32;          // channels per CTA (128 B per pixel)
-constexpr int kBoxRows = 256;       // pixels per TMA box
-constexpr int kBoxBytes = kBoxRows * kSlice * 4;
+constexpr int kBoxRows = 256;       // max pixels per TMA box
 
 struct BandArgs {
   RoiArgs r;
   int rows_per_band, n_bands, n_slices;
-  int chunk;      // rois per plan block
-  int n_chunks;   // plan blocks per (image, band)
-  int nbox;       // TMA boxes per band
-  int scan_all;   // 1: rois of any image may be anywhere (box_ind given) -> every block scans every roi
-  unsigned char* plan;   // [b, n_bands, n_chunks] plan blocks (global workspace)
+  int cap;          // rois per plan block (shared-memory table capacity of the band kernel)
+  int n_blocks_max; // plan blocks reserved per (image, band)
+  int nbox;         // TMA boxes per band
+  int box_rows;     // pixels per TMA box (<= 256)
+  int band_bytes;   // nbox * box_rows * 128: the all-zero row starts here
+  int scan_all;     // 1: rois of any image may be anywhere (box_ind given) -> every plan CTA scans every roi
+  unsigned char* plan;   // [b, n_bands, n_blocks_max] plan blocks (global workspace)
   float neg_zero;        // -0.0f at run time: addend that turns fma.rn.f32x2 into an exact, non-contractible multiply
+  unsigned long long* dbg;   // optional [grid,4] timestamps (globaltimer ns: start, band ready, done; smid) — BX_BAND_DEBUG
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -63,30 +64,30 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 
 // ---------------------------------------------------------------------------------------------------------------
 // Plan: everything about the crop geometry that does not depend on the channel slice is computed once per
-// (image, band, roi chunk) by roi_plan_kernel and stored in global memory as one contiguous "plan block"; each band CTA
-// pulls its block into shared memory with one bulk copy (cp.async.bulk) next to the TMA tile loads of the band.
+// (image, band) by roi_plan_kernel and stored in global memory as contiguous "plan blocks" of `cap` rois; only the rois
+// that own output rows in the band are listed (compacted).  Each band CTA pulls a block into shared memory with one
+// bulk copy (cp.async.bulk) next to the TMA tile loads of the band.
 //
-// Plan block layout (byte offsets, chunk = rois per block, Q = crop size):
-//   [0]                      int   n_runs  (+ padding to 16 B)
-//   [16]                     u64   xval [chunk]     validity bit per sample column
-//   [.. ]                    uint2 xtab [chunk*Q]   (lo_off | hi_off << 16: byte offsets of the tap columns in a band row, lerp_x)
-//   [.. ]                    uint2 ytab [chunk*Q]   (a | in_band << 15 | b << 16 | valid << 31, lerp_y): in_band: a, b = offsets
-//                                                   (16 B units) of the top / bottom tap rows in the staged band (the zero row
-//                                                   when the sample is invalid); else absolute feature rows (pooled pairs only)
-//   [.. ]                    uint2 runs [4*chunk]   (roi_local | zero << 12 | all_x_valid << 13 | py_begin << 16 | py_end << 24,
-//                                                    offset of output pixel (roi, py_begin, 0) in float4 units from the first roi
-//                                                    of the block)
+// Plan block layout (byte offsets; Q = crop size):
+//   [0]   int n_runs ; [4] int n_blocks_used (block 0 only) ; padding to 16 B
+//   [16]  u64   xval [cap]      validity bit per sample column
+//   [..]  uint2 xtab [cap*Q]    (lo_off | hi_off << 16: byte offsets of the tap columns in a band row, lerp_x)
+//   [..]  uint2 ytab [cap*Q]    (a | in_band << 15 | b << 16 | valid << 31, lerp_y): in_band: a, b = offsets (16 B units) of
+//                               the top / bottom tap rows in the staged band (the zero row when the sample is invalid);
+//                               else absolute feature rows (pooled pairs only)
+//   [..]  uint2 runs [4*cap]    (slot | zero << 12 | all_x_valid << 13 | py_begin << 16 | py_end << 24,
+//                                offset of output pixel (roi, py_begin, 0) in float4 units from the image's first roi)
 struct PlanLayout {
   uint32_t off_xval, off_xtab, off_ytab, off_runs, bytes;
 };
 
-__host__ __device__ inline PlanLayout plan_layout(int chunk, int Q) {
+__host__ __device__ inline PlanLayout plan_layout(int cap, int Q) {
   PlanLayout L;
   L.off_xval = 16;
-  L.off_xtab = L.off_xval + 8u * chunk;
-  L.off_ytab = L.off_xtab + 8u * chunk * Q;
-  L.off_runs = L.off_ytab + 8u * chunk * Q;
-  L.bytes = (L.off_runs + 32u * chunk + 127u) & ~127u;
+  L.off_xtab = L.off_xval + 8u * cap;
+  L.off_ytab = L.off_xtab + 8u * cap * Q;
+  L.off_runs = L.off_ytab + 8u * cap * Q;
+  L.bytes = (L.off_runs + 32u * cap + 127u) & ~127u;
   return L;
 }
 
@@ -107,21 +108,22 @@ __device__ __forceinline__ void axis_from_par(float base, float scale, int s, in
 }
 
 constexpr int kPlanThreads = 512;
-constexpr int kPlanMaxChunk = 1024;
+constexpr int kPlanPass = 1024;      // rois examined per pass of the plan kernel
+constexpr int kPlanMaxBlocks = 64;
 
 template <int S>
 __global__ void __launch_bounds__(kPlanThreads) roi_plan_kernel(const BandArgs a) {
-  __shared__ float4 rpar[kPlanMaxChunk];
-  __shared__ uint32_t pym[kPlanMaxChunk];
-  __shared__ uint32_t xv_lo[kPlanMaxChunk], xv_hi[kPlanMaxChunk];
-  __shared__ unsigned char rflag[kPlanMaxChunk];
-  __shared__ int n_runs;
+  __shared__ float4 rpar[kPlanPass];
+  __shared__ uint32_t pym[kPlanPass];
+  __shared__ uint32_t xv_lo[kPlanPass], xv_hi[kPlanPass];
+  __shared__ uint32_t cidx[kPlanPass];
+  __shared__ unsigned char rflag[kPlanPass];
+  __shared__ int blk_runs[kPlanMaxBlocks];
+  __shared__ int total_j;
   const RoiArgs& r = a.r;
-  const int tid = threadIdx.x;
-  int u = blockIdx.x;
-  const int ch = u % a.n_chunks; u /= a.n_chunks;
-  const int band_i = u % a.n_bands;
-  const int img = u / a.n_bands;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int band_i = blockIdx.x % a.n_bands;
+  const int img = blockIdx.x / a.n_bands;
   const int P = r.P, Q = r.Q;
   const int fh = r.lv[0].fh, fw = r.lv[0].fw;
   const int r0 = band_i * a.rows_per_band;
@@ -130,118 +132,166 @@ __global__ void __launch_bounds__(kPlanThreads) roi_plan_kernel(const BandArgs a
   const int pad = (r.mode == BX_ROI_ALIGN_PAD) ? 1 : 0;
   const int dimy = fh + 2 * pad, dimx = fw + 2 * pad;
   const uint32_t row_bytes = static_cast<uint32_t>(fw) * (kSlice * 4);
-  const uint32_t zrow_off = static_cast<uint32_t>(a.nbox) * kBoxBytes;
-  const PlanLayout L = plan_layout(a.chunk, Q);
-  unsigned char* blk = a.plan + static_cast<size_t>(blockIdx.x) * L.bytes;
-  unsigned long long* g_xval = reinterpret_cast<unsigned long long*>(blk + L.off_xval);
-  uint2* g_xtab = reinterpret_cast<uint2*>(blk + L.off_xtab);
-  uint2* g_ytab = reinterpret_cast<uint2*>(blk + L.off_ytab);
-  uint2* g_runs = reinterpret_cast<uint2*>(blk + L.off_runs);
+  const uint32_t zrow_off = static_cast<uint32_t>(a.band_bytes);
+  const PlanLayout L = plan_layout(a.cap, Q);
+  unsigned char* blk0 = a.plan + static_cast<size_t>(blockIdx.x) * a.n_blocks_max * L.bytes;
 
   int g_begin = 0, g_end = r.r;
   if (!a.scan_all && r.roi_counts) {
     g_begin = img * r.rois_per_image;
     g_end = g_begin + r.rois_per_image;
   }
-  const int c0 = g_begin + ch * a.chunk;
-  const int nroi = max(0, min(a.chunk, g_end - c0));
-
-  // ---- per-roi crop parameters
-  for (int l = tid; l < nroi; l += kPlanThreads) {
-    const int g = c0 + l;
-    int rimg = 0;
-    uint32_t flag = 0;
-    if (r.roi_counts) {
-      rimg = g / r.rois_per_image;
-      if ((g % r.rois_per_image) >= r.roi_counts[rimg]) flag |= 2u;
-    } else if (r.box_ind) {
-      rimg = r.box_ind[g];
-    }
-    if (rimg == img) flag |= 1u;
-    else if (r.box_ind && (rimg < 0 || rimg >= r.b) && img == 0) flag |= 3u;   // bad box_ind: zero-filled by image 0
-    const NormBox nb = roi_norm_box(r, r.rois[g], fh, fw);
-    const float dmx = static_cast<float>(dimx - 1), dmy = static_cast<float>(dimy - 1);
-    float4 par;
-    if (Q > 1) {
-      par.x = nb.x1 * dmx;
-      par.y = (nb.x2 - nb.x1) * dmx / static_cast<float>(Q - 1);
-      par.z = nb.y1 * dmy;
-      par.w = (nb.y2 - nb.y1) * dmy / static_cast<float>(Q - 1);
-    } else {
-      par.x = 0.5f * (nb.x1 + nb.x2) * dmx;
-      par.y = 0.0f;
-      par.z = 0.5f * (nb.y1 + nb.y2) * dmy;
-      par.w = 0.0f;
-    }
-    rpar[l] = par;
-    pym[l] = 0u;
-    xv_lo[l] = 0u;
-    xv_hi[l] = 0u;
-    rflag[l] = static_cast<unsigned char>(flag);
-  }
-  if (tid == 0) n_runs = 0;
+  if (tid < kPlanMaxBlocks) blk_runs[tid] = 0;
+  if (tid == 0) total_j = 0;
   __syncthreads();
-  // ---- x / y sample tables, ownership of output rows
-  for (int idx = tid; idx < nroi * Q; idx += kPlanThreads) {
-    const int l = idx / Q, s = idx - l * Q;
-    const uint32_t flag = rflag[l];
-    if (!(flag & 1u)) continue;
-    const bool zero = flag & 2u;
-    const float4 par = rpar[l];
-    int lo, hi;
-    float lerp;
-    bool valid;
-    axis_from_par(par.x, par.y, s, dimx, pad, lo, hi, lerp, valid);
-    valid = valid && !zero;
-    g_xtab[idx] = make_uint2(valid ? (static_cast<uint32_t>(lo * (kSlice * 4)) | (static_cast<uint32_t>(hi * (kSlice * 4)) << 16)) : 0u,
-                             __float_as_uint(lerp));
-    if (valid) atomicOr(s < 32 ? &xv_lo[l] : &xv_hi[l], 1u << (s & 31));
-    axis_from_par(par.z, par.w, s, dimy, pad, lo, hi, lerp, valid);
-    valid = valid && !zero;
-    const bool inb = valid && (lo >= r0 && hi < r0 + rows_loaded);
-    uint32_t ya, yb;
-    if (inb) {
-      ya = (static_cast<uint32_t>(lo - r0) * row_bytes) >> 4;
-      yb = (static_cast<uint32_t>(hi - r0) * row_bytes) >> 4;
-    } else if (!valid) {
-      ya = yb = zrow_off >> 4;
-    } else {
-      ya = static_cast<uint32_t>(lo);
-      yb = static_cast<uint32_t>(hi);
+
+  for (int c0 = g_begin; c0 < g_end; c0 += kPlanPass) {
+    const int nroi = min(kPlanPass, g_end - c0);
+    // ---- per-roi crop parameters
+    for (int l = tid; l < nroi; l += kPlanThreads) {
+      const int g = c0 + l;
+      int rimg = 0;
+      uint32_t flag = 0;
+      if (r.roi_counts) {
+        rimg = g / r.rois_per_image;
+        if ((g % r.rois_per_image) >= r.roi_counts[rimg]) flag |= 2u;
+      } else if (r.box_ind) {
+        rimg = r.box_ind[g];
+      }
+      if (rimg == img) flag |= 1u;
+      else if (r.box_ind && (rimg < 0 || rimg >= r.b) && img == 0) flag |= 3u;   // bad box_ind: zero-filled by image 0
+      const NormBox nb = roi_norm_box(r, r.rois[g], fh, fw);
+      const float dmx = static_cast<float>(dimx - 1), dmy = static_cast<float>(dimy - 1);
+      float4 par;
+      if (Q > 1) {
+        par.x = nb.x1 * dmx;
+        par.y = (nb.x2 - nb.x1) * dmx / static_cast<float>(Q - 1);
+        par.z = nb.y1 * dmy;
+        par.w = (nb.y2 - nb.y1) * dmy / static_cast<float>(Q - 1);
+      } else {
+        par.x = 0.5f * (nb.x1 + nb.x2) * dmx;
+        par.y = 0.0f;
+        par.z = 0.5f * (nb.y1 + nb.y2) * dmy;
+        par.w = 0.0f;
+      }
+      rpar[l] = par;
+      pym[l] = 0u;
+      xv_lo[l] = 0u;
+      xv_hi[l] = 0u;
+      rflag[l] = static_cast<unsigned char>(flag);
     }
-    g_ytab[idx] = make_uint2(ya | ((inb || !valid) ? (1u << 15) : 0u) | (yb << 16) | (valid ? (1u << 31) : 0u),
-                             __float_as_uint(valid ? lerp : 0.0f));
-    // the band that owns output row py = s / S is the one holding the top tap row of its first valid sample row
-    if (S == 1 || (s & 1) == 0) {
-      int owner_row = valid ? lo : -1;
-      if (S == 2 && !valid) {
-        int lo2, hi2; float l2; bool v2;
-        axis_from_par(par.z, par.w, s + 1, dimy, pad, lo2, hi2, l2, v2);
-        if (v2 && !zero) owner_row = lo2;
+    __syncthreads();
+    // ---- ownership: the band that owns output row py is the one holding the top tap row of its first valid sample row
+    for (int idx = tid; idx < nroi * P; idx += kPlanThreads) {
+      const int l = idx / P, py = idx - l * P;
+      const uint32_t flag = rflag[l];
+      if (!(flag & 1u)) continue;
+      const bool zero = flag & 2u;
+      const float4 par = rpar[l];
+      int owner_row = -1;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        int lo, hi; float lerp; bool valid;
+        axis_from_par(par.z, par.w, py * S + s, dimy, pad, lo, hi, lerp, valid);
+        if (valid && !zero && owner_row < 0) owner_row = lo;
       }
       const int owner = owner_row < 0 ? 0 : min(owner_row / a.rows_per_band, a.n_bands - 1);
-      if (owner == band_i) atomicOr(&pym[l], 1u << (s / S));
+      if (owner == band_i) atomicOr(&pym[l], 1u << py);
+    }
+    __syncthreads();
+    // ---- compact the rois that own rows here (order within the plan is irrelevant: outputs are disjoint)
+    for (int l0 = 0; l0 < nroi; l0 += kPlanThreads) {
+      const int l = l0 + tid;
+      const bool has = (l < nroi) && pym[l] != 0u;
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, has);
+      if (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&total_j, __popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (has) cidx[l] = static_cast<uint32_t>(base + __popc(bal & ((1u << lane) - 1u)));
+      }
+    }
+    __syncthreads();
+    // ---- x / y sample tables of the listed rois
+    for (int idx = tid; idx < nroi * Q; idx += kPlanThreads) {
+      const int l = idx / Q, s = idx - l * Q;
+      if (pym[l] == 0u) continue;
+      const int j = cidx[l], bi = j / a.cap, slot = j - bi * a.cap;
+      if (bi >= a.n_blocks_max) continue;
+      unsigned char* blk = blk0 + static_cast<size_t>(bi) * L.bytes;
+      const bool zero = rflag[l] & 2u;
+      const float4 par = rpar[l];
+      int lo, hi;
+      float lerp;
+      bool valid;
+      axis_from_par(par.x, par.y, s, dimx, pad, lo, hi, lerp, valid);
+      valid = valid && !zero;
+      reinterpret_cast<uint2*>(blk + L.off_xtab)[slot * Q + s] =
+          make_uint2(valid ? (static_cast<uint32_t>(lo * (kSlice * 4)) | (static_cast<uint32_t>(hi * (kSlice * 4)) << 16)) : 0u,
+                     __float_as_uint(lerp));
+      if (valid) atomicOr(s < 32 ? &xv_lo[l] : &xv_hi[l], 1u << (s & 31));
+      axis_from_par(par.z, par.w, s, dimy, pad, lo, hi, lerp, valid);
+      valid = valid && !zero;
+      const bool inb = valid && (lo >= r0 && hi < r0 + rows_loaded);
+      uint32_t ya, yb;
+      if (inb) {
+        ya = (static_cast<uint32_t>(lo - r0) * row_bytes) >> 4;
+        yb = (static_cast<uint32_t>(hi - r0) * row_bytes) >> 4;
+      } else if (!valid) {
+        ya = yb = zrow_off >> 4;
+      } else {
+        ya = static_cast<uint32_t>(lo);
+        yb = static_cast<uint32_t>(hi);
+      }
+      reinterpret_cast<uint2*>(blk + L.off_ytab)[slot * Q + s] =
+          make_uint2(ya | ((inb || !valid) ? (1u << 15) : 0u) | (yb << 16) | (valid ? (1u << 31) : 0u),
+                     __float_as_uint(valid ? lerp : 0.0f));
+    }
+    __syncthreads();
+    // ---- validity masks
+    for (int l = tid; l < nroi; l += kPlanThreads) {
+      if (pym[l] == 0u) continue;
+      const int j = cidx[l], bi = j / a.cap, slot = j - bi * a.cap;
+      if (bi >= a.n_blocks_max) continue;
+      unsigned char* blk = blk0 + static_cast<size_t>(bi) * L.bytes;
+      reinterpret_cast<unsigned long long*>(blk + L.off_xval)[slot] =
+          static_cast<unsigned long long>(xv_lo[l]) | (static_cast<unsigned long long>(xv_hi[l]) << 32);
+    }
+    // ---- one work item per run of consecutive owned rows, longest runs first: the band kernel deals runs to its warps
+    //      round-robin, so descending length keeps the warps balanced without any run-time scheduling
+    for (int want = P; want >= 1; --want) {
+      for (int l = tid; l < nroi; l += kPlanThreads) {
+        uint32_t m = pym[l];
+        if (m == 0u) continue;
+        const int j = cidx[l], bi = j / a.cap, slot = j - bi * a.cap;
+        if (bi >= a.n_blocks_max) continue;
+        unsigned char* blk = blk0 + static_cast<size_t>(bi) * L.bytes;
+        const unsigned long long xv = static_cast<unsigned long long>(xv_lo[l]) | (static_cast<unsigned long long>(xv_hi[l]) << 32);
+        const unsigned long long full = (Q >= 64) ? ~0ull : ((1ull << Q) - 1ull);
+        const uint32_t z = ((static_cast<uint32_t>(rflag[l]) & 2u) << 11) | ((xv == full) ? (1u << 13) : 0u);
+        uint2* g_runs = reinterpret_cast<uint2*>(blk + L.off_runs);
+        const uint32_t roi_in_img = static_cast<uint32_t>(c0 - g_begin + l);
+        while (m) {
+          const int b0 = __ffs(m) - 1;
+          const int len = __ffs(~(m >> b0)) - 1;               // first zero above b0 ends the run (len <= P < 32)
+          if (len == want) {
+            const int pos = atomicAdd(&blk_runs[bi], 1);
+            if (pos < 4 * a.cap)
+              g_runs[pos] = make_uint2(static_cast<uint32_t>(slot) | z | (static_cast<uint32_t>(b0) << 16) |
+                                           (static_cast<uint32_t>(b0 + len) << 24),
+                                       ((roi_in_img * P + b0) * P) * static_cast<uint32_t>(r.c / 4));
+          }
+          m &= ~(((1u << len) - 1u) << b0);
+        }
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
-  // ---- one work item per run of consecutive owned rows of a roi
-  for (int l = tid; l < nroi; l += kPlanThreads) {
-    const unsigned long long xv = static_cast<unsigned long long>(xv_lo[l]) | (static_cast<unsigned long long>(xv_hi[l]) << 32);
-    g_xval[l] = xv;
-    const unsigned long long full = (Q >= 64) ? ~0ull : ((1ull << Q) - 1ull);
-    uint32_t m = pym[l];
-    const uint32_t z = ((static_cast<uint32_t>(rflag[l]) & 2u) << 11) | ((xv == full) ? (1u << 13) : 0u);
-    while (m) {
-      const int b0 = __ffs(m) - 1;
-      const int len = __ffs(~(m >> b0)) - 1;               // first zero above b0 ends the run (len <= P < 32)
-      g_runs[atomicAdd(&n_runs, 1)] = make_uint2(static_cast<uint32_t>(l) | z | (static_cast<uint32_t>(b0) << 16) |
-                                                     (static_cast<uint32_t>(b0 + len) << 24),
-                                                 static_cast<uint32_t>((l * P + b0) * P) * static_cast<uint32_t>(r.c / 4));
-      m &= ~(((1u << len) - 1u) << b0);
-    }
+  if (tid < a.n_blocks_max) {
+    int* hdr = reinterpret_cast<int*>(blk0 + static_cast<size_t>(tid) * L.bytes);
+    hdr[0] = min(blk_runs[tid], 4 * a.cap);
+    hdr[1] = min((total_j + a.cap - 1) / a.cap, a.n_blocks_max);
   }
-  __syncthreads();
-  if (tid == 0) *reinterpret_cast<int*>(blk) = n_runs;
 }
 
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -304,85 +354,83 @@ __device__ __forceinline__ void pool_acc(float4& acc, const float4 v, bool first
   else acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
 }
 
-template <int POOL>
-__global__ void __launch_bounds__(kThreads, 1) roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
+template <int POOL, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 512) ? 2 : 1)
+roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
   constexpr int S = (POOL == BX_POOL_NONE) ? 1 : 2;
   extern __shared__ __align__(128) unsigned char smem[];
   const RoiArgs& r = a.r;
   const int fh = r.lv[0].fh, fw = r.lv[0].fw;
   const uint32_t row_bytes = static_cast<uint32_t>(fw) * (kSlice * 4);
-  const uint32_t zrow_off = static_cast<uint32_t>(a.nbox) * kBoxBytes;      // one all-zero band row after the TMA boxes
-  const PlanLayout L = plan_layout(a.chunk, r.Q);
+  const uint32_t zrow_off = static_cast<uint32_t>(a.band_bytes);            // one all-zero band row after the TMA boxes
+  const PlanLayout L = plan_layout(a.cap, r.Q);
   unsigned char* tab = smem + zrow_off + ((row_bytes + 127u) & ~127u);
   const unsigned long long* xval = reinterpret_cast<const unsigned long long*>(tab + L.off_xval);
   const uint2* xtab = reinterpret_cast<const uint2*>(tab + L.off_xtab);
   const uint2* ytab = reinterpret_cast<const uint2*>(tab + L.off_ytab);
   const uint2* runs = reinterpret_cast<const uint2*>(tab + L.off_runs);
   __shared__ uint64_t mbar;
-  __shared__ int next_item;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int P = r.P, Q = r.Q, C = r.c;
+  if (a.dbg && tid == 0) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    a.dbg[blockIdx.x * 4 + 0] = t; a.dbg[blockIdx.x * 4 + 3] = sm;
+  }
+  // band-major CTA order: band 0 (which also owns every roi's invalid rows) is the heaviest, the last band the
+  // lightest, so the hardware dispatcher hands out the long units first and the tail of the launch is short
   int u = blockIdx.x;
-  const int band_i = u % a.n_bands; u /= a.n_bands;
+  const int per_band = a.n_slices * r.b;
+  const int band_i = u / per_band; u -= band_i * per_band;
   const int slice = u % a.n_slices;
   const int img = u / a.n_slices;
   const int r0 = band_i * a.rows_per_band;
   const float* feat_img = r.lv[0].feat + static_cast<size_t>(img) * fh * fw * C;
-  const unsigned char* plan0 = a.plan + static_cast<size_t>((img * a.n_bands + band_i) * a.n_chunks) * L.bytes;
+  const unsigned char* plan0 = a.plan + static_cast<size_t>(img * a.n_bands + band_i) * a.n_blocks_max * L.bytes;
 
   if (tid == 0) {
     mbar_init(&mbar, 1);
-    mbar_expect_tx(&mbar, static_cast<uint32_t>(a.nbox) * kBoxBytes + L.bytes);
+    mbar_expect_tx(&mbar, static_cast<uint32_t>(a.band_bytes) + L.bytes);
     bulk_load(tab, plan0, L.bytes, &mbar);
     const int row0 = (img * fh + r0) * fw;
-#if defined(BX_EXP) && BX_EXP == 5
-    for (int bx = 0; bx < a.nbox; ++bx)   // experiment: band boxes all read the same rows (L2-hot, no DRAM)
-      tma_load_2d(smem + static_cast<size_t>(bx) * kBoxBytes, &tmap, 0, 0, &mbar);
-#else
     for (int bx = 0; bx < a.nbox; ++bx)
-      tma_load_2d(smem + static_cast<size_t>(bx) * kBoxBytes, &tmap, slice * kSlice, row0 + bx * kBoxRows, &mbar);
-#endif
-    next_item = 0;
+      tma_load_2d(smem + static_cast<size_t>(bx) * a.box_rows * (kSlice * 4), &tmap, slice * kSlice, row0 + bx * a.box_rows, &mbar);
   }
-  for (uint32_t i = tid * 16u; i < row_bytes; i += kThreads * 16u)
+  for (uint32_t i = tid * 16u; i < row_bytes; i += THREADS * 16u)
     *reinterpret_cast<float4*>(smem + zrow_off + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
-  int g_begin = 0;   // first roi of plan block 0
+  int g_begin = 0;   // first roi of the image's range
   if (!a.scan_all && r.roi_counts) g_begin = img * r.rois_per_image;
   const int q = lane & 7, sub = lane >> 3;
   const unsigned char* band_q = smem + q * 16;
   const bool ext_zero = (r.extrapolation == 0.0f);
   const unsigned long long nz2 = f2_splat(a.neg_zero);
+  // output pixel (first roi of the image, py 0, px 0), this CTA's channel slice, this lane's 4 channels
+  float4* out_c0 = reinterpret_cast<float4*>(r.out + static_cast<size_t>(g_begin) * P * P * C + slice * kSlice + q * 4);
+  const uint32_t c4 = static_cast<uint32_t>(C) >> 2;
 
-  for (int ch = 0; ch < a.n_chunks; ++ch) {
+  int n_blocks = 1;
+  for (int ch = 0; ch < n_blocks; ++ch) {
     if (ch > 0) {
       __syncthreads();                       // everyone is done with the previous plan block
       if (tid == 0) {
-        next_item = 0;
         mbar_expect_tx(&mbar, L.bytes);
         bulk_load(tab, plan0 + static_cast<size_t>(ch) * L.bytes, L.bytes, &mbar);
       }
       __syncthreads();
     }
     mbar_wait(&mbar, static_cast<uint32_t>(ch & 1));
-#if defined(BX_EXP) && BX_EXP == 4
-    if (a.neg_zero == 0.0f) return;   // experiment: load + wait only (-0.0f == 0.0f is true)
-#endif
-    const int c0 = g_begin + ch * a.chunk;
+    if (ch == 0) n_blocks = reinterpret_cast<const int*>(tab)[1];
+    if (a.dbg && tid == 0 && ch == 0) {
+      unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.dbg[blockIdx.x * 4 + 1] = t;
+    }
     const int n_items = *reinterpret_cast<const int*>(tab);
-    // output pixel (roi c0, py 0, px 0), this CTA's channel slice, this lane's 4 channels
-    float4* out_c0 = reinterpret_cast<float4*>(r.out + static_cast<size_t>(c0) * P * P * C + slice * kSlice + q * 4);
-    const uint32_t c4 = static_cast<uint32_t>(C) >> 2;
-    // ---- one warp per run of output rows of a roi; 8 lanes (32 channels) per pixel, 4 pixels per pass.  Runs are handed
-    //      out dynamically; the next ticket is drawn before the current run is processed so its latency is hidden.
-    int it = 0;
-    if (lane == 0) it = atomicAdd(&next_item, 1);
-    it = __shfl_sync(0xFFFFFFFFu, it, 0);
-    while (it < n_items) {
-      int nxt = 0;
-      if (lane == 0) nxt = atomicAdd(&next_item, 1);
+    // ---- one warp per run of output rows of a roi; 8 lanes (32 channels) per pixel.  Runs are sorted by descending
+    //      length in the plan and dealt round-robin to the warps.
+    for (int it = tid >> 5; it < n_items; it += THREADS / 32) {
       const uint2 we = runs[it];
       const int l = we.x & 0xFFF;
       const bool zero = (we.x >> 12) & 1u;
@@ -392,39 +440,45 @@ __global__ void __launch_bounds__(kThreads, 1) roi_band_kernel(const __grid_cons
       const uint2* xrow = xtab + l * Q;
       const uint2* yrow = ytab + l * Q;
       const bool fast = (S == 1) && (ext_zero || zero) && ((we.x >> 13) & 1u);
-      for (int px0 = 0; px0 < P; px0 += 4) {
-        const int px = px0 + sub;
-        const bool act = px < P;
-        const int pxc = act ? px : 0;
-        float4* out_px = out_c0 + (we.y + static_cast<uint32_t>(px) * c4);
-        if (fast) {
-          // every sample column valid and extrapolation 0: invalid sample rows read the zero row, no selects needed
-          const uint2 xp = xrow[pxc];
-          const unsigned char* band_lo = band_q + (xp.x & 0xFFFFu);
-          const unsigned char* band_hi = band_q + (xp.x >> 16);
-          const unsigned long long wx2 = f2_splat(__uint_as_float(xp.y));
+      if (fast) {
+        // every sample column valid and extrapolation 0: invalid sample rows read the zero row, no selects needed.
+        // Two pixels per lane (px and px + 4) share each row's y parameters: 8 independent tap loads in flight per row.
+        for (int px0 = 0; px0 < P; px0 += 8) {
+          const int pxA = px0 + sub, pxB = pxA + 4;
+          const bool actA = pxA < P, actB = pxB < P;
+          const uint2 xa = xrow[actA ? pxA : 0], xb = xrow[actB ? pxB : 0];
+          const unsigned char* a_lo = band_q + (xa.x & 0xFFFFu);
+          const unsigned char* a_hi = band_q + (xa.x >> 16);
+          const unsigned char* b_lo = band_q + (xb.x & 0xFFFFu);
+          const unsigned char* b_hi = band_q + (xb.x >> 16);
+          const unsigned long long wa2 = f2_splat(__uint_as_float(xa.y)), wb2 = f2_splat(__uint_as_float(xb.y));
+          float4* out_a = out_c0 + (we.y + static_cast<uint32_t>(pxA) * c4);
+          const bool two = px0 + 4 < P;                        // warp-uniform: is there a second group of pixels?
           for (int py = py_begin; py < py_end; ++py) {
             const uint2 ye = yrow[py];
             const uint32_t ta = (ye.x & 0x3FFFu) << 4, tb = ((ye.x >> 16) & 0x3FFFu) << 4;
-#if defined(BX_EXP) && (BX_EXP == 2 || BX_EXP == 3)
-            // experiment: no shared-memory tap loads
-            ulonglong2 fake; fake.x = wx2 + ta; fake.y = wx2 + tb;
-            const ulonglong2 o = lerp2_packed(fake, fake, fake, fake, wx2, f2_splat(__uint_as_float(ye.y)), nz2);
-#else
-            const ulonglong2 o = lerp2_packed(*reinterpret_cast<const ulonglong2*>(band_lo + ta),
-                                              *reinterpret_cast<const ulonglong2*>(band_hi + ta),
-                                              *reinterpret_cast<const ulonglong2*>(band_lo + tb),
-                                              *reinterpret_cast<const ulonglong2*>(band_hi + tb), wx2,
-                                              f2_splat(__uint_as_float(ye.y)), nz2);
-#endif
-#if defined(BX_EXP) && (BX_EXP == 1 || BX_EXP == 3)
-            if (act && o.x == 0x123456789ull) *reinterpret_cast<ulonglong2*>(out_px) = o;   // experiment: (almost) no stores
-#else
-            if (act) *reinterpret_cast<ulonglong2*>(out_px) = o;
-#endif
-            out_px += static_cast<uint32_t>(P) * c4;
+            const unsigned long long wy2 = f2_splat(__uint_as_float(ye.y));
+            const ulonglong2 oa = lerp2_packed(*reinterpret_cast<const ulonglong2*>(a_lo + ta),
+                                               *reinterpret_cast<const ulonglong2*>(a_hi + ta),
+                                               *reinterpret_cast<const ulonglong2*>(a_lo + tb),
+                                               *reinterpret_cast<const ulonglong2*>(a_hi + tb), wa2, wy2, nz2);
+            if (two) {
+              const ulonglong2 ob = lerp2_packed(*reinterpret_cast<const ulonglong2*>(b_lo + ta),
+                                                 *reinterpret_cast<const ulonglong2*>(b_hi + ta),
+                                                 *reinterpret_cast<const ulonglong2*>(b_lo + tb),
+                                                 *reinterpret_cast<const ulonglong2*>(b_hi + tb), wb2, wy2, nz2);
+              if (actB) *reinterpret_cast<ulonglong2*>(out_a + 4 * c4) = ob;
+            }
+            if (actA) *reinterpret_cast<ulonglong2*>(out_a) = oa;
+            out_a += static_cast<uint32_t>(P) * c4;
           }
-        } else {
+        }
+      } else {
+        for (int px0 = 0; px0 < P; px0 += 4) {
+          const int px = px0 + sub;
+          const bool act = px < P;
+          const int pxc = act ? px : 0;
+          float4* out_px = out_c0 + (we.y + static_cast<uint32_t>(px) * c4);
           uint32_t xlo[S], xhi[S];
           float lx[S];
           bool xok[S];
@@ -474,7 +528,13 @@ __global__ void __launch_bounds__(kThreads, 1) roi_band_kernel(const __grid_cons
           }
         }
       }
-      it = __shfl_sync(0xFFFFFFFFu, nxt, 0);
+    }
+  }
+  if (a.dbg) {
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.dbg[blockIdx.x * 4 + 2] = t;
     }
   }
 }
@@ -497,15 +557,61 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int POOL>
-int launch_band(bx_handle* h, const BandArgs& a, const CUtensorMap& tmap, size_t smem, cudaStream_t st) {
+template <int POOL, int THREADS>
+int launch_band_t(bx_handle* h, const BandArgs& a, const CUtensorMap& tmap, size_t smem, cudaStream_t st) {
   constexpr int S = (POOL == BX_POOL_NONE) ? 1 : 2;
-  roi_plan_kernel<S><<<a.r.b * a.n_bands * a.n_chunks, kPlanThreads, 0, st>>>(a);
+  roi_plan_kernel<S><<<a.r.b * a.n_bands, kPlanThreads, 0, st>>>(a);
   BX_LAUNCH_CHECK(h);
-  BX_CUDA(cudaFuncSetAttribute(roi_band_kernel<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  roi_band_kernel<POOL><<<a.r.b * a.n_slices * a.n_bands, kThreads, smem, st>>>(tmap, a);
+  BX_CUDA(cudaFuncSetAttribute(roi_band_kernel<POOL, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BX_CUDA(cudaFuncSetAttribute(roi_band_kernel<POOL, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  roi_band_kernel<POOL, THREADS><<<a.r.b * a.n_slices * a.n_bands, THREADS, smem, st>>>(tmap, a);
   BX_LAUNCH_CHECK(h);
   return BX_OK;
+}
+
+template <int POOL>
+int launch_band(bx_handle* h, const BandArgs& a, const CUtensorMap& tmap, size_t smem, int threads, cudaStream_t st) {
+  return threads == 512 ? launch_band_t<POOL, 512>(h, a, tmap, smem, st) : launch_band_t<POOL, 1024>(h, a, tmap, smem, st);
+}
+
+// shared-memory plan of one band configuration; returns false when it does not fit `budget`
+struct BandCfg {
+  int rows_per_band, n_bands, nbox, box_rows, band_bytes, cap, n_blocks_max;
+  size_t smem;
+};
+
+bool make_band_cfg(int fh, int fw, int Q, int rois_range, size_t budget, BandCfg* c) {
+  const size_t row_bytes = static_cast<size_t>(fw) * kSlice * 4;
+  const size_t zrow = (row_bytes + 127) & ~static_cast<size_t>(127);       // the all-zero row behind the TMA boxes
+  // table capacity: the rois of one image that own rows in one band — about (band height + roi height) / map height
+  // of them; sized generously, overflow spills into further plan blocks handled sequentially by the same CTA
+  int cap = rois_range < 160 ? rois_range : 160;
+  if (cap < 1) cap = 1;
+  while (cap > 32 && plan_layout(cap, Q).bytes > budget / 4) cap = (cap + 1) / 2;
+  const size_t tab = plan_layout(cap, Q).bytes;
+  if (budget < tab + zrow + 3 * row_bytes + 256) return false;
+  int max_rows_loaded = static_cast<int>((budget - tab - zrow - 256) / row_bytes);
+  if (max_rows_loaded < 3) return false;                                    // map too wide for a useful band
+  if (max_rows_loaded > fh) max_rows_loaded = fh;
+  int rows_per_band = (max_rows_loaded >= fh) ? fh : max_rows_loaded - 1;
+  const int n_bands = (fh + rows_per_band - 1) / rows_per_band;
+  rows_per_band = (fh + n_bands - 1) / n_bands;
+  const int rows_loaded = (rows_per_band + 1 < fh) ? rows_per_band + 1 : fh;
+  const int px = rows_loaded * fw;
+  const int nbox = (px + kBoxRows - 1) / kBoxRows;
+  const int box_rows = (px + nbox - 1) / nbox;
+  c->rows_per_band = rows_per_band;
+  c->n_bands = n_bands;
+  c->nbox = nbox;
+  c->box_rows = box_rows;
+  c->band_bytes = nbox * box_rows * kSlice * 4;
+  c->cap = cap;
+  c->n_blocks_max = (rois_range + cap - 1) / cap;
+  c->smem = static_cast<size_t>(c->band_bytes) + zrow + tab;
+  if (c->n_blocks_max > kPlanMaxBlocks) return false;
+  if (static_cast<size_t>(c->band_bytes) + zrow > (1u << 18)) return false;      // 14-bit row offsets in 16 B units
+  if (static_cast<size_t>(c->band_bytes) + tab >= (1u << 20)) return false;       // mbarrier tx-count limit
+  return c->smem <= budget;
 }
 
 }  // namespace
@@ -520,59 +626,59 @@ int roi_band_launch(bx_handle* h, const RoiArgs& ra, int pool, cudaStream_t st, 
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return BX_OK;
   if (fw * kSlice * 4 > 65535 || ra.P > 31 || ra.Q > 64) return BX_OK;   // 16-bit tap offsets, 32-bit row masks
-  const size_t budget = h->smem_optin - 1024;
-  // rois per plan block: everything of one image when that fits in ~1/5 of shared memory
   const int rois_range = ra.roi_counts ? ra.rois_per_image : ra.r;
-  int chunk = rois_range < kPlanMaxChunk ? rois_range : kPlanMaxChunk;
-  while (chunk > 32 && plan_layout(chunk, ra.Q).bytes > budget / 5) chunk = (chunk + 1) / 2;
-  if (chunk < 1) return BX_OK;
-  if (static_cast<unsigned long long>(chunk) * ra.P * ra.P * (ra.c / 4) >= (1ull << 31)) return BX_OK;
-  const int n_chunks = (rois_range + chunk - 1) / chunk;
-  const size_t tab = plan_layout(chunk, ra.Q).bytes;
-  // band height: as many rows (+1 halo) as fit, then balanced over the bands
-  const size_t row_bytes = static_cast<size_t>(fw) * kSlice * 4;
-  const size_t zrow = (row_bytes + 127) & ~static_cast<size_t>(127);       // the all-zero row behind the TMA boxes
-  if (budget < tab + zrow + kBoxBytes) return BX_OK;
-  int max_rows_loaded = static_cast<int>(((budget - tab - zrow) / kBoxBytes) * kBoxBytes / row_bytes);
-  if (max_rows_loaded < 3) return BX_OK;                          // map too wide for a useful band: direct kernel
-  int rows_per_band = max_rows_loaded - 1;
-  int n_bands = (fh + rows_per_band - 1) / rows_per_band;
-  rows_per_band = (fh + n_bands - 1) / n_bands;
-  const int rows_loaded = (rows_per_band + 1 < fh) ? rows_per_band + 1 : fh;
-  const int nbox = static_cast<int>((static_cast<size_t>(rows_loaded) * fw + kBoxRows - 1) / kBoxRows);
-  const size_t smem = static_cast<size_t>(nbox) * kBoxBytes + zrow + tab;
-  if (static_cast<size_t>(nbox) * kBoxBytes + zrow > (1u << 18)) return BX_OK;    // 14-bit row offsets in 16 B units
-  if (smem > budget) return BX_OK;
-  if (static_cast<size_t>(nbox) * kBoxBytes + tab >= (1u << 20)) return BX_OK;    // mbarrier tx-count limit
+  if (static_cast<unsigned long long>(rois_range) * ra.P * ra.P * (ra.c / 4) >= (1ull << 31)) return BX_OK;
+  // two 512-thread CTAs per SM (TMA waits of one overlap the other's compute) when the band fits in half an SM's
+  // shared memory, else one 1024-thread CTA per SM
+  BandCfg cfg;
+  int threads = 512;
+  const char* force1 = getenv("BX_ROI_ONE_CTA");
+  if (force1 || !make_band_cfg(fh, fw, ra.Q, rois_range, (h->smem_sm - 2 * 1024) / 2 - 64, &cfg)) {
+    threads = 1024;
+    if (!make_band_cfg(fh, fw, ra.Q, rois_range, h->smem_optin - 1024, &cfg)) return BX_OK;
+  }
 
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ra.c), static_cast<cuuint64_t>(ra.b) * fh * fw};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ra.c) * sizeof(float)};
-  const cuuint32_t box[2] = {kSlice, kBoxRows};
+  const cuuint32_t box[2] = {kSlice, static_cast<cuuint32_t>(cfg.box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ra.lv[0].feat), gdim, gstride,
                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BX_REQUIRE(cr == CUDA_SUCCESS, BX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-  const size_t plan_bytes = static_cast<size_t>(ra.b) * n_bands * n_chunks * tab;
+  const size_t plan_bytes = static_cast<size_t>(ra.b) * cfg.n_bands * cfg.n_blocks_max * plan_layout(cfg.cap, ra.Q).bytes;
   int rc = bx_plan_reserve(h, plan_bytes);
   if (rc) return rc;
 
   BandArgs a;
   a.r = ra;
-  a.rows_per_band = rows_per_band;
-  a.n_bands = n_bands;
+  a.rows_per_band = cfg.rows_per_band;
+  a.n_bands = cfg.n_bands;
   a.n_slices = ra.c / kSlice;
-  a.chunk = chunk;
-  a.n_chunks = n_chunks;
-  a.nbox = nbox;
+  a.cap = cfg.cap;
+  a.n_blocks_max = cfg.n_blocks_max;
+  a.nbox = cfg.nbox;
+  a.box_rows = cfg.box_rows;
+  a.band_bytes = cfg.band_bytes;
   a.scan_all = (ra.box_ind != nullptr && !ra.roi_counts) ? 1 : 0;
   a.plan = static_cast<unsigned char*>(h->plan);
   a.neg_zero = -0.0f;
-  if (pool == BX_POOL_NONE) rc = launch_band<BX_POOL_NONE>(h, a, tmap, smem, st);
-  else if (pool == BX_POOL_MAX2) rc = launch_band<BX_POOL_MAX2>(h, a, tmap, smem, st);
-  else rc = launch_band<BX_POOL_AVG2>(h, a, tmap, smem, st);
+  a.dbg = nullptr;
+  if (getenv("BX_BAND_DEBUG")) {   // measurement aid: per-CTA timestamps appended to the plan buffer, dumped by the caller
+    const size_t grid = static_cast<size_t>(ra.b) * a.n_slices * a.n_bands;
+    rc = bx_plan_reserve(h, plan_bytes + 256 + grid * 32);
+    if (rc) return rc;
+    a.plan = static_cast<unsigned char*>(h->plan);
+    a.dbg = reinterpret_cast<unsigned long long*>(a.plan + ((plan_bytes + 255) & ~static_cast<size_t>(255)));
+    h->dbg_ptr = a.dbg;
+    h->dbg_count = static_cast<long long>(grid);
+    h->dbg_info[0] = a.n_bands; h->dbg_info[1] = a.n_slices; h->dbg_info[2] = threads; h->dbg_info[3] = (int)cfg.smem;
+  }
+  if (pool == BX_POOL_NONE) rc = launch_band<BX_POOL_NONE>(h, a, tmap, cfg.smem, threads, st);
+  else if (pool == BX_POOL_MAX2) rc = launch_band<BX_POOL_MAX2>(h, a, tmap, cfg.smem, threads, st);
+  else rc = launch_band<BX_POOL_AVG2>(h, a, tmap, cfg.smem, threads, st);
   if (rc == BX_OK) *used = 1;
   return rc;
 }
