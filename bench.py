@@ -30,6 +30,7 @@ WORKLOAD = dict(name='cfg2: ResNet-50 C4 600x1000, 21546 anchors, pre-NMS 6000 -
 METRIC = 'proposal+NMS+RoIAlign images/s'
 UNIT = 'images/s'
 FALLBACK_HBM_GBS = 6650.0
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 526834432   # profiles/r1h: 93.8 MB read + 433.0 MB written by roi_band_kernel
 
 
 def algorithmic_bytes(w, n, fh, fw):
@@ -73,6 +74,11 @@ def load_cpu_oracle():
                                         [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_float, ctypes.c_int,
                                                               ctypes.c_int] + [ctypes.c_void_p] * 4)
     lib.orc_max_threads.restype = ctypes.c_int
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    lib.orc_set_threads(ctypes.c_int(ncpu))      # torchrun sets OMP_NUM_THREADS=1; the CPU arm uses every host core
     return lib
 
 
@@ -263,23 +269,35 @@ def run_ours(args):
         barrier()
         return e0.elapsed_time(e1)
 
-    launches0 = [int(lib.bx_launch_count(hh)) for hh in handles]
+    def timed_single_stream(nsteps, first):
+        """The same steps on ONE stream: per-launch CUDA-event durations of the RoI kernels without co-running launches."""
+        saved = NSTREAM
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(main)
+        streams[0].wait_event(e0)
+        for k in range(nsteps):
+            launch((first + k) * saved)          # step index = multiple of NSTREAM -> always stream 0 / handle 0
+        ev = torch.cuda.Event(); ev.record(streams[0]); main.wait_event(ev)
+        e1.record(main)
+        barrier()
+        return e0.elapsed_time(e1)
+
     timed(max(3, args.warmup), 0)                       # warm-up (>= 3 steps)
     launches_w = [int(lib.bx_launch_count(hh)) for hh in handles]
-    for hh in handles:
-        _lib.check(lib.bx_profile_roi(hh, 1, args.steps // NSTREAM + 2))
     sampler = ClockSampler(local); sampler.start()
-    ms = timed(args.steps, max(3, args.warmup))
-    sampler.stop_flag = True; sampler.join()
+    ms = timed(args.steps, max(3, args.warmup))         # ---- the timed region: K steps pipelined over the streams
     launches_t = [int(lib.bx_launch_count(hh)) for hh in handles]
     gpu_launches = sum(launches_t) - sum(launches_w)
-    # dominant kernel: per-launch CUDA-event durations recorded on the launch streams inside the timed region
-    roi_ms = []
-    for hh in handles:
-        buf = (ctypes.c_float * (args.steps + 4))(); cnt = ctypes.c_int()
-        _lib.check(lib.bx_profile_read(hh, buf, args.steps + 4, ctypes.byref(cnt)))
-        roi_ms += list(buf[:cnt.value])
-        _lib.check(lib.bx_profile_roi(hh, 0, 0))
+    # ---- roofline leg: the dominant kernel pair (plan + band) bracketed by CUDA events on its launch stream, K steps
+    #      issued on one stream so that every launch is timed alone (compared with the burst HBM peak)
+    _lib.check(lib.bx_profile_roi(handles[0], 1, args.steps + 2))
+    ms_single = timed_single_stream(args.steps, 1)
+    sampler.stop_flag = True; sampler.join()
+    buf = (ctypes.c_float * (args.steps + 4))(); cnt = ctypes.c_int()
+    _lib.check(lib.bx_profile_read(handles[0], buf, args.steps + 4, ctypes.byref(cnt)))
+    roi_ms = list(buf[:cnt.value])
+    _lib.check(lib.bx_profile_roi(handles[0], 0, 0))
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,30 +312,38 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
     hb = host_batches[0]
     pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
-    h_in = [dict(deltas=pin(b_['deltas']), scores=pin(b_['scores']), feat=pin(b_['feat'])) for b_ in host_batches[:2]]
-    h_out = (torch.empty((B, post, 4)).pin_memory(), torch.empty((B, post), dtype=torch.int32).pin_memory(),
-             torch.empty((B,), dtype=torch.int32).pin_memory(), torch.empty((B * post, P, P, C)).pin_memory())
+    NE = 2   # two streams, two sets of pinned buffers: the D2H of step i overlaps the H2D + kernels of step i+1
+    h_in = [dict(deltas=pin(b_['deltas']), scores=pin(b_['scores']), feat=pin(b_['feat'])) for b_ in host_batches[:NE]]
+    h_outs = [(torch.empty((B, post, 4)).pin_memory(), torch.empty((B, post), dtype=torch.int32).pin_memory(),
+               torch.empty((B,), dtype=torch.int32).pin_memory(), torch.empty((B * post, P, P, C)).pin_memory())
+              for _ in range(NE)]
     h2d = sum(t_.numel() * t_.element_size() for t_ in h_in[0].values())
-    d2h = sum(t_.numel() * t_.element_size() for t_ in h_out)
+    d2h = sum(t_.numel() * t_.element_size() for t_ in h_outs[0])
+    e_streams = [torch.cuda.Stream(dev) for _ in range(NE)]
 
     def e2e_step(k):
-        hi = h_in[k % 2]
-        ops.c4_proposal_roi_host(anchors, hi['deltas'], hi['scores'], hi['feat'], w['image_hw'], post, h_out,
-                                 stride=float(w['stride']), pool_size=P, pre_nms_top_k=w['pre_nms'],
-                                 iou_threshold=w['iou_thr'])
-    for k in range(2):
+        hi = h_in[k % NE]
+        with torch.cuda.stream(e_streams[k % NE]):
+            ops.c4_proposal_roi_host(anchors, hi['deltas'], hi['scores'], hi['feat'], w['image_hw'], post, h_outs[k % NE],
+                                     stride=float(w['stride']), pool_size=P, pre_nms_top_k=w['pre_nms'],
+                                     iou_threshold=w['iou_thr'])
+    for k in range(NE):
         e2e_step(k)
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(main)
+    for s_ in e_streams:
+        s_.wait_event(e0)
     for k in range(e2e_steps):
         e2e_step(k)
-    e1.record()
+    for s_ in e_streams:
+        ev = torch.cuda.Event(); ev.record(s_); main.wait_event(ev)
+    e1.record(main)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     wall_ms = (time.perf_counter() - t0) * 1e3
-    assert int(h_out[2].min()) == post
+    assert all(int(o[2].min()) == post for o in h_outs)
     t = torch.tensor([max(e2e_ms, 0.0)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -341,14 +367,18 @@ def run_ours(args):
                                    % (step_bytes / 1e6, NBUF, B * post * P * P * C * 4 / 1e6),
                                 algorithmic_bytes_per_image=b_prop + b_roi,
                                 composite_hbm_frac=round(step_bytes * args.steps / (ms_max * 1e-3) / 1e9 / peak, 4)),
-                    roofline=dict(bound='hbm', kernel='roi_pool_kernel', achieved=round(achieved, 1), peak=peak,
-                                  peak_source=which, unit='GB/s', frac=round(achieved / peak, 4), traffic=None,
+                    roofline=dict(bound='hbm', kernel='roi_plan_kernel + roi_band_kernel (RoI pooling of one batch)',
+                                  achieved=round(achieved, 1), peak=peak, peak_source=which, unit='GB/s',
+                                  frac=round(achieved / peak, 4), traffic=NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                                  traffic_source='profiles/ (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum)',
                                   launches_timed=len(roi_ms), avg_launch_ms=round(roi_avg_ms, 5),
-                                  algorithmic_bytes_per_launch=roi_bytes),
+                                  algorithmic_bytes_per_launch=roi_bytes,
+                                  timed='CUDA events around every launch, same K steps issued on one stream '
+                                        '(kernel timed alone); single-stream step %.5f ms' % (ms_single / args.steps)),
                     cpu_baseline=cpu,
                     e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              steps=e2e_steps, ms_per_step=round(e2e_ms / e2e_steps, 3), wall_ms_per_step=round(wall_ms / e2e_steps, 3),
-                             api='ops.c4_proposal_roi_host -> bx_c4_proposal_roi_host (pinned host buffers)'),
+                             api='ops.c4_proposal_roi_host -> bx_c4_proposal_roi_host (pinned host buffers, 2 streams)'),
                     gpu_launches=gpu_launches, clocks=sampler.summary())
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -361,7 +391,7 @@ def main():
     ap.add_argument('--steps', type=int, default=1000)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--streams', type=int, default=2, help='steps are issued round-robin over this many CUDA streams')
+    ap.add_argument('--streams', type=int, default=4, help='steps are issued round-robin over this many CUDA streams')
     ap.add_argument('--e2e-steps', type=int, default=20)
     args = ap.parse_args()
     if args.impl == 'reference':

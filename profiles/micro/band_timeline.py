@@ -19,7 +19,7 @@ lib = _lib.load()
 lib.bx_debug_band_dump.restype = ctypes.c_longlong
 lib.bx_debug_band_dump.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]
 buf = np.zeros((8192, 4), np.uint64); info = np.zeros(4, np.int32)
-n = lib.bx_debug_band_dump(_lib.handle(0), buf.ctypes.data, 8192, info.ctypes.data)
+n = lib.bx_debug_band_dump(list(_lib._handles.values())[0], buf.ctypes.data, 8192, info.ctypes.data)
 t = buf[:n].astype(np.int64)
 t0 = t[:, 0].min()
 start, ready, done, sm = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3, (t[:, 2] - t0) / 1e3, t[:, 3]

@@ -111,9 +111,10 @@ def check(rc):
     raise BoxpathError(msg)
 
 
-def handle(device_index):
-    """bx_handle* for (device, calling thread) — SURVEY §8b: one handle per (device, host thread)."""
-    key = (int(device_index), threading.get_ident())
+def handle(device_index, stream=0):
+    """bx_handle* for (device, calling thread, stream) — SURVEY §8b: one handle per (device, host thread); keyed by the
+    stream as well so that calls issued on different streams never share a workspace."""
+    key = (int(device_index), threading.get_ident(), int(stream or 0))
     h = _handles.get(key)
     if h is None:
         lib = load()

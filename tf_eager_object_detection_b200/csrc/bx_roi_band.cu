@@ -120,6 +120,9 @@ __global__ void __launch_bounds__(kPlanThreads) roi_plan_kernel(const BandArgs a
   __shared__ unsigned char rflag[kPlanPass];
   __shared__ int blk_runs[kPlanMaxBlocks];
   __shared__ int total_j;
+  // programmatic dependent launch: let the band kernel start (and issue its TMA band loads) while the plan is computed;
+  // it waits on griddepcontrol.wait before touching the plan
+  asm volatile("griddepcontrol.launch_dependents;");
   const RoiArgs& r = a.r;
   const int tid = threadIdx.x, lane = tid & 31;
   const int band_i = blockIdx.x % a.n_bands;
@@ -392,10 +395,11 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
   if (tid == 0) {
     mbar_init(&mbar, 1);
     mbar_expect_tx(&mbar, static_cast<uint32_t>(a.band_bytes) + L.bytes);
-    bulk_load(tab, plan0, L.bytes, &mbar);
     const int row0 = (img * fh + r0) * fw;
     for (int bx = 0; bx < a.nbox; ++bx)
       tma_load_2d(smem + static_cast<size_t>(bx) * a.box_rows * (kSlice * 4), &tmap, slice * kSlice, row0 + bx * a.box_rows, &mbar);
+    asm volatile("griddepcontrol.wait;" ::: "memory");    // the plan kernel (previous launch in the stream) is complete
+    bulk_load(tab, plan0, L.bytes, &mbar);
   }
   for (uint32_t i = tid * 16u; i < row_bytes; i += THREADS * 16u)
     *reinterpret_cast<float4*>(smem + zrow_off + i) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -564,7 +568,17 @@ int launch_band_t(bx_handle* h, const BandArgs& a, const CUtensorMap& tmap, size
   BX_LAUNCH_CHECK(h);
   BX_CUDA(cudaFuncSetAttribute(roi_band_kernel<POOL, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BX_CUDA(cudaFuncSetAttribute(roi_band_kernel<POOL, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  roi_band_kernel<POOL, THREADS><<<a.r.b * a.n_slices * a.n_bands, THREADS, smem, st>>>(tmap, a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.r.b * a.n_slices * a.n_bands);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BX_CUDA(cudaLaunchKernelEx(&cfg, roi_band_kernel<POOL, THREADS>, tmap, a));
   BX_LAUNCH_CHECK(h);
   return BX_OK;
 }

@@ -15,7 +15,8 @@ f32, i32 = torch.float32, torch.int32
 
 def _ctx(t):
     dev = device_index_of(t)
-    return dev, _lib.handle(dev), Borrow(dev), stream_ptr(dev), _lib.load()
+    st = stream_ptr(dev)
+    return dev, _lib.handle(dev, st.value), Borrow(dev), st, _lib.load()
 
 
 def decode_clip(anchors, deltas, means=(0, 0, 0, 0), stds=(1, 1, 1, 1), image_shape=None):
