@@ -73,9 +73,6 @@ struct Shared {
   int cand_count;
   int kept;
   int state;
-  int shift;
-  int found_bin;
-  int suffix_count;
 };
 
 template <bool kCache>
@@ -166,7 +163,6 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
       if (prev == 0xFFFFFFFFFFFFFFFFull) sh->hi = (static_cast<uint64_t>(sh->kmax) << 32) | 0xFFFFFFFFull;
     }
     __syncthreads();
-    int above = 0;  // elements already known to be >= the upper edge of the current range (all selected)
     for (;;) {
       const uint64_t lo = sh->lo, hi = sh->hi;
       const uint64_t span = hi - lo;  // inclusive span - 1
@@ -181,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         if (v >= lo && v <= hi) atomicAdd(&hist[static_cast<uint32_t>((v - lo) >> shift)], 1u);
       }
       __syncthreads();
-      // suffix scan from the top bin: largest suffix whose count (+above) <= want
+      // suffix scan from the top bin: largest suffix whose count <= want
       if (warp == 0) {
         // each lane owns kBins/32 consecutive bins, highest lane = highest bins
         constexpr int per = kBins / 32;
@@ -195,17 +191,13 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         }
         const uint32_t higher = suf - mine;  // count in lanes above
         // walk own bins from the top
-        int fit_bin = -1;         // lowest bin index such that suffix(bin..top)+above <= want
         int over_bin = -1;        // first (highest) bin where the running count exceeds want
-        uint32_t run = higher + above;
-        uint32_t fit_count = 0;
+        uint32_t run = higher;
         if (run <= static_cast<uint32_t>(want)) {
           for (int j = per - 1; j >= 0; --j) {
             const uint32_t c = hist[lane * per + j];
             if (run + c <= static_cast<uint32_t>(want)) {
               run += c;
-              fit_bin = lane * per + j;
-              fit_count = run;
             } else {
               over_bin = lane * per + j;
               break;
@@ -223,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         } else {
           const int src = 31 - __clz(has_over);
           const int ob = __shfl_sync(0xFFFFFFFFu, over_bin, src);
-          // count of the suffix strictly above bin `ob` (+above): take it from the crossing lane's walk
+          // count of the suffix strictly above bin `ob`: take it from the crossing lane's walk
           uint32_t cnt_above = __shfl_sync(0xFFFFFFFFu, run, src);
           if (lane == 0) {
             if (cnt_above > 0) {
@@ -241,8 +233,6 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
             }
           }
         }
-        (void)fit_bin;
-        (void)fit_count;
       }
       __syncthreads();
       if (sh->state == 1) break;
