@@ -1,6 +1,8 @@
 """GPU parity: the CUDA path (through the Python mirror -> ctypes -> C ABI) against the numpy oracle and the committed
 golden vectors.  Bit-exact for indices / labels / IEEE-only arithmetic; <= 1e-5 relative where exp/log differ by ulps.
 Nothing here reads /root/reference."""
+import os
+
 import numpy as np
 import pytest
 
@@ -143,13 +145,29 @@ def test_nms_argument_errors(bx):
     with pytest.raises(NotImplementedError):
         bx.nms(b, s, 5000, 0.5)          # documented limit: max_output_size <= 2048
     from tf_eager_object_detection_b200._tensor import FLOAT32, INT32, Borrow
-    with pytest.raises(TypeError):       # wrong dtype is rejected by bx_dlpack_data, never silently converted
-        Borrow(0).ptr(b.to(torch.float64), FLOAT32, (4, 4))
-    with pytest.raises(TypeError):       # wrong shape
-        Borrow(0).ptr(b, FLOAT32, (4, 5))
-    with pytest.raises(TypeError):       # host memory is not accepted: there is no CPU path
-        Borrow(0).ptr(torch.zeros(4, 4), FLOAT32, (4, 4))
-    assert Borrow(0).ptr(s.to(torch.int32), INT32, (-1,)) != 0
+    for mode in ('0', '1'):              # torch metadata borrow, then the DLPack capsule path (bx_dlpack_data)
+        os.environ['BX_FORCE_DLPACK'] = mode
+        try:
+            with pytest.raises(TypeError):       # wrong dtype is rejected, never silently converted
+                Borrow(0).ptr(b.to(torch.float64), FLOAT32, (4, 4))
+            with pytest.raises(TypeError):       # wrong shape
+                Borrow(0).ptr(b, FLOAT32, (4, 5))
+            with pytest.raises(TypeError):       # host memory is not accepted: there is no CPU path
+                Borrow(0).ptr(torch.zeros(4, 4), FLOAT32, (4, 4))
+            with pytest.raises(TypeError):       # misaligned box tensor
+                Borrow(0).ptr(cu(np.zeros(17, np.float32))[1:].reshape(4, 4), FLOAT32, (4, 4), 16)
+            si = s.to(torch.int32)
+            assert Borrow(0).ptr(si, INT32, (-1,)) == si.data_ptr()
+            assert Borrow(0).ptr(b, FLOAT32, (-1, 4), 16) == b.data_ptr()
+        finally:
+            os.environ.pop('BX_FORCE_DLPACK', None)
+
+
+def test_dlpack_capsule_path_end_to_end(bx, golden, c4, monkeypatch):
+    """Every tensor of a whole call travels as a DLPack capsule (the protocol a non-torch host uses)."""
+    monkeypatch.setenv('BX_FORCE_DLPACK', '1')
+    ob, oi, oc = bx.proposals(cu(c4['anchors']), cu(c4['deltas'])[None], cu(c4['scores'])[None], (600, 1000), 300)
+    assert np.array_equal(oi[0].cpu().numpy(), golden['c4_eval_idx'])
 
 
 # ------------------------------------------------------------------------------------------------ a3 proposals

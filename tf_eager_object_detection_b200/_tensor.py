@@ -3,6 +3,7 @@ tf.experimental.dlpack in the reference's world) -> DLTensor* -> validated devic
 
 torch is used for device memory (output allocation), streams and nothing else."""
 import ctypes
+import os
 from ctypes import c_char_p, c_int64, c_void_p, py_object
 
 import numpy as np
@@ -33,10 +34,20 @@ def to_device(x, dtype, device=None):
             x = x.cuda(device)
         if x.dtype != dtype:
             x = x.to(dtype)
-        return x.detach()
+        return x.detach() if x.requires_grad else x
     require_cuda()
     np_dtype = {torch.float32: np.float32, torch.int32: np.int32}[dtype]
     return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np_dtype)), device=device or 'cuda')
+
+
+_TORCH_KIND = {torch.float32: (2, 32), torch.int32: (0, 32)}
+
+
+def force_dlpack():
+    """BX_FORCE_DLPACK=1 routes torch tensors through the DLPack capsule path too (it is always used for tensors of
+    other frameworks).  By default a torch.Tensor is validated on its own metadata — the same checks bx_dlpack_data
+    makes — and its storage pointer is borrowed directly, which saves ~6 us of host time per tensor."""
+    return os.environ.get('BX_FORCE_DLPACK', '') not in ('', '0')
 
 
 class Borrow:
@@ -46,6 +57,7 @@ class Borrow:
         self.device = device_index
         self._caps = []
         self._lib = _lib.load()
+        self._dlpack = force_dlpack()
 
     def ptr(self, t, kind, shape, align=4):
         if t is None:
@@ -53,6 +65,23 @@ class Borrow:
         if isinstance(t, torch.Tensor) and not t.is_contiguous():
             t = t.contiguous()
             self._caps.append(t)
+        if isinstance(t, torch.Tensor) and not self._dlpack:
+            # zero-copy borrow of a torch tensor: same rejections as bx_dlpack_data (device, dtype, shape, alignment)
+            dv = t.device
+            if dv.type != 'cuda':
+                raise TypeError('tensor is not on a CUDA device (%s); libboxpath has no CPU path' % dv)
+            if dv.index is not None and dv.index != self.device:
+                raise TypeError('tensor is on cuda:%d, handle is on cuda:%d' % (dv.index, self.device))
+            if _TORCH_KIND.get(t.dtype) != kind:
+                raise TypeError('tensor dtype %s != expected (code %d, %d bits)' % (t.dtype, kind[0], kind[1]))
+            ts = t.shape
+            if len(ts) != len(shape) or any(e >= 0 and e != a for a, e in zip(ts, shape)):
+                raise TypeError('tensor shape %s, expected %s' % (tuple(ts), tuple(shape)))
+            p = t.data_ptr()
+            if align > 1 and p % align and t.numel():
+                raise TypeError('tensor data is not %d-byte aligned' % align)
+            self._caps.append(t)
+            return p
         cap = t.__dlpack__()
         self._caps.append(cap)
         dl = _PyCapsule_GetPointer(cap, b'dltensor')
@@ -70,5 +99,11 @@ def stream_ptr(device_index):
     return c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
 
 
+_DEVICES = {}
+
+
 def empty(shape, dtype, device_index):
-    return torch.empty(shape, dtype=dtype, device=torch.device('cuda', device_index))
+    dev = _DEVICES.get(device_index)
+    if dev is None:
+        dev = _DEVICES[device_index] = torch.device('cuda', device_index)
+    return torch.empty(shape, dtype=dtype, device=dev)

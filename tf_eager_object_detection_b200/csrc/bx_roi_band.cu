@@ -75,7 +75,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 //   [..]  uint2 ytab [cap*Q]    (a | in_band << 15 | b << 16 | valid << 31, lerp_y): in_band: a, b = offsets (16 B units) of
 //                               the top / bottom tap rows in the staged band (the zero row when the sample is invalid);
 //                               else absolute feature rows (pooled pairs only)
-//   [..]  uint2 runs [4*cap]    (slot | zero << 12 | all_x_valid << 13 | py_begin << 16 | py_end << 24,
+//   [..]  uint2 runs [4*cap]    (slot | zero << 12 | all_x_valid << 13 | all_rows_in_band << 14 | py_begin << 16 | py_end << 24,
 //                                offset of output pixel (roi, py_begin, 0) in float4 units from the image's first roi)
 struct PlanLayout {
   uint32_t off_xval, off_xtab, off_ytab, off_runs, bytes;
@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kPlanThreads) roi_plan_kernel(const BandArgs a
   __shared__ float4 rpar[kPlanPass];
   __shared__ uint32_t pym[kPlanPass];
   __shared__ uint32_t xv_lo[kPlanPass], xv_hi[kPlanPass];
+  __shared__ uint32_t oobm[kPlanPass];   // output rows with a valid sample row outside the staged band (read from L2)
   __shared__ uint32_t cidx[kPlanPass];
   __shared__ unsigned char rflag[kPlanPass];
   __shared__ int blk_runs[kPlanMaxBlocks];
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(kPlanThreads) roi_plan_kernel(const BandArgs a
       pym[l] = 0u;
       xv_lo[l] = 0u;
       xv_hi[l] = 0u;
+      oobm[l] = 0u;
       rflag[l] = static_cast<unsigned char>(flag);
     }
     __syncthreads();
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(kPlanThreads) roi_plan_kernel(const BandArgs a
       } else {
         ya = static_cast<uint32_t>(lo);
         yb = static_cast<uint32_t>(hi);
+        atomicOr(&oobm[l], 1u << (s / S));
       }
       reinterpret_cast<uint2*>(blk + L.off_ytab)[slot * Q + s] =
           make_uint2(ya | ((inb || !valid) ? (1u << 15) : 0u) | (yb << 16) | (valid ? (1u << 31) : 0u),
@@ -279,8 +282,9 @@ __global__ void __launch_bounds__(kPlanThreads) roi_plan_kernel(const BandArgs a
           const int len = __ffs(~(m >> b0)) - 1;               // first zero above b0 ends the run (len <= P < 32)
           if (len == want) {
             const int pos = atomicAdd(&blk_runs[bi], 1);
+            const uint32_t inb_all = ((oobm[l] >> b0) & ((1u << len) - 1u)) == 0u ? (1u << 14) : 0u;
             if (pos < 4 * a.cap)
-              g_runs[pos] = make_uint2(static_cast<uint32_t>(slot) | z | (static_cast<uint32_t>(b0) << 16) |
+              g_runs[pos] = make_uint2(static_cast<uint32_t>(slot) | z | inb_all | (static_cast<uint32_t>(b0) << 16) |
                                            (static_cast<uint32_t>(b0 + len) << 24),
                                        ((roi_in_img * P + b0) * P) * static_cast<uint32_t>(r.c / 4));
           }
@@ -348,6 +352,21 @@ __device__ __forceinline__ ulonglong2 lerp2_packed(const ulonglong2 tl, const ul
   o.x = f2_add(t01, f2_mul(f2_sub(b01, t01), wy, nz));
   o.y = f2_add(t23, f2_mul(f2_sub(b23, t23), wy, nz));
   return o;
+}
+
+// running 2x2 pool over packed values: max (Keras MaxPooling2D) or sum (tf.nn.avg_pool, divided by 4 afterwards)
+template <int POOL>
+__device__ __forceinline__ ulonglong2 pool2(const ulonglong2 a, const ulonglong2 b) {
+  ulonglong2 r;
+  if (POOL == BX_POOL_MAX2) {
+    const float4 x = *reinterpret_cast<const float4*>(&a), y = *reinterpret_cast<const float4*>(&b);
+    const float4 m = make_float4(fmaxf(x.x, y.x), fmaxf(x.y, y.y), fmaxf(x.z, y.z), fmaxf(x.w, y.w));
+    r = *reinterpret_cast<const ulonglong2*>(&m);
+  } else {
+    r.x = f2_add(a.x, b.x);
+    r.y = f2_add(a.y, b.y);
+  }
+  return r;
 }
 
 template <int POOL>
@@ -443,10 +462,11 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
       const unsigned long long xv = xval[l];
       const uint2* xrow = xtab + l * Q;
       const uint2* yrow = ytab + l * Q;
-      const bool fast = (S == 1) && (ext_zero || zero) && ((we.x >> 13) & 1u);
-      if (fast) {
-        // every sample column valid and extrapolation 0: invalid sample rows read the zero row, no selects needed.
-        // Two pixels per lane (px and px + 4) share each row's y parameters: 8 independent tap loads in flight per row.
+      // fast paths: every sample column valid, extrapolation 0 and (pooled crops) every valid sample row inside the
+      // staged band: invalid sample rows read the zero row, so no selects and no validity tests are needed
+      const bool fast = (ext_zero || zero) && ((we.x >> 13) & 1u) && (S == 1 || ((we.x >> 14) & 1u));
+      if (fast && S == 1) {
+        // two pixels per lane (px and px + 4) share each row's y parameters: 8 independent tap loads in flight per row
         for (int px0 = 0; px0 < P; px0 += 8) {
           const int pxA = px0 + sub, pxB = pxA + 4;
           const bool actA = pxA < P, actB = pxB < P;
@@ -475,6 +495,46 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
             }
             if (actA) *reinterpret_cast<ulonglong2*>(out_a) = oa;
             out_a += static_cast<uint32_t>(P) * c4;
+          }
+        }
+      } else if (fast) {
+        // pooled crop (2x2 samples per output pixel), packed math, max / mean in the slow path's order (sy major)
+        for (int px0 = 0; px0 < P; px0 += 4) {
+          const int px = px0 + sub;
+          const bool act = px < P;
+          const int pxc = act ? px : 0;
+          const uint2 x0 = xrow[pxc * 2], x1 = xrow[pxc * 2 + 1];
+          const unsigned char* lo0 = band_q + (x0.x & 0xFFFFu);
+          const unsigned char* hi0 = band_q + (x0.x >> 16);
+          const unsigned char* lo1 = band_q + (x1.x & 0xFFFFu);
+          const unsigned char* hi1 = band_q + (x1.x >> 16);
+          const unsigned long long w0 = f2_splat(__uint_as_float(x0.y)), w1 = f2_splat(__uint_as_float(x1.y));
+          float4* out_px = out_c0 + (we.y + static_cast<uint32_t>(px) * c4);
+          for (int py = py_begin; py < py_end; ++py) {
+            ulonglong2 acc;
+#pragma unroll
+            for (int sy = 0; sy < 2; ++sy) {
+              const uint2 ye = yrow[py * 2 + sy];
+              const uint32_t ta = (ye.x & 0x3FFFu) << 4, tb = ((ye.x >> 16) & 0x3FFFu) << 4;
+              const unsigned long long wy2 = f2_splat(__uint_as_float(ye.y));
+              const ulonglong2 v0 = lerp2_packed(*reinterpret_cast<const ulonglong2*>(lo0 + ta),
+                                                 *reinterpret_cast<const ulonglong2*>(hi0 + ta),
+                                                 *reinterpret_cast<const ulonglong2*>(lo0 + tb),
+                                                 *reinterpret_cast<const ulonglong2*>(hi0 + tb), w0, wy2, nz2);
+              const ulonglong2 v1 = lerp2_packed(*reinterpret_cast<const ulonglong2*>(lo1 + ta),
+                                                 *reinterpret_cast<const ulonglong2*>(hi1 + ta),
+                                                 *reinterpret_cast<const ulonglong2*>(lo1 + tb),
+                                                 *reinterpret_cast<const ulonglong2*>(hi1 + tb), w1, wy2, nz2);
+              if (sy == 0) acc = v0; else acc = pool2<POOL>(acc, v0);
+              acc = pool2<POOL>(acc, v1);
+            }
+            if (POOL == BX_POOL_AVG2) {
+              const unsigned long long q4 = f2_splat(0.25f);   // x / 4 == x * 0.25 exactly (power of two)
+              acc.x = f2_mul(acc.x, q4, nz2);
+              acc.y = f2_mul(acc.y, q4, nz2);
+            }
+            if (act) *reinterpret_cast<ulonglong2*>(out_px) = acc;
+            out_px += static_cast<uint32_t>(P) * c4;
           }
         }
       } else {
