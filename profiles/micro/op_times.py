@@ -57,6 +57,12 @@ rb, _, _ = ops.proposals(fa, fd, fs, (600, 1000), 1000)
 feats = [torch.randn((1, h, w, 256), device=dev) for (h, w) in syn.fpn_feature_shapes((600, 1000))[:4]]
 fb = 4 * 256 * sum(h * w for (h, w) in syn.fpn_feature_shapes((600, 1000))[:4])
 rows.append(('cfg3 fpn_roi_features R=1000 C=256 (levels + pool)', t(lambda: ops.fpn_roi_features(feats, rb[0], (600, 1000))), fb + 16 * 1000 + 4 * 1000 * 49 * 256))
+B3 = 16
+feats16 = [torch.randn((B3, h, w, 256), device=dev) for (h, w) in syn.fpn_feature_shapes((600, 1000))[:4]]
+rb16 = rb[0].repeat(B3, 1)
+bi16 = torch.arange(B3, device=dev, dtype=torch.int32).repeat_interleave(1000)
+rows.append(('cfg3 fpn_roi_features B=16 R=16000 C=256 (direct kernel)', t(lambda: ops.fpn_roi_features(feats16, rb16, (600, 1000), box_ind=bi16), n=10), B3 * (fb + 16 * 1000 + 4 * 1000 * 49 * 256)))
+del feats16
 rows.append(('cfg3 fpn_assign_levels R=1000', t(lambda: ops.fpn_assign_levels(rb[0])), 1000 * 24))
 # ---- cfg5 FPN 800x1333
 f5 = syn.fpn_image(5, 0, (800, 1333), with_features=False)

@@ -487,10 +487,16 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
                                                *reinterpret_cast<const ulonglong2*>(a_lo + tb),
                                                *reinterpret_cast<const ulonglong2*>(a_hi + tb), wa2, wy2, nz2);
             if (two) {
-              const ulonglong2 ob = lerp2_packed(*reinterpret_cast<const ulonglong2*>(b_lo + ta),
-                                                 *reinterpret_cast<const ulonglong2*>(b_hi + ta),
-                                                 *reinterpret_cast<const ulonglong2*>(b_lo + tb),
-                                                 *reinterpret_cast<const ulonglong2*>(b_hi + tb), wb2, wy2, nz2);
+              // lanes whose second pixel does not exist (px >= P) issue no loads: their 128 B would be a wasted
+              // shared-memory wavefront per tap, and this kernel is bound by the LSU data pipe
+              ulonglong2 b0 = make_ulonglong2(0ull, 0ull), b1 = b0, b2 = b0, b3 = b0;
+              if (actB) {
+                b0 = *reinterpret_cast<const ulonglong2*>(b_lo + ta);
+                b1 = *reinterpret_cast<const ulonglong2*>(b_hi + ta);
+                b2 = *reinterpret_cast<const ulonglong2*>(b_lo + tb);
+                b3 = *reinterpret_cast<const ulonglong2*>(b_hi + tb);
+              }
+              const ulonglong2 ob = lerp2_packed(b0, b1, b2, b3, wb2, wy2, nz2);
               if (actB) *reinterpret_cast<ulonglong2*>(out_a + 4 * c4) = ob;
             }
             if (actA) *reinterpret_cast<ulonglong2*>(out_a) = oa;
