@@ -497,3 +497,30 @@ def test_band_kernel_padded_rois_are_zero_filled(bx):
         ref = orc.roi_pool_c4(feat[i:i + 1], rois[i, :counts[i]], 16, 7, False)
         assert np.array_equal(out[i, :counts[i]], ref)
         assert (out[i, counts[i]:] == 0).all()
+
+
+def test_fpn_band_path_matches_oracle(bx):
+    """FPN level routing through the per-level band launches (C a multiple of 32), batched with box_ind."""
+    from tf_eager_object_detection_b200 import fpn as fpn_mod
+    rng = np.random.default_rng(99)
+    B, C = 3, 64
+    shapes = syn.fpn_feature_shapes((600, 1000))[:4]
+    feats = [rng.standard_normal((B, h, w, C), dtype=np.float32) for (h, w) in shapes]
+    rois = np.concatenate([syn.random_rois(rng, 300, (600, 1000)), np.float32([[0, 0, 999, 599], [10, 10, 10, 10]])])
+    R = rois.shape[0]
+    bi = rng.integers(0, B, R).astype(np.int32)
+    assert orc.level_margin(rois).min() > 1e-5
+    fused, order, lv, counts = fpn_mod.fpn_roi_features(cu(rois), [cu(f) for f in feats], (600, 1000), box_ind=cu(bi))
+    _, rois_list, ref_order = orc.assign_levels(rois)
+    assert np.array_equal(order.cpu().numpy(), ref_order)
+    assert counts.cpu().numpy().tolist() == [r_.shape[0] for r_ in rois_list]
+    ref = np.concatenate([orc.roi_pool_fpn(f, rois[idx], (600, 1000), 7, box_ind=bi[idx])
+                          for f, idx in zip(feats, np.split(ref_order, np.cumsum([r_.shape[0] for r_ in rois_list])[:-1]))
+                          if idx.size])
+    assert np.array_equal(fused.cpu().numpy(), ref)
+    # single image, no box_ind (the reference's own call pattern)
+    fused1, order1, _, _ = fpn_mod.fpn_roi_features(cu(rois), [cu(f[:1]) for f in feats], (600, 1000))
+    ref1 = np.concatenate([orc.roi_pool_fpn(f[:1], rois[idx], (600, 1000), 7)
+                           for f, idx in zip(feats, np.split(ref_order, np.cumsum([r_.shape[0] for r_ in rois_list])[:-1]))
+                           if idx.size])
+    assert np.array_equal(fused1.cpu().numpy(), ref1)
