@@ -464,7 +464,9 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
       const uint2* yrow = ytab + l * Q;
       // fast paths: every sample column valid, extrapolation 0 and (pooled crops) every valid sample row inside the
       // staged band: invalid sample rows read the zero row, so no selects and no validity tests are needed
-      const bool fast = (ext_zero || zero) && ((we.x >> 13) & 1u) && (S == 1 || ((we.x >> 14) & 1u));
+      // (sample columns outside the map — rois clipped at the right / bottom image border end there in the C4 geometry —
+      //  read pixel 0 and are zeroed by one select per output, so they stay on the fast paths)
+      const bool fast = (ext_zero || zero) && (S == 1 || ((we.x >> 14) & 1u));
       if (fast && S == 1) {
         // two pixels per lane (px and px + 4) share each row's y parameters: 8 independent tap loads in flight per row
         for (int px0 = 0; px0 < P; px0 += 8) {
@@ -476,16 +478,18 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
           const unsigned char* b_lo = band_q + (xb.x & 0xFFFFu);
           const unsigned char* b_hi = band_q + (xb.x >> 16);
           const unsigned long long wa2 = f2_splat(__uint_as_float(xa.y)), wb2 = f2_splat(__uint_as_float(xb.y));
+          const bool okA = (xv >> (actA ? pxA : 0)) & 1ull, okB = (xv >> (actB ? pxB : 0)) & 1ull;
           float4* out_a = out_c0 + (we.y + static_cast<uint32_t>(pxA) * c4);
           const bool two = px0 + 4 < P;                        // warp-uniform: is there a second group of pixels?
           for (int py = py_begin; py < py_end; ++py) {
             const uint2 ye = yrow[py];
             const uint32_t ta = (ye.x & 0x3FFFu) << 4, tb = ((ye.x >> 16) & 0x3FFFu) << 4;
             const unsigned long long wy2 = f2_splat(__uint_as_float(ye.y));
-            const ulonglong2 oa = lerp2_packed(*reinterpret_cast<const ulonglong2*>(a_lo + ta),
-                                               *reinterpret_cast<const ulonglong2*>(a_hi + ta),
-                                               *reinterpret_cast<const ulonglong2*>(a_lo + tb),
-                                               *reinterpret_cast<const ulonglong2*>(a_hi + tb), wa2, wy2, nz2);
+            ulonglong2 oa = lerp2_packed(*reinterpret_cast<const ulonglong2*>(a_lo + ta),
+                                         *reinterpret_cast<const ulonglong2*>(a_hi + ta),
+                                         *reinterpret_cast<const ulonglong2*>(a_lo + tb),
+                                         *reinterpret_cast<const ulonglong2*>(a_hi + tb), wa2, wy2, nz2);
+            if (!okA) oa = make_ulonglong2(0ull, 0ull);
             if (two) {
               // lanes whose second pixel does not exist (px >= P) issue no loads: their 128 B would be a wasted
               // shared-memory wavefront per tap, and this kernel is bound by the LSU data pipe
@@ -496,7 +500,8 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
                 b2 = *reinterpret_cast<const ulonglong2*>(b_lo + tb);
                 b3 = *reinterpret_cast<const ulonglong2*>(b_hi + tb);
               }
-              const ulonglong2 ob = lerp2_packed(b0, b1, b2, b3, wb2, wy2, nz2);
+              ulonglong2 ob = lerp2_packed(b0, b1, b2, b3, wb2, wy2, nz2);
+              if (!okB) ob = make_ulonglong2(0ull, 0ull);
               if (actB) *reinterpret_cast<ulonglong2*>(out_a + 4 * c4) = ob;
             }
             if (actA) *reinterpret_cast<ulonglong2*>(out_a) = oa;
@@ -515,6 +520,7 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
           const unsigned char* lo1 = band_q + (x1.x & 0xFFFFu);
           const unsigned char* hi1 = band_q + (x1.x >> 16);
           const unsigned long long w0 = f2_splat(__uint_as_float(x0.y)), w1 = f2_splat(__uint_as_float(x1.y));
+          const bool ok0 = (xv >> (pxc * 2)) & 1ull, ok1 = (xv >> (pxc * 2 + 1)) & 1ull;
           float4* out_px = out_c0 + (we.y + static_cast<uint32_t>(px) * c4);
           for (int py = py_begin; py < py_end; ++py) {
             ulonglong2 acc;
@@ -523,14 +529,16 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
               const uint2 ye = yrow[py * 2 + sy];
               const uint32_t ta = (ye.x & 0x3FFFu) << 4, tb = ((ye.x >> 16) & 0x3FFFu) << 4;
               const unsigned long long wy2 = f2_splat(__uint_as_float(ye.y));
-              const ulonglong2 v0 = lerp2_packed(*reinterpret_cast<const ulonglong2*>(lo0 + ta),
-                                                 *reinterpret_cast<const ulonglong2*>(hi0 + ta),
-                                                 *reinterpret_cast<const ulonglong2*>(lo0 + tb),
-                                                 *reinterpret_cast<const ulonglong2*>(hi0 + tb), w0, wy2, nz2);
-              const ulonglong2 v1 = lerp2_packed(*reinterpret_cast<const ulonglong2*>(lo1 + ta),
-                                                 *reinterpret_cast<const ulonglong2*>(hi1 + ta),
-                                                 *reinterpret_cast<const ulonglong2*>(lo1 + tb),
-                                                 *reinterpret_cast<const ulonglong2*>(hi1 + tb), w1, wy2, nz2);
+              ulonglong2 v0 = lerp2_packed(*reinterpret_cast<const ulonglong2*>(lo0 + ta),
+                                           *reinterpret_cast<const ulonglong2*>(hi0 + ta),
+                                           *reinterpret_cast<const ulonglong2*>(lo0 + tb),
+                                           *reinterpret_cast<const ulonglong2*>(hi0 + tb), w0, wy2, nz2);
+              ulonglong2 v1 = lerp2_packed(*reinterpret_cast<const ulonglong2*>(lo1 + ta),
+                                           *reinterpret_cast<const ulonglong2*>(hi1 + ta),
+                                           *reinterpret_cast<const ulonglong2*>(lo1 + tb),
+                                           *reinterpret_cast<const ulonglong2*>(hi1 + tb), w1, wy2, nz2);
+              if (!ok0) v0 = make_ulonglong2(0ull, 0ull);
+              if (!ok1) v1 = make_ulonglong2(0ull, 0ull);
               if (sy == 0) acc = v0; else acc = pool2<POOL>(acc, v0);
               acc = pool2<POOL>(acc, v1);
             }
