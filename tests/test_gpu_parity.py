@@ -524,3 +524,95 @@ def test_fpn_band_path_matches_oracle(bx):
                            for f, idx in zip(feats, np.split(ref_order, np.cumsum([r_.shape[0] for r_ in rois_list])[:-1]))
                            if idx.size])
     assert np.array_equal(fused1.cpu().numpy(), ref1)
+
+
+# ------------------------------------------------------------------------------------------------ other BASELINE configs
+def test_full_size_cfg3_fpn_batch16(bx):
+    """BASELINE cfg 3 (ResNet-101 FPN, 150 111 anchors P2-P6, batch 16): every image's global NMS matches the oracle;
+    level routing and pooled features (C=256) match on a sampled image; size-independent properties on the whole batch."""
+    from tf_eager_object_detection_b200 import fpn as fpn_mod
+    B = 16
+    imgs = [syn.fpn_image(3, i, with_features=False) for i in range(B)]
+    anchors = cu(imgs[0]['anchors'])
+    deltas = cu(np.stack([im['deltas'] for im in imgs])); scores = cu(np.stack([im['scores'] for im in imgs]))
+    ob, oi, oc = bx.proposals(anchors, deltas, scores, (600, 1000), 1000)
+    assert (oc == 1000).all()
+    s_kept = torch.gather(scores, 1, oi.long())
+    assert (s_kept[:, 1:] < s_kept[:, :-1]).all()
+    for i in (0, 7, 15):
+        _, idx = orc.region_proposal(imgs[i]['deltas'], imgs[i]['anchors'], imgs[i]['scores'], (600, 1000), 1000)
+        assert np.array_equal(oi[i].cpu().numpy(), idx)
+    g = torch.Generator(device='cuda'); g.manual_seed(3)
+    feats = [torch.randn((B, h, w, 256), device='cuda', generator=g) for (h, w) in syn.fpn_feature_shapes((600, 1000))[:4]]
+    rois = ob.reshape(-1, 4)
+    bi = torch.arange(B, device='cuda', dtype=torch.int32).repeat_interleave(1000)
+    fused, order, lv, counts = fpn_mod.fpn_roi_features(rois, feats, (600, 1000), box_ind=bi)
+    assert int(counts.sum()) == B * 1000 and fused.shape == (B * 1000, 7, 7, 256)
+    o = order.cpu().numpy()
+    assert np.array_equal(np.sort(o), np.arange(B * 1000))                       # a permutation
+    lvl = lv.cpu().numpy()
+    assert (np.diff(lvl[o]) >= 0).all()                                           # level-major
+    for l_ in range(2, 6):                                                        # stable inside a level
+        assert (np.diff(o[lvl[o] == l_]) > 0).all()
+    # oracle on image 5: its rows of the fused output, whatever their position
+    rows = np.nonzero((o >= 5000) & (o < 6000))[0]
+    r5 = ob[5].cpu().numpy()
+    assert orc.level_margin(r5).min() > 1e-6
+    _, rl, ro = orc.assign_levels(r5)
+    ref = orc.fpn_roi_features(rl, [f[5:6].cpu().numpy() for f in feats], (600, 1000))
+    assert np.array_equal(o[rows] - 5000, ro)
+    assert np.array_equal(fused[torch.as_tensor(rows, device='cuda')].cpu().numpy(), ref)
+
+
+def test_full_size_cfg4_targets_batch16(bx):
+    """BASELINE cfg 4: anchor_target + proposal_target at batch 16 (21 546 anchors x 100 gt, 2000 proposals)."""
+    from tf_eager_object_detection_b200.anchor_target import AnchorTarget
+    from tf_eager_object_detection_b200.proposal_target import ProposalTarget
+    B = 16
+    rng = np.random.default_rng(syn.seed_for(4, 1))
+    anchors = syn.c4_anchors(38, 63)
+    gts, gls, perms = [], [], []
+    for _ in range(B):
+        g_, l_ = syn.gt_boxes(rng, 100, (600, 1000))
+        gts.append(g_); gls.append(l_); perms.append(rng.permutation(anchors.shape[0]).astype(np.int32))
+    lab, tg, iw, ow, cnt = AnchorTarget().call_batched((cu(np.stack(gts)), [600, 1000], cu(anchors)), perm=np.stack(perms))
+    labn = lab.cpu().numpy()
+    assert ((labn == 1).sum(1) <= 128).all() and ((labn >= 0).sum(1) <= 256).all()
+    for i in (0, 9, 15):
+        rl, rt, ri, ro, _ = orc.anchor_target(gts[i], [600, 1000], anchors, perms[i])
+        assert np.array_equal(labn[i], rl) and np.array_equal(iw[i].cpu().numpy(), ri)
+        assert np.array_equal(ow[i].cpu().numpy(), ro)
+        close(tg[i].cpu().numpy(), rt, scale=1.0)
+    imgs = [syn.c4_image(4, i, with_features=False) for i in range(B)]
+    deltas = cu(np.stack([im['deltas'] for im in imgs])); scores = cu(np.stack([im['scores'] for im in imgs]))
+    rois, _, rc = bx.proposals(cu(anchors), deltas, scores, (600, 1000), 2000)
+    perm_r = np.stack([rng.permutation(2000) for _ in range(B)]).astype(np.int32)
+    pt = ProposalTarget(num_classes=21, pos_iou_threshold=0.5, neg_iou_threshold=0.0, total_num_samples=128,
+                        max_pos_samples=32, target_stds=[0.1, 0.1, 0.2, 0.2])
+    o_r, o_l, o_t, o_i, o_o, o_k, o_c = pt.call_batched((rois, cu(np.stack(gts)), cu(np.stack(gls))), perm=perm_r, roi_counts=rc)
+    assert (o_c[:, 1] == 0).all()
+    for i in (0, 8, 15):
+        ref = orc.proposal_target(rois[i].cpu().numpy(), gts[i], gls[i], perm_r[i], 21, 0.5, 0.0, 128, 32, stds=(0.1, 0.1, 0.2, 0.2))
+        assert np.array_equal(o_k[i].cpu().numpy(), ref[5]['keep'])                 # sampled indices bit-exact
+        assert np.array_equal(o_l[i].cpu().numpy(), ref[1]) and np.array_equal(o_i[i].cpu().numpy(), ref[3])
+        close(o_t[i].cpu().numpy(), ref[2], scale=1.0)
+
+
+def test_cfg5_shape_shard_equivalence(bx):
+    """BASELINE cfg 5 (800x1333 FPN, 267 069 anchors): processing a batch in shards (as the GPUs of a node do) gives
+    byte-identical per-image results to processing it whole — the property the multi-GPU all-gather relies on."""
+    from tf_eager_object_detection_b200 import distributed as bxd
+    B = 8
+    imgs = [syn.fpn_image(5, i, (800, 1333), with_features=False) for i in range(B)]
+    anchors = cu(imgs[0]['anchors'])
+    assert anchors.shape[0] == 267069
+    deltas = cu(np.stack([im['deltas'] for im in imgs])); scores = cu(np.stack([im['scores'] for im in imgs]))
+    ob, oi, oc = bx.proposals(anchors, deltas, scores, (800, 1333), 1000)
+    parts = []
+    for rank in range(4):
+        lo, hi = bxd.shard_bounds(B, rank, 4)
+        parts.append(bx.proposals(anchors, deltas[lo:hi], scores[lo:hi], (800, 1333), 1000))
+    assert torch.equal(torch.cat([p[0] for p in parts]), ob)
+    assert torch.equal(torch.cat([p[1] for p in parts]), oi) and torch.equal(torch.cat([p[2] for p in parts]), oc)
+    _, idx = orc.region_proposal(imgs[3]['deltas'], imgs[3]['anchors'], imgs[3]['scores'], (800, 1333), 1000)
+    assert np.array_equal(oi[3].cpu().numpy(), idx)
