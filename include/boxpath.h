@@ -176,6 +176,29 @@ int bx_proposal_target(bx_handle* h, const float* rois, const int* roi_counts, i
                        const bx_proposal_target_params* p, float* out_rois, int* out_labels, float* out_targets,
                        float* out_in_w, float* out_out_w, int* out_keep, int* out_counts, void* stream);
 
+/* ---- f1 ("next" row): model/prediction.py:103-163 post_ops_prediction, batched over images.  Per foreground class:
+ *      score > score_threshold -> decode with the roi-head means/stds (utils/bbox_transform.py:32-55) -> clip to the image
+ *      + min-edge filter (utils/bbox_tf.py:59-84, min_edge = extractor_stride) -> tf.image.non_max_suppression
+ *      (max_per_class, nms_iou_threshold) -> concatenation over classes -> top max_per_image by score (descending; ties
+ *      to the lower class, then the earlier NMS pick).
+ *      scores [batch,r,C] softmax; deltas [batch,r,C,4]; rois [batch,r,4]; roi_counts [batch] or NULL ->
+ *      out_det [batch,max_per_image,6] = (x1,y1,x2,y2,score,class) zero padded — the record layout that
+ *      distributed.allgather_detections ships — and out_count [batch].  Limits: (C-1)*max_per_class <= 8192. */
+typedef struct {
+  float means[4];
+  float stds[4];            /* roi head: (0.1, 0.1, 0.2, 0.2) */
+  int image_h, image_w;
+  int num_classes;          /* C, class 0 = background */
+  int max_per_class;        /* 50 */
+  int max_per_image;        /* 150 (ctor default; the configs use 50) */
+  float nms_iou_threshold;  /* 0.3 */
+  float score_threshold;    /* 0.05 (configs: 0.0) */
+  float min_edge;           /* extractor_stride = 16; <= 0 disables the filter */
+} bx_prediction_params;
+int bx_post_ops_prediction(bx_handle* h, const float* scores, const float* deltas, const float* rois,
+                           const int* roi_counts, int batch, int r, const bx_prediction_params* p, float* out_det,
+                           int* out_count, void* stream);
+
 /* ---- composite used by the benchmark and by BaseFasterRcnn.call eval (faster_rcnn/base_faster_rcnn_model.py:153,182):
  *      bx_proposals followed by bx_roi_pool(BX_ROI_STRIDE_NORM) on the kept boxes, device-resident tensors. */
 int bx_c4_proposal_roi(bx_handle* h, const float* anchors, const float* deltas, const float* scores,

@@ -384,3 +384,32 @@ def proposal_target(rois, gt_bboxes, gt_labels, perm, num_classes=21, pos_iou_th
             tg[i, labels[i]] = bt[i]                                                      # :116-117
     return (final_rois, final_labels, tg.reshape(s, num_classes * 4), in_w.reshape(s, num_classes * 4),
             np.ones((s, num_classes * 4), F), {'keep': keep, 'num_fg': fg.size})         # :122-124
+
+
+# --------------------------------------------------------------------------- f1 post-head detection filtering
+def post_ops_prediction(roi_scores_softmax, roi_txtytwth, rois, image_shape, means=(0, 0, 0, 0), stds=(1, 1, 1, 1),
+                        max_num_per_class=50, max_num_per_image=150, nms_iou_threshold=0.3, score_threshold=0.05,
+                        extractor_stride=16, num_classes=21):
+    """model/prediction.py:103-163 `post_ops_prediction`.  Per foreground class: score threshold
+    (strict >, :135) -> decode with the roi-head stds (:137-139) -> clip + min-edge filter with min_edge =
+    extractor_stride (:140-142) -> NMS (:145) -> concat (:154-156) -> top max_num_per_image by score (:158-159;
+    `tf.nn.top_k(sorted=False)` order is unspecified in TF — fixed here as descending score, ties to the lower
+    concatenated index).  Returns (boxes [n,4], classes [n] int32, scores [n]) or (None, None, None)."""
+    s = np.asarray(roi_scores_softmax, F); d = np.asarray(roi_txtytwth, F).reshape(s.shape[0], s.shape[1], 4)
+    rois = np.asarray(rois, F)
+    res_s, res_b, res_c = [], [], []
+    for i in range(1, num_classes):
+        inds = np.nonzero(s[:, i] > F(score_threshold))[0]
+        cls_score = s[inds, i]
+        boxes = decode_bbox(rois[inds], d[inds, i, :], means, stds)
+        boxes, sel = bboxes_clip_filter(boxes, 0, image_shape[0], image_shape[1], min_edge=extractor_stride)
+        cls_score = cls_score[sel]
+        keep = nms_tf(boxes, cls_score, max_num_per_class, nms_iou_threshold)
+        if keep.size == 0:
+            continue
+        res_s.append(cls_score[keep]); res_b.append(boxes[keep]); res_c.append(np.full(keep.size, i, np.int32))
+    if not res_s:
+        return None, None, None
+    sc = np.concatenate(res_s); bb = np.concatenate(res_b); cc = np.concatenate(res_c)
+    order = np.argsort(-sc, kind='stable')[:min(max_num_per_image, sc.size)]
+    return bb[order], cc[order], sc[order]

@@ -22,6 +22,7 @@ import tensorflow as tf  # noqa: E402  (the shim)
 from object_detection.model.anchor_target import AnchorTarget  # noqa: E402
 from object_detection.model.proposal_target import ProposalTarget  # noqa: E402
 from object_detection.model.region_proposal import RegionProposal  # noqa: E402
+from object_detection.model.prediction import post_ops_prediction as ref_post_ops  # noqa: E402
 from object_detection.model.roi_pooling import (RoiPoolingCropAndResize, RoiPoolingCropAndResize2,  # noqa: E402
                                                 RoiPoolingRoiAlign)
 from object_detection.utils import anchor_generator as ref_ag  # noqa: E402
@@ -175,6 +176,14 @@ def main():
     finally:
         np.random.choice = real_choice
     del cycle
+
+    # ---- f1: post-head detection filtering on synthetic roi-head outputs over the 300 eval rois
+    from tf_eager_object_detection_b200.synthetic import roi_head_outputs
+    hs, hd = roi_head_outputs(np.random.default_rng(syn.seed_for(1, 77)), rois_e.shape[0], 21)
+    pb, pc, ps = ref_post_ops(tf.constant(hs), tf.constant(hd), tf.constant(rois_e), [600, 1000], [0, 0, 0, 0],
+                              [0.1, 0.1, 0.2, 0.2], max_num_per_class=50, max_num_per_image=150, nms_iou_threshold=0.3,
+                              score_threshold=0.05, extractor_stride=16, num_classes=21)
+    g['post_boxes'], g['post_classes'], g['post_scores'] = np.asarray(pb), np.asarray(pc), np.asarray(ps)
 
     np.savez_compressed(os.path.join(OUT, 'reference_on_shim.npz'), **g)
     sz = os.path.getsize(os.path.join(OUT, 'reference_on_shim.npz'))

@@ -22,7 +22,8 @@ def test_header_declares_the_documented_entry_points():
     names = header_functions()
     for must in ('bx_create', 'bx_destroy', 'bx_last_error', 'bx_version', 'bx_decode_clip', 'bx_nms', 'bx_proposals',
                  'bx_crop_and_resize', 'bx_roi_pool', 'bx_fpn_assign_levels', 'bx_fpn_roi_features', 'bx_pairwise_iou',
-                 'bx_anchor_target', 'bx_proposal_target', 'bx_c4_proposal_roi', 'bx_c4_proposal_roi_host'):
+                 'bx_anchor_target', 'bx_proposal_target', 'bx_post_ops_prediction', 'bx_c4_proposal_roi',
+                 'bx_c4_proposal_roi_host'):
         assert must in names
 
 
@@ -41,7 +42,8 @@ def test_every_entry_point_cites_the_reference():
     src = open(HEADER).read()
     for path in ('model/region_proposal.py:37-81', 'utils/bbox_transform.py:32-55', 'utils/bbox_tf.py:59-78',
                  'model/roi_pooling.py', 'model/fpn/base_fpn_model.py:303-324', 'model/fpn/base_fpn_model.py:152-161',
-                 'utils/bbox_tf.py:37-56', 'model/anchor_target.py:29-107', 'model/proposal_target.py:32-124'):
+                 'utils/bbox_tf.py:37-56', 'model/anchor_target.py:29-107', 'model/proposal_target.py:32-124',
+                 'model/prediction.py:103-163'):
         assert path in src, path
 
 
@@ -49,6 +51,7 @@ def test_param_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.ProposalParams) == 4 * 4 + 4 * 4 + 6 * 4
     assert ctypes.sizeof(_lib.AnchorTargetParams) == 2 * 4 + 2 * 4 + 8 * 4 + 2 * 4
     assert ctypes.sizeof(_lib.ProposalTargetParams) == 5 * 4 + 8 * 4
+    assert ctypes.sizeof(_lib.PredictionParams) == 8 * 4 + 8 * 4
 
 
 def test_no_cpu_fallback():

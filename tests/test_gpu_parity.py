@@ -616,3 +616,37 @@ def test_cfg5_shape_shard_equivalence(bx):
     assert torch.equal(torch.cat([p[1] for p in parts]), oi) and torch.equal(torch.cat([p[2] for p in parts]), oc)
     _, idx = orc.region_proposal(imgs[3]['deltas'], imgs[3]['anchors'], imgs[3]['scores'], (800, 1333), 1000)
     assert np.array_equal(oi[3].cpu().numpy(), idx)
+
+
+# ------------------------------------------------------------------------------------------------ f1 post-head filtering
+def test_post_ops_prediction(bx, golden):
+    from tf_eager_object_detection_b200.prediction import post_ops_prediction, post_ops_prediction_batched
+    hs, hd = syn.roi_head_outputs(np.random.default_rng(syn.seed_for(1, 77)), 300, 21)
+    rois = golden['c4_eval_rois']
+    b, c, s = post_ops_prediction(cu(hs), cu(hd), cu(rois), [600, 1000], [0, 0, 0, 0], [0.1, 0.1, 0.2, 0.2])
+    assert c.dtype == torch.int32 and np.array_equal(c.cpu().numpy(), golden['post_classes'])     # kept set + order bit-exact
+    assert np.array_equal(s.cpu().numpy(), golden['post_scores'])
+    close(b.cpu().numpy(), golden['post_boxes'], scale=1000.0)
+    assert post_ops_prediction(cu(hs), cu(hd), cu(rois), [600, 1000], None, None, score_threshold=2.0) == (None, None, None)
+    # batched, other limits, roi_counts padding; COCO-sized class count
+    rng = np.random.default_rng(5)
+    B, R, C = 3, 200, 81
+    sc, dl = zip(*[syn.roi_head_outputs(rng, R, C) for _ in range(B)])
+    rr = np.stack([syn.random_rois(rng, R, (600, 1000)) for _ in range(B)])
+    counts = np.int32([200, 120, 0])
+    det, cnt = post_ops_prediction_batched(cu(np.stack(sc)), cu(np.stack(dl)), cu(rr), [600, 1000], None, [0.1, 0.1, 0.2, 0.2],
+                                           max_num_per_class=100, max_num_per_image=100, score_threshold=0.02,
+                                           roi_counts=cu(counts))
+    for i in range(B):
+        n = counts[i]
+        ref = orc.post_ops_prediction(sc[i][:n], dl[i][:n], rr[i][:n], (600, 1000), stds=(0.1, 0.1, 0.2, 0.2),
+                                      max_num_per_class=100, max_num_per_image=100, score_threshold=0.02, num_classes=C)
+        k = int(cnt[i])
+        if ref[0] is None:
+            assert k == 0
+            continue
+        assert k == ref[0].shape[0]
+        d = det[i, :k].cpu().numpy()
+        assert np.array_equal(d[:, 5].astype(np.int32), ref[1]) and np.array_equal(d[:, 4], ref[2])
+        close(d[:, :4], ref[0], scale=1000.0)
+        assert (det[i, k:] == 0).all()

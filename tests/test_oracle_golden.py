@@ -129,3 +129,13 @@ def test_proposal_target(golden, name, kw):
         assert np.array_equal(v, golden['%s_%s' % (name, k)]), k
     if name == 'pt_pad':   # the np.random.choice(replace=True) branch really ran
         assert len(np.unique(out[5]['keep'])) < 2048
+
+
+def test_post_ops_prediction(golden):
+    """model/prediction.py:103-163 on synthetic roi-head outputs over the 300 eval rois."""
+    hs, hd = syn.roi_head_outputs(np.random.default_rng(syn.seed_for(1, 77)), 300, 21)
+    b, c, s = orc.post_ops_prediction(hs, hd, golden['c4_eval_rois'], (600, 1000), stds=(0.1, 0.1, 0.2, 0.2))
+    assert np.array_equal(b, golden['post_boxes']) and np.array_equal(c, golden['post_classes'])
+    assert np.array_equal(s, golden['post_scores']) and b.shape == (150, 4)
+    assert (np.diff(s) <= 0).all()
+    assert orc.post_ops_prediction(hs, hd, golden['c4_eval_rois'], (600, 1000), score_threshold=2.0) == (None, None, None)

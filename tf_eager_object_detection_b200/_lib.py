@@ -30,6 +30,12 @@ class ProposalTargetParams(ctypes.Structure):
                 ('total_num_samples', c_int), ('max_pos_samples', c_int), ('means', F4), ('stds', F4)]
 
 
+class PredictionParams(ctypes.Structure):
+    _fields_ = [('means', F4), ('stds', F4), ('image_h', c_int), ('image_w', c_int), ('num_classes', c_int),
+                ('max_per_class', c_int), ('max_per_image', c_int), ('nms_iou_threshold', c_float),
+                ('score_threshold', c_float), ('min_edge', c_float)]
+
+
 P = c_void_p  # device pointers travel as integers
 
 # name -> (restype, argtypes); every symbol include/boxpath.h declares
@@ -60,6 +66,7 @@ SIGNATURES = {
                                  P, c_void_p]),
     'bx_proposal_target': (c_int, [c_void_p, P, P, c_int, P, P, P, c_int, c_int, P, POINTER(ProposalTargetParams), P,
                                    P, P, P, P, P, P, c_void_p]),
+    'bx_post_ops_prediction': (c_int, [c_void_p, P, P, P, P, c_int, c_int, POINTER(PredictionParams), P, P, c_void_p]),
     'bx_c4_proposal_roi': (c_int, [c_void_p, P, P, P, P, c_int, c_int, c_int, c_int, c_int, POINTER(ProposalParams),
                                    c_float, c_int, c_int, P, P, P, P, c_void_p]),
     'bx_c4_proposal_roi_host': (c_int, [c_void_p, P, P, P, P, c_int, c_int, c_int, c_int, c_int,

@@ -35,6 +35,8 @@ void bx_set_error(const char* fmt, ...);
 int bx_ws_reserve(bx_handle* h, size_t bytes);       // ensure h->ws has >= bytes (may cudaMalloc; not in steady state)
 int bx_stage_reserve(bx_handle* h, size_t bytes);
 int bx_plan_reserve(bx_handle* h, size_t bytes);
+int bx_internal_nms_keys(bx_handle* h, const float* boxes, const uint32_t* keys, int batch, int n, int max_out,
+                         float iou_threshold, float* out_boxes, int* out_idx, int* out_count, cudaStream_t st);
 
 #define BX_REQUIRE(cond, code, ...)  \
   do {                               \

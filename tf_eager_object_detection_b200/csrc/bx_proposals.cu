@@ -589,6 +589,23 @@ extern "C" int bx_range_filter(bx_handle* h, const float* anchors, int n, int im
   return BX_OK;
 }
 
+// internal (bx_prediction.cu): greedy NMS over precomputed boxes with precomputed order keys (0 = excluded candidate)
+int bx_internal_nms_keys(bx_handle* h, const float* boxes, const uint32_t* keys, int batch, int n, int max_out,
+                         float iou_threshold, float* out_boxes, int* out_idx, int* out_count, cudaStream_t st) {
+  BX_REQUIRE(max_out <= kMaxPost, BX_ERR_UNSUPPORTED, "max_output_size %d > %d", max_out, kMaxPost);
+  BX_REQUIRE(n < (1 << 22), BX_ERR_UNSUPPORTED, "n must be < 2^22");
+  ProposalArgs a = {};
+  a.boxes = reinterpret_cast<const float4*>(boxes);
+  a.keys = keys;
+  a.n = n;
+  a.post_nms = max_out;
+  a.thr = iou_threshold;
+  a.out_boxes = reinterpret_cast<float4*>(out_boxes);
+  a.out_idx = out_idx;
+  a.out_count = out_count;
+  return launch_proposals(h, a, batch, st);
+}
+
 extern "C" int bx_nms(bx_handle* h, const float* boxes, const float* scores, int batch, int n, int max_out,
                       float iou_threshold, int* out_idx, int* out_count, void* stream) {
   BX_REQUIRE(h && boxes && scores && out_idx && out_count, BX_ERR_INVALID, "bx_nms: NULL argument");

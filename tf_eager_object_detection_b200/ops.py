@@ -263,6 +263,28 @@ def proposal_target(rois, gt, gt_labels, perm, num_classes=21, pos_iou_threshold
     return o_rois, o_lab, o_t, o_i, o_o, o_keep, o_cnt
 
 
+def post_ops_prediction(scores, deltas, rois, image_shape, means=(0, 0, 0, 0), stds=(1, 1, 1, 1), max_num_per_class=50,
+                        max_num_per_image=150, nms_iou_threshold=0.3, score_threshold=0.05, extractor_stride=16,
+                        roi_counts=None):
+    """f1 batched: scores [b,r,C] softmax; deltas [b,r,C,4] (or [b,r,4C]); rois [b,r,4] ->
+    (det [b,max_per_image,6] = (x1,y1,x2,y2,score,class) zero padded, count [b]).  No host sync."""
+    scores = to_device(scores, f32)
+    b, r, c = scores.shape
+    deltas = to_device(deltas, f32, scores.device).reshape(b, r, c, 4)
+    rois = to_device(rois, f32, scores.device)
+    dev, h, bw, st, lib = _ctx(scores)
+    p = _lib.PredictionParams(_lib.f4(means), _lib.f4(stds), int(image_shape[0]), int(image_shape[1]), int(c),
+                              int(max_num_per_class), int(max_num_per_image), float(nms_iou_threshold),
+                              float(score_threshold), float(extractor_stride if extractor_stride is not None else 0))
+    det, cnt = empty((b, int(max_num_per_image), 6), f32, dev), empty((b,), i32, dev)
+    rc = bw.ptr(to_device(roi_counts, i32, scores.device), INT32, (b,)) if roi_counts is not None else None
+    _lib.check(lib.bx_post_ops_prediction(h, bw.ptr(scores, FLOAT32, (b, r, c)) if r else 0,
+                                          bw.ptr(deltas, FLOAT32, (b, r, c, 4), 16) if r else 0,
+                                          bw.ptr(rois, FLOAT32, (b, r, 4), 16) if r else 0, rc, b, r, ctypes.byref(p),
+                                          bw.ptr(det, FLOAT32, (b, int(max_num_per_image), 6)), bw.ptr(cnt, INT32, (b,)), st))
+    return det, cnt
+
+
 def c4_proposal_roi(anchors, deltas, scores, feat, image_shape, post_nms, stride=16.0, pool_size=7,
                     max_pooling_flag=False, iou_threshold=0.7, means=(0, 0, 0, 0), stds=(1, 1, 1, 1), pre_nms_top_k=0,
                     min_size=0.0, out=None):

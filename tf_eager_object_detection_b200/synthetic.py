@@ -134,3 +134,13 @@ def fpn_image(cfg, image_index, image_hw=IMAGE_600x1000, channels=256, with_feat
     if with_features:
         out['feats'] = [features(rng, h, w, channels) for (h, w) in fpn_feature_shapes(image_hw)[:4]]
     return out
+
+
+def roi_head_outputs(rng, r, num_classes=21):
+    """Synthetic RoI-head outputs for the post-head filtering stage: softmax scores [r,C] with a few confident
+    foreground classes per roi (unique values), class-specific deltas [r,C,4] ~ N(0, 1)."""
+    logits = rng.normal(0.0, 1.0, (r, num_classes)) + 4.0 * (rng.random((r, num_classes)) < 0.08)
+    e = np.exp(logits - logits.max(axis=1, keepdims=True))
+    scores = (e / e.sum(axis=1, keepdims=True)).astype(F)
+    deltas = rng.normal(0.0, 1.0, (r, num_classes, 4)).astype(F)
+    return scores, deltas
