@@ -119,6 +119,15 @@ int bx_roi_pool(bx_handle* h, int mode, int pool, int pool_size, const float* fe
                 const float* rois, const int* box_ind, const int* roi_counts, int r, float stride, int image_h,
                 int image_w, float* out, void* stream);
 
+/* ---- f3 ("next" row): gradient of bx_roi_pool w.r.t. the feature map, i.e. the backward pass TF runs through
+ *      tf.image.crop_and_resize (+ the 2x2 pool) when scripts/train.py:99-103 differentiates the model (the boxes are
+ *      under tf.stop_gradient, model/roi_pooling.py:37,79,86).  Same arguments as bx_roi_pool; grad_out [r,P,P,c];
+ *      grad_feat [b,fh,fw,c] is zeroed by the call, then accumulated with fp32 atomics (summation order, hence the
+ *      last bits, vary from run to run).  feat is read only for BX_POOL_MAX2 (argmax).  c must be a multiple of 4. */
+int bx_roi_pool_grad(bx_handle* h, int mode, int pool, int pool_size, const float* feat, int b, int fh, int fw, int c,
+                     const float* rois, const int* box_ind, const int* roi_counts, int r, float stride, int image_h,
+                     int image_w, const float* grad_out, float* grad_feat, void* stream);
+
 /* ---- a6: model/fpn/base_fpn_model.py:303-324 BaseFPN._assign_levels.
  *      rois [r,4] -> out_level [r] int32 in [min_level,max_level]; out_order [r] int32 = concat over levels of the
  *      ascending indices of each level (the reference's `assign_level_idx`); out_counts [max_level-min_level+1]. */

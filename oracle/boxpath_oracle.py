@@ -413,3 +413,64 @@ def post_ops_prediction(roi_scores_softmax, roi_txtytwth, rois, image_shape, mea
     sc = np.concatenate(res_s); bb = np.concatenate(res_b); cc = np.concatenate(res_c)
     order = np.argsort(-sc, kind='stable')[:min(max_num_per_image, sc.size)]
     return bb[order], cc[order], sc[order]
+
+
+# --------------------------------------------------------------------------- f3 RoI-pooling backward (w.r.t. features)
+def crop_and_resize_grad_image(image_shape, boxes, box_ind, grad_crops):
+    """TF r1.13 `CropAndResizeGradImage` (the gradient TF applies for tf.image.crop_and_resize w.r.t. `image`,
+    recalled from core/kernels/crop_and_resize_op.cc like App. B.2): every in-range sample scatters
+    dtop = (1-ly) g, dbottom = ly g, then (1-lx) / lx of each to its left / right tap."""
+    b, h, w, c = image_shape
+    g = np.asarray(grad_crops, F)
+    bx = np.asarray(boxes, F); bi = np.asarray(box_ind).astype(np.int64)
+    r, ch, cw, _ = g.shape
+    out = np.zeros((b, h, w, c), F)
+    if r == 0:
+        return out
+    y1, x1, y2, x2 = bx[:, 0], bx[:, 1], bx[:, 2], bx[:, 3]
+    hs = (y2 - y1) * F(h - 1) / F(ch - 1) if ch > 1 else np.zeros(r, F)
+    ws = (x2 - x1) * F(w - 1) / F(cw - 1) if cw > 1 else np.zeros(r, F)
+    for y in range(ch):
+        in_y = ((y1 * F(h - 1) + F(y) * hs) if ch > 1 else F(0.5) * (y1 + y2) * F(h - 1)).astype(F)
+        oky = ~((in_y < 0) | (in_y > F(h - 1)))
+        top = np.floor(in_y); bot = np.ceil(in_y); ly = (in_y - top).astype(F)
+        for x in range(cw):
+            in_x = ((x1 * F(w - 1) + F(x) * ws) if cw > 1 else F(0.5) * (x1 + x2) * F(w - 1)).astype(F)
+            ok = oky & ~((in_x < 0) | (in_x > F(w - 1)))
+            k = np.nonzero(ok)[0]
+            if k.size == 0:
+                continue
+            left = np.floor(in_x[k]); right = np.ceil(in_x[k]); lx = (in_x[k] - left).astype(F)[:, None]
+            t_, b_ = top[k].astype(np.int64), bot[k].astype(np.int64)
+            l_, r_ = left.astype(np.int64), right.astype(np.int64)
+            gk = g[k, y, x]
+            dtop = (F(1) - ly[k, None]) * gk
+            dbot = ly[k, None] * gk
+            np.add.at(out, (bi[k], t_, l_), (F(1) - lx) * dtop)
+            np.add.at(out, (bi[k], t_, r_), lx * dtop)
+            np.add.at(out, (bi[k], b_, l_), (F(1) - lx) * dbot)
+            np.add.at(out, (bi[k], b_, r_), lx * dbot)
+    return out
+
+
+def roi_pool_c4_grad(feat, rois, stride, grad_out, pool_size=7, max_pooling_flag=True, box_ind=None):
+    """Gradient of roi_pool_c4 w.r.t. feat: MaxPooling2D gradient (all of it to the first maximal element of each 2x2
+    window, row-major — TF MaxPoolGrad) followed by crop_and_resize_grad_image."""
+    feat = np.asarray(feat, F); g = np.asarray(grad_out, F)
+    r = np.asarray(rois, F) / F(stride)
+    h, w = feat.shape[1:3]
+    bi = np.zeros(r.shape[0], np.int32) if box_ind is None else box_ind
+    nb = np.stack([r[:, 1] / F(h - 1), r[:, 0] / F(w - 1), r[:, 3] / F(h - 1), r[:, 2] / F(w - 1)], axis=1)
+    if not max_pooling_flag:
+        return crop_and_resize_grad_image(feat.shape, nb, bi, g)
+    q = 2 * pool_size
+    crops = crop_and_resize_tf(feat, nb, bi, q, q)
+    gc = np.zeros_like(crops)
+    n, _, _, c = crops.shape
+    for i in range(pool_size):
+        for j in range(pool_size):
+            win = crops[:, 2 * i:2 * i + 2, 2 * j:2 * j + 2].reshape(n, 4, c)
+            arg = np.argmax(win, axis=1)                       # first maximum
+            for s in range(4):
+                gc[:, 2 * i + s // 2, 2 * j + s % 2] = np.where(arg == s, g[:, i, j], F(0))
+    return crop_and_resize_grad_image(feat.shape, nb, bi, gc)

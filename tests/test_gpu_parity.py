@@ -650,3 +650,32 @@ def test_post_ops_prediction(bx, golden):
         assert np.array_equal(d[:, 5].astype(np.int32), ref[1]) and np.array_equal(d[:, 4], ref[2])
         close(d[:, :4], ref[0], scale=1000.0)
         assert (det[i, k:] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------ f3 RoI pooling backward
+@pytest.mark.parametrize('max_flag', [False, True])
+def test_roi_pool_backward(bx, max_flag):
+    """Gradient of the C4 extractor w.r.t. the feature map (what TF back-propagates through crop_and_resize + max pool
+    in scripts/train.py:99-103), through torch autograd on the mirror class."""
+    from tf_eager_object_detection_b200.roi_pooling import RoiPoolingCropAndResize
+    rng = np.random.default_rng(31 + max_flag)
+    feat = rng.standard_normal((2, 20, 30, 32), dtype=np.float32)
+    rois = syn.random_rois(rng, 40, (320, 480))
+    g = rng.standard_normal((40, 7, 7, 32), dtype=np.float32)
+    ft = cu(feat[:1]).requires_grad_(True)
+    out = RoiPoolingCropAndResize(7, max_flag)((ft, cu(rois), 16))
+    assert out.requires_grad
+    out.backward(cu(g))
+    ref = orc.roi_pool_c4_grad(feat[:1], rois, 16, g, 7, max_flag)
+    got = ft.grad.cpu().numpy()
+    close(got, ref, scale=np.abs(ref).max())            # fp32 atomics: summation order differs from the oracle's
+    assert np.array_equal(out.detach().cpu().numpy(), orc.roi_pool_c4(feat[:1], rois, 16, 7, max_flag))
+    # batched with box_ind through the functional op; linear in grad_out
+    from tf_eager_object_detection_b200 import _lib
+    bi = rng.integers(0, 2, 40).astype(np.int32)
+    pool = _lib.POOL_MAX2 if max_flag else _lib.POOL_NONE
+    g1 = bx.roi_pool_grad(_lib.ROI_STRIDE_NORM, pool, 7, cu(feat), cu(rois), cu(g), stride=16.0, box_ind=cu(bi))
+    ref2 = orc.roi_pool_c4_grad(feat, rois, 16, g, 7, max_flag, box_ind=bi)
+    close(g1.cpu().numpy(), ref2, scale=np.abs(ref2).max())
+    g2 = bx.roi_pool_grad(_lib.ROI_STRIDE_NORM, pool, 7, cu(feat), cu(rois), cu(2 * g), stride=16.0, box_ind=cu(bi))
+    assert torch.allclose(g2, 2 * g1, rtol=1e-5, atol=1e-5)

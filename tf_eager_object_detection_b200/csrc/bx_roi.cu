@@ -109,6 +109,118 @@ __global__ void __launch_bounds__(256) roi_pool_kernel(const RoiArgs a) {
   }
 }
 
+// ---- backward of the RoI extractors w.r.t. the feature map ("next" row f3): gradient of tf.image.crop_and_resize
+//      (TF CropAndResizeGradImage: each sample scatters (1-ly)(1-lx), (1-ly)lx, ly(1-lx), ly lx times its gradient to its 4
+//      taps) composed with the gradient of the 2x2 pool (max: all of it to the first maximal sample of the window in
+//      row-major order, as TF's MaxPoolGrad; avg: a quarter to each).  The boxes get no gradient (tf.stop_gradient,
+//      roi_pooling.py:37,79,86).  One CTA per (roi, py); fp32 atomics (red.global.add.v4.f32).
+struct RoiGradArgs {
+  RoiArgs a;              // forward description; a.out is unused
+  const float* grad_out;  // [r,P,P,c]
+  float* grad_feat;       // [b,fh,fw,c], pre-zeroed
+};
+
+template <int POOL>
+__global__ void __launch_bounds__(256) roi_pool_grad_kernel(const RoiGradArgs g) {
+  constexpr int S = (POOL == BX_POOL_NONE) ? 1 : 2;
+  const RoiArgs& a = g.a;
+  __shared__ Axis ax_y[2];
+  __shared__ Axis ax_x[kMaxQ];
+  __shared__ int s_meta[4];
+  const int P = a.P, Q = a.Q;
+  const int j = blockIdx.x / P, py = blockIdx.x % P;
+  const int tid = threadIdx.x;
+  const int cv = a.c / 4;
+  if (tid < Q + 2) {
+    int img = a.box_ind ? a.box_ind[j] : 0;
+    int zero = 0;
+    if (a.roi_counts) {
+      img = j / a.rois_per_image;
+      zero = (j % a.rois_per_image) >= a.roi_counts[img];
+    }
+    if (tid == 0) {
+      s_meta[0] = img;
+      s_meta[2] = zero || img < 0 || img >= a.b;
+    }
+    const NormBox nb = roi_norm_box(a, a.rois[j], a.lv[0].fh, a.lv[0].fw);
+    if (tid < Q) ax_x[tid] = sample_axis(nb.x1, nb.x2, tid, Q, nb.dimx, nb.pad);
+    else if (tid - Q < S) ax_y[tid - Q] = sample_axis(nb.y1, nb.y2, py * S + (tid - Q), Q, nb.dimy, nb.pad);
+  }
+  __syncthreads();
+  if (s_meta[2]) return;   // padded roi: its output was a constant, no gradient
+  const LevelFeat lf = a.lv[0];
+  const size_t img_off = static_cast<size_t>(s_meta[0]) * lf.fh * lf.fw * a.c;
+  const float4* feat = reinterpret_cast<const float4*>(lf.feat + img_off);
+  float4* gfeat = reinterpret_cast<float4*>(g.grad_feat + img_off);
+  const float4* gout = reinterpret_cast<const float4*>(g.grad_out + (static_cast<size_t>(j) * P + py) * P * a.c);
+  const int items = P * cv;
+  for (int it = tid; it < items; it += 256) {
+    const int px = it / cv, cg = it % cv;
+    const float4 go = gout[it];
+    float gs[S * S][4];   // gradient routed to each of the S*S samples of this output pixel, per channel
+    if (POOL == BX_POOL_NONE) {
+      gs[0][0] = go.x; gs[0][1] = go.y; gs[0][2] = go.z; gs[0][3] = go.w;
+    } else if (POOL == BX_POOL_AVG2) {
+#pragma unroll
+      for (int s = 0; s < S * S; ++s) { gs[s][0] = go.x / 4.0f; gs[s][1] = go.y / 4.0f; gs[s][2] = go.z / 4.0f; gs[s][3] = go.w / 4.0f; }
+    } else {
+      // recompute the four sample values and give the gradient to the first maximum per channel
+      float best[4];
+      int arg[4];
+#pragma unroll
+      for (int sy = 0; sy < S; ++sy)
+#pragma unroll
+        for (int sx = 0; sx < S; ++sx) {
+          const Axis ay = ax_y[sy], axx = ax_x[px * S + sx];
+          float val[4] = {a.extrapolation, a.extrapolation, a.extrapolation, a.extrapolation};
+          if (ay.valid && axx.valid) {
+            const float4 tl = __ldg(feat + (static_cast<size_t>(ay.lo) * lf.fw + axx.lo) * cv + cg);
+            const float4 tr = __ldg(feat + (static_cast<size_t>(ay.lo) * lf.fw + axx.hi) * cv + cg);
+            const float4 bl = __ldg(feat + (static_cast<size_t>(ay.hi) * lf.fw + axx.lo) * cv + cg);
+            const float4 br = __ldg(feat + (static_cast<size_t>(ay.hi) * lf.fw + axx.hi) * cv + cg);
+            const float* ptl = reinterpret_cast<const float*>(&tl); const float* ptr = reinterpret_cast<const float*>(&tr);
+            const float* pbl = reinterpret_cast<const float*>(&bl); const float* pbr = reinterpret_cast<const float*>(&br);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const float top = ptl[v] + (ptr[v] - ptl[v]) * axx.lerp;
+              const float bot = pbl[v] + (pbr[v] - pbl[v]) * axx.lerp;
+              val[v] = top + (bot - top) * ay.lerp;
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if ((sy == 0 && sx == 0) || val[v] > best[v]) { best[v] = val[v]; arg[v] = sy * S + sx; }
+        }
+      const float gov[4] = {go.x, go.y, go.z, go.w};
+#pragma unroll
+      for (int s = 0; s < S * S; ++s)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) gs[s][v] = (arg[v] == s) ? gov[v] : 0.0f;
+    }
+#pragma unroll
+    for (int sy = 0; sy < S; ++sy)
+#pragma unroll
+      for (int sx = 0; sx < S; ++sx) {
+        const Axis ay = ax_y[sy], axx = ax_x[px * S + sx];
+        if (!(ay.valid && axx.valid)) continue;   // extrapolated sample: constant, no gradient
+        const float* q = gs[sy * S + sx];
+        if (q[0] == 0.0f && q[1] == 0.0f && q[2] == 0.0f && q[3] == 0.0f) continue;
+        const float wy1 = ay.lerp, wy0 = 1.0f - ay.lerp, wx1 = axx.lerp, wx0 = 1.0f - axx.lerp;
+        float4 t;
+        const float dt0 = wy0 * q[0], dt1 = wy0 * q[1], dt2 = wy0 * q[2], dt3 = wy0 * q[3];   // dtop = (1 - ly) * g
+        const float db0 = wy1 * q[0], db1 = wy1 * q[1], db2 = wy1 * q[2], db3 = wy1 * q[3];   // dbottom = ly * g
+        t = make_float4(wx0 * dt0, wx0 * dt1, wx0 * dt2, wx0 * dt3);
+        atomicAdd(gfeat + (static_cast<size_t>(ay.lo) * lf.fw + axx.lo) * cv + cg, t);
+        t = make_float4(wx1 * dt0, wx1 * dt1, wx1 * dt2, wx1 * dt3);
+        atomicAdd(gfeat + (static_cast<size_t>(ay.lo) * lf.fw + axx.hi) * cv + cg, t);
+        t = make_float4(wx0 * db0, wx0 * db1, wx0 * db2, wx0 * db3);
+        atomicAdd(gfeat + (static_cast<size_t>(ay.hi) * lf.fw + axx.lo) * cv + cg, t);
+        t = make_float4(wx1 * db0, wx1 * db1, wx1 * db2, wx1 * db3);
+        atomicAdd(gfeat + (static_cast<size_t>(ay.hi) * lf.fw + axx.hi) * cv + cg, t);
+      }
+  }
+}
+
 template <typename VecT>
 int launch_roi_v(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
   const int grid = a.r * a.P;
@@ -264,6 +376,49 @@ extern "C" int bx_roi_pool(bx_handle* h, int mode, int pool, int pool_size, cons
   a.extrapolation = 0.0f;
   a.out = out;
   return launch_roi(h, a, pool, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bx_roi_pool_grad(bx_handle* h, int mode, int pool, int pool_size, const float* feat, int b, int fh,
+                                int fw, int c, const float* rois, const int* box_ind, const int* roi_counts, int r,
+                                float stride, int image_h, int image_w, const float* grad_out, float* grad_feat,
+                                void* stream) {
+  int rc = check_roi_common("bx_roi_pool_grad", h, pool_size, c, r, rois, grad_feat);
+  if (rc) return rc;
+  BX_REQUIRE(grad_out || r == 0, BX_ERR_INVALID, "bx_roi_pool_grad: NULL grad_out");
+  BX_REQUIRE(b > 0 && fh > 1 && fw > 1, BX_ERR_INVALID, "bx_roi_pool_grad: bad feature map");
+  BX_REQUIRE(mode >= 0 && mode <= 2 && pool >= 0 && pool <= 2, BX_ERR_INVALID, "bx_roi_pool_grad: bad mode/pool enum");
+  BX_REQUIRE(pool != BX_POOL_MAX2 || feat, BX_ERR_INVALID, "bx_roi_pool_grad: the max-pool gradient needs the features");
+  BX_REQUIRE(mode == BX_ROI_IMAGE_NORM ? (image_h > 0 && image_w > 0) : (stride > 0.0f), BX_ERR_INVALID,
+             "bx_roi_pool_grad: stride (or image shape) must be positive");
+  BX_REQUIRE(!roi_counts || (r % b == 0), BX_ERR_INVALID, "bx_roi_pool_grad: with roi_counts, r must be batch * rois_per_image");
+  BX_REQUIRE(c % 4 == 0 && bx_aligned(grad_feat, 16) && bx_aligned(grad_out, 16) && bx_aligned(feat, 16),
+             BX_ERR_UNSUPPORTED, "bx_roi_pool_grad: channels must be a multiple of 4 and tensors 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BX_CUDA(cudaMemsetAsync(grad_feat, 0, sizeof(float) * static_cast<size_t>(b) * fh * fw * c, st));
+  if (r == 0) return BX_OK;
+  RoiGradArgs g = {};
+  g.a.lv[0] = {feat, fh, fw};
+  g.a.n_levels = 1;
+  g.a.rois = reinterpret_cast<const float4*>(rois);
+  g.a.box_ind = box_ind;
+  g.a.roi_counts = roi_counts;
+  g.a.rois_per_image = roi_counts ? r / b : 0;
+  g.a.r = r; g.a.b = b; g.a.c = c;
+  g.a.mode = mode;
+  g.a.P = pool_size;
+  g.a.Q = (pool == BX_POOL_NONE) ? pool_size : 2 * pool_size;
+  g.a.stride = stride;
+  g.a.image_h = static_cast<float>(image_h);
+  g.a.image_w = static_cast<float>(image_w);
+  g.a.extrapolation = 0.0f;
+  g.grad_out = grad_out;
+  g.grad_feat = grad_feat;
+  const int grid = r * pool_size;
+  if (pool == BX_POOL_NONE) roi_pool_grad_kernel<BX_POOL_NONE><<<grid, 256, 0, st>>>(g);
+  else if (pool == BX_POOL_MAX2) roi_pool_grad_kernel<BX_POOL_MAX2><<<grid, 256, 0, st>>>(g);
+  else roi_pool_grad_kernel<BX_POOL_AVG2><<<grid, 256, 0, st>>>(g);
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
 }
 
 extern "C" int bx_fpn_assign_levels(bx_handle* h, const float* rois, int r, int min_level, int max_level,

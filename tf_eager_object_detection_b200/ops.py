@@ -159,6 +159,52 @@ def roi_pool(mode, pool, pool_size, feat, rois, stride=16.0, image_shape=(0, 0),
     return out
 
 
+def roi_pool_grad(mode, pool, pool_size, feat, rois, grad_out, stride=16.0, image_shape=(0, 0), box_ind=None,
+                  roi_counts=None):
+    """f3: gradient of roi_pool w.r.t. feat: grad_out [r,P,P,c] -> grad_feat [b,fh,fw,c]."""
+    feat = to_device(feat, f32)
+    rois = to_device(rois, f32, feat.device).reshape(-1, 4)
+    grad_out = to_device(grad_out, f32, feat.device)
+    b, fh, fw, c = feat.shape
+    r = rois.shape[0]
+    dev, h, bw, st, lib = _ctx(feat)
+    gf = empty((b, fh, fw, c), f32, dev)
+    bi = bw.ptr(to_device(box_ind, i32, feat.device), INT32, (r,)) if (box_ind is not None and r) else None
+    rc = bw.ptr(to_device(roi_counts, i32, feat.device), INT32, (b,)) if roi_counts is not None else None
+    _lib.check(lib.bx_roi_pool_grad(h, mode, pool, int(pool_size), bw.ptr(feat, FLOAT32, (b, fh, fw, c), 16), b, fh, fw, c,
+                                    bw.ptr(rois, FLOAT32, (r, 4), 16) if r else 0, bi, rc, r, float(stride),
+                                    int(image_shape[0]), int(image_shape[1]),
+                                    bw.ptr(grad_out, FLOAT32, (r, pool_size, pool_size, c), 16) if r else 0,
+                                    bw.ptr(gf, FLOAT32, (b, fh, fw, c), 16), st))
+    return gf
+
+
+class _RoiPoolFn(torch.autograd.Function):
+    """roi_pool with a feature-map gradient (the boxes are constants, as under tf.stop_gradient in the reference)."""
+
+    @staticmethod
+    def forward(ctx, feat, rois, mode, pool, pool_size, stride, image_shape, box_ind, roi_counts):
+        out = roi_pool(mode, pool, pool_size, feat, rois, stride, image_shape, box_ind, roi_counts)
+        ctx.save_for_backward(feat.detach(), rois.detach())
+        ctx.cfg = (mode, pool, pool_size, stride, image_shape, box_ind, roi_counts)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        feat, rois = ctx.saved_tensors
+        mode, pool, pool_size, stride, image_shape, box_ind, roi_counts = ctx.cfg
+        gf = roi_pool_grad(mode, pool, pool_size, feat, rois, grad_out.contiguous(), stride, image_shape, box_ind, roi_counts)
+        return gf, None, None, None, None, None, None, None, None
+
+
+def roi_pool_autograd(mode, pool, pool_size, feat, rois, stride=16.0, image_shape=(0, 0), box_ind=None, roi_counts=None):
+    """roi_pool that records a backward pass when `feat` requires grad (training drop-in); plain roi_pool otherwise."""
+    if isinstance(feat, torch.Tensor) and feat.requires_grad and torch.is_grad_enabled():
+        rois_t = to_device(rois, f32, feat.device)
+        return _RoiPoolFn.apply(feat, rois_t, mode, pool, pool_size, stride, image_shape, box_ind, roi_counts)
+    return roi_pool(mode, pool, pool_size, feat, rois, stride, image_shape, box_ind, roi_counts)
+
+
 def fpn_assign_levels(rois, min_level=2, max_level=5):
     """a6: rois [r,4] -> (level [r] int32, order [r] int32 level-major stable, counts [L] int32)."""
     rois = to_device(rois, f32)

@@ -12,7 +12,7 @@ class RoiPoolingCropAndResize2:
 
     def call(self, inputs, training=None, mask=None):
         shared_layers, rois, image_shape = inputs
-        return ops.roi_pool(_lib.ROI_IMAGE_NORM, _lib.POOL_MAX2, self._pool_size, shared_layers, rois,
+        return ops.roi_pool_autograd(_lib.ROI_IMAGE_NORM, _lib.POOL_MAX2, self._pool_size, shared_layers, rois,
                             image_shape=image_shape)
 
     __call__ = call
@@ -29,7 +29,7 @@ class RoiPoolingCropAndResize:
     def call(self, inputs, training=None, mask=None):
         shared_layers, rois, extractor_stride = inputs
         pool = _lib.POOL_MAX2 if self._max_pooling_flag else _lib.POOL_NONE
-        return ops.roi_pool(_lib.ROI_STRIDE_NORM, pool, self._pool_size, shared_layers, rois,
+        return ops.roi_pool_autograd(_lib.ROI_STRIDE_NORM, pool, self._pool_size, shared_layers, rois,
                             stride=float(extractor_stride))
 
     __call__ = call
@@ -43,7 +43,7 @@ class RoiPoolingRoiAlign:
 
     def call(self, inputs, training=None, mask=None):
         shared_layers, rois, extractor_stride = inputs
-        return ops.roi_pool(_lib.ROI_ALIGN_PAD, _lib.POOL_AVG2, self._pool_size, shared_layers, rois,
+        return ops.roi_pool_autograd(_lib.ROI_ALIGN_PAD, _lib.POOL_AVG2, self._pool_size, shared_layers, rois,
                             stride=float(extractor_stride))
 
     __call__ = call
