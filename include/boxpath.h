@@ -128,6 +128,21 @@ int bx_roi_pool_grad(bx_handle* h, int mode, int pool, int pool_size, const floa
                      const float* rois, const int* box_ind, const int* roi_counts, int r, float stride, int image_h,
                      int image_w, const float* grad_out, float* grad_feat, void* stream);
 
+/* ---- f3 ("next" row): model/losses.py:16-28 smooth_l1_loss as called at faster_rcnn/base_faster_rcnn_model.py:209-211
+ *      (dim=[0,1], reduce_all=1: the total sum) and :220-222 (dim=[1], reduce_all=0: sum / n).  pred, target, in_w,
+ *      out_w [n,d]; out_loss [1]; out_grad [n,d] or NULL = d loss / d pred (the `sign` mask is a constant,
+ *      losses.py:21).  Deterministic reduction (fixed tree, fp64 partials). */
+int bx_smooth_l1_loss(bx_handle* h, const float* pred, const float* target, const float* in_w, const float* out_w,
+                      long long n, int d, float sigma, int reduce_all, float* out_loss, float* out_grad, void* stream);
+
+/* ---- f3: model/losses.py:4-13 cls_loss = tf.losses.sparse_softmax_cross_entropy(logits, to_int32(labels), weight)
+ *      with the caller's `labels >= 0` gather (base_faster_rcnn_model.py:204-207) folded in: rows whose label is
+ *      negative are skipped.  logits [n,c]; labels [n] fp32 (what bx_anchor_target / bx_proposal_target emit);
+ *      loss = weight * sum(logsumexp(x) - x[label]) / #selected (0 when none, or weight == 0:
+ *      SUM_BY_NONZERO_WEIGHTS).  out_count (nullable) = #selected; out_grad [n,c] or NULL = d loss / d logits. */
+int bx_cls_loss(bx_handle* h, const float* logits, const float* labels, int n, int c, float weight, float* out_loss,
+                int* out_count, float* out_grad, void* stream);
+
 /* ---- a6: model/fpn/base_fpn_model.py:303-324 BaseFPN._assign_levels.
  *      rois [r,4] -> out_level [r] int32 in [min_level,max_level]; out_order [r] int32 = concat over levels of the
  *      ascending indices of each level (the reference's `assign_level_idx`); out_counts [max_level-min_level+1]. */

@@ -474,3 +474,54 @@ def roi_pool_c4_grad(feat, rois, stride, grad_out, pool_size=7, max_pooling_flag
             for s in range(4):
                 gc[:, 2 * i + s // 2, 2 * j + s % 2] = np.where(arg == s, g[:, i, j], F(0))
     return crop_and_resize_grad_image(feat.shape, nb, bi, gc)
+
+
+# --------------------------------------------------------------------------- f3 losses (model/losses.py)
+def smooth_l1_loss(pred, target, in_w, out_w, sigma=1.0, dim=(1,)):
+    """model/losses.py:16-28.  dim=[1]: mean over rows of the row sums; dim=[0,1]: the total sum."""
+    s2 = F(sigma) * F(sigma)
+    d = np.asarray(in_w, F) * (np.asarray(pred, F) - np.asarray(target, F))
+    a = np.abs(d)
+    sign = (a < F(1.0) / s2).astype(F)
+    per = (d * d) * (s2 / F(2)) * sign + (a - F(0.5) / s2) * (F(1) - sign)
+    per = np.asarray(out_w, F) * per
+    return F(np.mean(np.sum(per, axis=tuple(dim), dtype=F), dtype=F))
+
+
+def smooth_l1_loss_grad(pred, target, in_w, out_w, sigma=1.0, dim=(1,)):
+    """d loss / d pred (sign is under stop_gradient, losses.py:21)."""
+    s2 = F(sigma) * F(sigma)
+    in_w = np.asarray(in_w, F)
+    d = in_w * (np.asarray(pred, F) - np.asarray(target, F))
+    a = np.abs(d)
+    sign = a < F(1.0) / s2
+    dd = np.where(sign, d * s2, np.sign(d)).astype(F)
+    denom = F(1) if tuple(dim) == (0, 1) else F(np.asarray(pred).shape[0])
+    return (np.asarray(out_w, F) * dd * in_w / denom).astype(F)
+
+
+def cls_loss(logits, labels, weight=1.0):
+    """model/losses.py:4-13 (tf.losses.sparse_softmax_cross_entropy, SUM_BY_NONZERO_WEIGHTS) with the caller's
+    `labels >= 0` gather (base_faster_rcnn_model.py:204-206) folded in: rows with a negative label are skipped."""
+    x = np.asarray(logits, F); lab = np.asarray(labels)
+    sel = np.nonzero(lab >= 0)[0]
+    if sel.size == 0 or weight == 0:
+        return F(0)
+    x = x[sel]; li = lab[sel].astype(np.int64)
+    z = x - x.max(axis=1, keepdims=True)
+    per = np.log(np.exp(z).sum(axis=1, dtype=F)) - z[np.arange(li.size), li]
+    return F(np.sum(per.astype(F) * F(weight), dtype=F) / F(sel.size))
+
+
+def cls_loss_grad(logits, labels, weight=1.0):
+    x = np.asarray(logits, F); lab = np.asarray(labels)
+    g = np.zeros_like(x)
+    sel = np.nonzero(lab >= 0)[0]
+    if sel.size == 0 or weight == 0:
+        return g
+    z = x[sel] - x[sel].max(axis=1, keepdims=True)
+    e = np.exp(z)
+    p = e / e.sum(axis=1, keepdims=True, dtype=F)
+    p[np.arange(sel.size), lab[sel].astype(np.int64)] -= F(1)
+    g[sel] = p * (F(weight) / F(sel.size))
+    return g

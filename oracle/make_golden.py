@@ -185,6 +185,26 @@ def main():
                               score_threshold=0.05, extractor_stride=16, num_classes=21)
     g['post_boxes'], g['post_classes'], g['post_scores'] = np.asarray(pb), np.asarray(pc), np.asarray(ps)
 
+    # ---- f3: the reference's losses.py on the RPN / RoI-head shapes it is called with
+    from object_detection.model.losses import cls_loss as ref_cls_loss, smooth_l1_loss as ref_sl1
+    lrng = np.random.default_rng(syn.seed_for(1, 78))
+    n_rpn = g['at_labels'].shape[0]
+    rpn_pred = (lrng.normal(0, 1, (n_rpn, 4)) * 0.5).astype(np.float32)
+    g['loss_rpn_pred'] = rpn_pred
+    g['loss_rpn_reg'] = np.asarray(ref_sl1(tf.constant(rpn_pred), tf.constant(g['at_targets']), tf.constant(g['at_in_w']),
+                                           tf.constant(g['at_out_w']), 3.0, dim=[0, 1]))
+    rpn_logits = lrng.normal(0, 2, (n_rpn, 2)).astype(np.float32)
+    sel = np.nonzero(g['at_labels'] >= 0)[0]                     # base_faster_rcnn_model.py:204-207
+    g['loss_rpn_logits'] = rpn_logits
+    g['loss_rpn_cls'] = np.asarray(ref_cls_loss(tf.constant(rpn_logits[sel]), tf.constant(g['at_labels'][sel])))
+    n_roi = g['pt_labels'].shape[0]
+    roi_pred = lrng.normal(0, 1, (n_roi, 84)).astype(np.float32)
+    roi_logits = lrng.normal(0, 2, (n_roi, 21)).astype(np.float32)
+    g['loss_roi_pred'], g['loss_roi_logits'] = roi_pred, roi_logits
+    g['loss_roi_reg'] = np.asarray(ref_sl1(tf.constant(roi_pred), tf.constant(g['pt_targets']), tf.constant(g['pt_in_w']),
+                                           tf.constant(g['pt_out_w']), sigma=1.0))
+    g['loss_roi_cls'] = np.asarray(ref_cls_loss(tf.constant(roi_logits), tf.constant(g['pt_labels'])))
+
     np.savez_compressed(os.path.join(OUT, 'reference_on_shim.npz'), **g)
     sz = os.path.getsize(os.path.join(OUT, 'reference_on_shim.npz'))
     print('wrote %d arrays, %.1f KiB' % (len(g), sz / 1024))

@@ -251,6 +251,36 @@ exp = _un(np.exp)
 log = _un(np.log)
 sqrt = _un(np.sqrt)
 floor = _un(np.floor)
+abs = _un(np.abs)  # noqa: A001
+less = _bin(np.less)
+
+
+def pow(x, y):  # noqa: A001
+    x = np.asarray(x)
+    return np.power(x, np.asarray(y, dtype=x.dtype)).view(EagerTensor)
+
+
+def reduce_mean(x, axis=None):
+    x = np.asarray(x)
+    axis = tuple(axis) if isinstance(axis, (list, tuple)) else axis
+    return np.asarray(np.mean(x, axis=axis, dtype=x.dtype)).view(EagerTensor)
+
+
+def _sparse_softmax_cross_entropy(logits, labels, weights=1.0):
+    """tf.losses.sparse_softmax_cross_entropy, TF r1.13 (python/ops/losses/losses_impl.py): per-row
+    `logsumexp(x) - x[label]` (kernel: max-shifted, core/kernels/xent_op.h), times `weights`, reduction
+    SUM_BY_NONZERO_WEIGHTS = sum / number of rows with a non-zero weight (0 when there are none)."""
+    x = np.asarray(logits, np.float32)
+    lab = np.asarray(labels).astype(np.int64).reshape(-1)
+    w = np.broadcast_to(np.asarray(weights, np.float32), lab.shape)
+    z = x - x.max(axis=1, keepdims=True)
+    per = np.log(np.exp(z).sum(axis=1, dtype=np.float32)) - z[np.arange(lab.size), lab]
+    present = np.float32(np.count_nonzero(w))
+    total = np.sum(per.astype(np.float32) * w, dtype=np.float32)
+    return np.asarray(total / present if present > 0 else np.float32(0), np.float32).view(EagerTensor)
+
+
+losses = types.SimpleNamespace(sparse_softmax_cross_entropy=_sparse_softmax_cross_entropy)
 
 
 def reduce_max(x, axis=None):
@@ -259,6 +289,7 @@ def reduce_max(x, axis=None):
 
 def reduce_sum(x, axis=None):
     x = np.asarray(x)
+    axis = tuple(axis) if isinstance(axis, (list, tuple)) else axis
     return np.asarray(np.sum(x, axis=axis, dtype=x.dtype)).view(EagerTensor)
 
 

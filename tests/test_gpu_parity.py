@@ -679,3 +679,38 @@ def test_roi_pool_backward(bx, max_flag):
     close(g1.cpu().numpy(), ref2, scale=np.abs(ref2).max())
     g2 = bx.roi_pool_grad(_lib.ROI_STRIDE_NORM, pool, 7, cu(feat), cu(rois), cu(2 * g), stride=16.0, box_ind=cu(bi))
     assert torch.allclose(g2, 2 * g1, rtol=1e-5, atol=1e-5)
+
+
+def test_losses(bx, golden):
+    """model/losses.py through the mirror: values against the reference-on-shim goldens and the oracle, gradients
+    (through torch autograd) against the oracle's."""
+    from tf_eager_object_detection_b200.losses import cls_loss, smooth_l1_loss
+    g = golden
+    cases = [(g['loss_rpn_pred'], g['at_targets'], g['at_in_w'], g['at_out_w'], 3.0, [0, 1], g['loss_rpn_reg']),
+             (g['loss_roi_pred'], g['pt_targets'], g['pt_in_w'], g['pt_out_w'], 1.0, [1], g['loss_roi_reg'])]
+    for pred, tgt, iw, ow, sigma, dim, want in cases:
+        p = cu(pred).requires_grad_(True)
+        loss = smooth_l1_loss(p, cu(tgt), cu(iw), cu(ow), sigma, dim)
+        assert loss.shape == () and np.isclose(float(loss.detach()), float(want), rtol=1e-5)
+        (3.0 * loss).backward()
+        ref = 3.0 * orc.smooth_l1_loss_grad(pred, tgt, iw, ow, sigma, tuple(dim))
+        close(p.grad.cpu().numpy(), ref, scale=np.abs(ref).max())
+        again = smooth_l1_loss(cu(pred), cu(tgt), cu(iw), cu(ow), sigma, dim)
+        assert float(again) == float(loss.detach())                       # deterministic reduction
+    for logits, labels, want in ((g['loss_rpn_logits'], g['at_labels'], g['loss_rpn_cls']),
+                                 (g['loss_roi_logits'], g['pt_labels'], g['loss_roi_cls'])):
+        x = cu(logits).requires_grad_(True)
+        loss = cls_loss(x, cu(labels))
+        assert np.isclose(float(loss.detach()), float(want), rtol=1e-5)
+        loss.backward()
+        ref = orc.cls_loss_grad(logits, labels)
+        close(x.grad.cpu().numpy(), ref, scale=np.abs(ref).max())
+    # edge cases: nothing selected, empty input, weight
+    none = cls_loss(cu(g['loss_roi_logits']), cu(np.full(128, -1, np.float32)))
+    assert float(none) == 0.0
+    assert float(bx.cls_loss(cu(np.zeros((0, 21), np.float32)), cu(np.zeros((0,), np.float32)))) == 0.0
+    w = bx.cls_loss(cu(g['loss_roi_logits']), cu(g['pt_labels']), weight=0.5)
+    assert np.isclose(float(w), 0.5 * float(g['loss_roi_cls']), rtol=1e-5)
+    assert float(bx.smooth_l1_loss(*(cu(np.zeros((0, 4), np.float32)),) * 4)) == 0.0
+    with pytest.raises(NotImplementedError):
+        smooth_l1_loss(cu(g['loss_roi_pred']), cu(g['pt_targets']), cu(g['pt_in_w']), cu(g['pt_out_w']), dim=[0])

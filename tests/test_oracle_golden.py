@@ -139,3 +139,61 @@ def test_post_ops_prediction(golden):
     assert np.array_equal(s, golden['post_scores']) and b.shape == (150, 4)
     assert (np.diff(s) <= 0).all()
     assert orc.post_ops_prediction(hs, hd, golden['c4_eval_rois'], (600, 1000), score_threshold=2.0) == (None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------ f3 losses + RoI backward
+def test_losses_match_reference_on_shim(golden):
+    g = golden
+    assert np.isclose(orc.smooth_l1_loss(g['loss_rpn_pred'], g['at_targets'], g['at_in_w'], g['at_out_w'], 3.0, (0, 1)),
+                      g['loss_rpn_reg'], rtol=1e-5)
+    assert np.isclose(orc.smooth_l1_loss(g['loss_roi_pred'], g['pt_targets'], g['pt_in_w'], g['pt_out_w'], 1.0, (1,)),
+                      g['loss_roi_reg'], rtol=1e-5)
+    assert np.isclose(orc.cls_loss(g['loss_rpn_logits'], g['at_labels']), g['loss_rpn_cls'], rtol=1e-5)
+    assert np.isclose(orc.cls_loss(g['loss_roi_logits'], g['pt_labels']), g['loss_roi_cls'], rtol=1e-5)
+
+
+def test_loss_and_roi_gradients_against_torch_autograd(golden):
+    """Independent witness for the oracle's hand-written gradients: torch autograd through a torch restatement."""
+    import torch
+    import torch.nn.functional as tnf
+    g = golden
+    p = torch.tensor(g['loss_roi_pred'], requires_grad=True)
+    d = torch.tensor(g['pt_in_w']) * (p - torch.tensor(g['pt_targets']))
+    per = torch.where(d.abs() < 1.0, 0.5 * d * d, d.abs() - 0.5) * torch.tensor(g['pt_out_w'])
+    per.sum(1).mean().backward()
+    np.testing.assert_allclose(orc.smooth_l1_loss_grad(g['loss_roi_pred'], g['pt_targets'], g['pt_in_w'], g['pt_out_w']),
+                               p.grad.numpy(), rtol=1e-5, atol=1e-8)
+    x = torch.tensor(g['loss_rpn_logits'], requires_grad=True)
+    lab = torch.tensor(g['at_labels']).long()
+    tnf.cross_entropy(x, lab, ignore_index=-1).backward()
+    np.testing.assert_allclose(orc.cls_loss_grad(g['loss_rpn_logits'], g['at_labels']), x.grad.numpy(), rtol=1e-4,
+                               atol=1e-9)
+    assert np.isclose(orc.cls_loss(g['loss_rpn_logits'], g['at_labels']),
+                      float(tnf.cross_entropy(x.detach(), lab, ignore_index=-1)), rtol=1e-5)
+    # RoI-pooling backward: autograd through a dense bilinear-weight restatement of the C4 extractor
+    rng = np.random.default_rng(5)
+    feat = rng.standard_normal((1, 9, 11, 4), dtype=np.float32)
+    rois = syn.random_rois(rng, 6, (144, 176))
+    go = rng.standard_normal((6, 3, 3, 4), dtype=np.float32)
+    for max_flag in (False, True):
+        ft = torch.tensor(feat, dtype=torch.float64, requires_grad=True)
+        q = 6 if max_flag else 3
+        r = rois.astype(np.float64) / 16.0
+        crops = []
+        for k in range(6):
+            ys = r[k, 1] + np.arange(q) * ((r[k, 3] - r[k, 1]) / (q - 1))
+            xs = r[k, 0] + np.arange(q) * ((r[k, 2] - r[k, 0]) / (q - 1))
+            wy = torch.zeros(q, 9, dtype=torch.float64); wx = torch.zeros(q, 11, dtype=torch.float64)
+            for i, y in enumerate(ys):
+                if 0 <= y <= 8:
+                    t = int(np.floor(y)); wy[i, t] += 1 - (y - t); wy[i, int(np.ceil(y))] += y - t
+            for i, xx in enumerate(xs):
+                if 0 <= xx <= 10:
+                    t = int(np.floor(xx)); wx[i, t] += 1 - (xx - t); wx[i, int(np.ceil(xx))] += xx - t
+            crops.append(torch.einsum('yh,xw,hwc->yxc', wy, wx, ft[0]))
+        out = torch.stack(crops)
+        if max_flag:
+            out = tnf.max_pool2d(out.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+        out.backward(torch.tensor(go, dtype=torch.float64))
+        got = orc.roi_pool_c4_grad(feat, rois, 16, go, 3, max_flag)
+        np.testing.assert_allclose(got, ft.grad.numpy(), rtol=1e-4, atol=1e-5)

@@ -309,6 +309,52 @@ def proposal_target(rois, gt, gt_labels, perm, num_classes=21, pos_iou_threshold
     return o_rois, o_lab, o_t, o_i, o_o, o_keep, o_cnt
 
 
+def smooth_l1_loss(pred, target, in_w, out_w, sigma=1.0, dim=(1,), with_grad=False):
+    """f3: model/losses.py:16-28.  pred/target/in_w/out_w [n,d] -> loss [] (0-dim fp32), optionally d loss / d pred."""
+    dim = tuple(int(v) for v in dim)
+    if dim not in ((1,), (0, 1)):
+        raise NotImplementedError('smooth_l1_loss: dim must be [1] or [0, 1] (the two forms the reference uses)')
+    pred = to_device(pred, f32)
+    n, d = pred.shape
+    dev, h, bw, st, lib = _ctx(pred)
+    args = [bw.ptr(to_device(t, f32, pred.device), FLOAT32, (n, d)) if n else 0 for t in (target, in_w, out_w)]
+    loss = empty((1,), f32, dev)
+    grad = empty((n, d), f32, dev) if with_grad else None
+    _lib.check(lib.bx_smooth_l1_loss(h, bw.ptr(pred, FLOAT32, (n, d)) if n else 0, *args, n, d, float(sigma),
+                                     int(dim == (0, 1)), bw.ptr(loss, FLOAT32, (1,)),
+                                     bw.ptr(grad, FLOAT32, (n, d)) if (with_grad and n) else None, st))
+    return (loss.reshape(()), grad) if with_grad else loss.reshape(())
+
+
+def cls_loss(logits, labels, weight=1.0, with_grad=False):
+    """f3: model/losses.py:4-13 with the `labels >= 0` gather folded in.  logits [n,c]; labels [n] -> loss []."""
+    logits = to_device(logits, f32)
+    n, c = logits.shape
+    labels = to_device(labels, f32, logits.device).reshape(-1)
+    dev, h, bw, st, lib = _ctx(logits)
+    loss = empty((1,), f32, dev)
+    grad = empty((n, c), f32, dev) if with_grad else None
+    _lib.check(lib.bx_cls_loss(h, bw.ptr(logits, FLOAT32, (n, c)) if n else 0, bw.ptr(labels, FLOAT32, (n,)) if n else 0,
+                               n, c, float(weight), bw.ptr(loss, FLOAT32, (1,)), None,
+                               bw.ptr(grad, FLOAT32, (n, c)) if (with_grad and n) else None, st))
+    return (loss.reshape(()), grad) if with_grad else loss.reshape(())
+
+
+class _LossFn(torch.autograd.Function):
+    """Loss + gradient from one library call; backward only scales the stored gradient."""
+
+    @staticmethod
+    def forward(ctx, x, fn, args):
+        loss, grad = fn(x.detach(), *args, with_grad=True)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
 def post_ops_prediction(scores, deltas, rois, image_shape, means=(0, 0, 0, 0), stds=(1, 1, 1, 1), max_num_per_class=50,
                         max_num_per_image=150, nms_iou_threshold=0.3, score_threshold=0.05, extractor_stride=16,
                         roi_counts=None):
