@@ -119,6 +119,26 @@ int bx_roi_pool(bx_handle* h, int mode, int pool, int pool_size, const float* fe
                 const float* rois, const int* box_ind, const int* roi_counts, int r, float stride, int image_h,
                 int image_w, float* out, void* stream);
 
+/* ---- f2 ("next" row): the inputs of the path, produced on the device.
+ *      bx_generate_anchors: utils/anchor_generator.py:46-60 generate_by_anchor_base_tf (one level; offsets = the
+ *      anchor base rows) and :137-162 make_anchors over P2..P6 as concatenated at fpn/base_fpn_model.py:163-186
+ *      (offsets = (-0.5ws, -0.5hs, +0.5ws, +0.5hs) per anchor): anchor = (x*stride, y*stride, x*stride, y*stride) +
+ *      offsets[level][k], cells row-major, anchors fastest.  fh/fw/stride [n_levels] and offsets [n_levels, A, 4] are
+ *      HOST arrays (passed as kernel parameters); out_anchors [sum fh*fw*A, 4].  n_levels <= 5, A <= 32.
+ *      bx_rpn_scores: raw RPN logits -> foreground probability (tf.nn.softmax over the (bg, fg) pair):
+ *        BX_RPN_CAFFE  faster_rcnn/base_faster_rcnn_model.py:149-152, logits [batch, n/A cells, 2A] = [bg x A | fg x A];
+ *        BX_RPN_PAIRS  fpn/base_fpn_model.py:223, logits [batch, n, 2] = (bg, fg) per anchor.
+ *      bx_proposals_rpn: bx_proposals on the raw logits; for n <= 24576 without min_size the softmax runs inside the
+ *      proposal kernel's key pass (no extra launch, no score tensor); out_scores [batch,n] is optional. */
+typedef enum { BX_RPN_CAFFE = 0, BX_RPN_PAIRS = 1 } bx_rpn_layout;
+int bx_generate_anchors(bx_handle* h, int n_levels, const int* fh, const int* fw, const float* stride,
+                        int anchors_per_cell, const float* offsets, float* out_anchors, void* stream);
+int bx_rpn_scores(bx_handle* h, const float* logits, int layout, int anchors_per_cell, int batch, int n,
+                  float* out_scores, void* stream);
+int bx_proposals_rpn(bx_handle* h, const float* anchors, const float* deltas, const float* logits, int layout,
+                     int anchors_per_cell, int batch, int n, const bx_proposal_params* p, float* out_boxes,
+                     int* out_idx, int* out_count, float* out_scores, void* stream);
+
 /* ---- f3 ("next" row): gradient of bx_roi_pool w.r.t. the feature map, i.e. the backward pass TF runs through
  *      tf.image.crop_and_resize (+ the 2x2 pool) when scripts/train.py:99-103 differentiates the model (the boxes are
  *      under tf.stop_gradient, model/roi_pooling.py:37,79,86).  Same arguments as bx_roi_pool; grad_out [r,P,P,c];

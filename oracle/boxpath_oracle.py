@@ -525,3 +525,21 @@ def cls_loss_grad(logits, labels, weight=1.0):
     p[np.arange(sel.size), lab[sel].astype(np.int64)] -= F(1)
     g[sel] = p * (F(weight) / F(sel.size))
     return g
+
+
+# --------------------------------------------------------------------------- f2 RPN score layout
+def rpn_fg_scores(logits, layout, anchors_per_cell=1):
+    """Foreground probability per anchor from the raw RPN logits.
+    'caffe': faster_rcnn/base_faster_rcnn_model.py:149-152 — rows [cells, 2A] = [bg x A | fg x A], the four
+    reshape/transpose steps reduce to softmax over (row[k], row[A+k]) read out cell-major, anchor-minor.
+    'pairs': fpn/base_fpn_model.py:223 — softmax(all_fpn_scores)[:, 1]."""
+    x = np.asarray(logits, F)
+    if layout == 'caffe':
+        a = anchors_per_cell
+        x = x.reshape(-1, 2, a)
+        pair = np.stack([x[:, 0, :], x[:, 1, :]], axis=-1).reshape(-1, 2)
+    else:
+        pair = x.reshape(-1, 2)
+    z = pair - pair.max(axis=1, keepdims=True)
+    e = np.exp(z)
+    return (e[:, 1] / (e[:, 0] + e[:, 1])).astype(F)

@@ -205,6 +205,24 @@ def main():
                                            tf.constant(g['pt_out_w']), sigma=1.0))
     g['loss_roi_cls'] = np.asarray(ref_cls_loss(tf.constant(roi_logits), tf.constant(g['pt_labels'])))
 
+    # ---- f2: the RPN score layout dances, executed from the reference's own statements
+    import ast
+    import types as _types
+    srng = np.random.default_rng(syn.seed_for(1, 79))
+    rpn_score = srng.normal(0, 3, (38 * 63, 18)).astype(np.float32)          # RpnHead output [cells, 2A], :345
+    path = '/root/reference/object_detection/model/faster_rcnn/base_faster_rcnn_model.py'
+    src = open(path).read()
+    stmts = [n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.Assign) and 149 <= n.lineno <= 152
+             and getattr(n.targets[0], 'id', '') == 'scores']
+    assert len(stmts) == 4, 'expected the 4 `scores = ...` statements at base_faster_rcnn_model.py:149-152'
+    ns = {'tf': tf, 'rpn_score': tf.constant(rpn_score), 'self': _types.SimpleNamespace(_num_anchors=9)}
+    for st_ in sorted(stmts, key=lambda n: n.lineno):
+        exec(compile(ast.get_source_segment(src, st_), path, 'exec'), ns)
+    g['rpn_caffe_logits'], g['rpn_caffe_scores'] = rpn_score, np.asarray(ns['scores'])
+    fpn_score = srng.normal(0, 3, (4096, 2)).astype(np.float32)
+    g['rpn_pairs_logits'] = fpn_score
+    g['rpn_pairs_scores'] = np.asarray(tf.nn.softmax(tf.constant(fpn_score))[:, 1])     # base_fpn_model.py:223
+
     np.savez_compressed(os.path.join(OUT, 'reference_on_shim.npz'), **g)
     sz = os.path.getsize(os.path.join(OUT, 'reference_on_shim.npz'))
     print('wrote %d arrays, %.1f KiB' % (len(g), sz / 1024))

@@ -355,7 +355,14 @@ def _avg_pool(x, ksize, strides, padding, data_format='NHWC', name=None):
     return _pool2x2(x, ksize, strides, padding, lambda v, axis: np.mean(v, axis=axis, dtype=np.float32))
 
 
-nn = types.SimpleNamespace(top_k=_top_k, avg_pool=_avg_pool)
+def _softmax(logits, axis=-1):
+    """tf.nn.softmax (core/kernels/softmax_op_functor.h): exp(x - max) / sum(exp(x - max)) along the last axis."""
+    x = np.asarray(logits, np.float32)
+    e = np.exp(x - x.max(axis=axis, keepdims=True))
+    return (e / e.sum(axis=axis, keepdims=True, dtype=np.float32)).view(EagerTensor)
+
+
+nn = types.SimpleNamespace(top_k=_top_k, avg_pool=_avg_pool, softmax=_softmax)
 
 
 # ---------------------------------------------------------------- tf.image (SURVEY App. B.1 / B.2)

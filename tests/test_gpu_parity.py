@@ -1,6 +1,7 @@
 """GPU parity: the CUDA path (through the Python mirror -> ctypes -> C ABI) against the numpy oracle and the committed
 golden vectors.  Bit-exact for indices / labels / IEEE-only arithmetic; <= 1e-5 relative where exp/log differ by ulps.
 Nothing here reads /root/reference."""
+import hashlib
 import os
 
 import numpy as np
@@ -14,6 +15,10 @@ from tf_eager_object_detection_b200 import synthetic as syn  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5   # BASELINE.json north_star: "RoI features and decoded boxes within 1e-5 relative (fp32)"
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
 
 
 def close(a, b, scale=1.0):
@@ -714,3 +719,62 @@ def test_losses(bx, golden):
     assert float(bx.smooth_l1_loss(*(cu(np.zeros((0, 4), np.float32)),) * 4)) == 0.0
     with pytest.raises(NotImplementedError):
         smooth_l1_loss(cu(g['loss_roi_pred']), cu(g['pt_targets']), cu(g['pt_in_w']), cu(g['pt_out_w']), dim=[0])
+
+
+# ------------------------------------------------------------------------------------------------ f2 inputs of the path
+def test_generate_anchors(bx, golden):
+    from tf_eager_object_detection_b200 import anchor_generator as ag
+    a = ag.generate_by_anchor_base_tf(ag.generate_anchor_base(16), 16, 38, 63)
+    assert np.array_equal(a.cpu().numpy(), syn.c4_anchors(38, 63, 16))         # == the reference's (sha in the goldens)
+    assert np.array_equal(sha(a.cpu().numpy()), golden['c4_anchors_sha'])
+    for hw in ((600, 1000), (800, 1333)):
+        f = ag.make_fpn_anchors(hw)
+        assert np.array_equal(f.cpu().numpy(), syn.fpn_anchors(hw))
+    one = ag.make_anchors(64, (1.0,), (0.5, 1.0, 2.0), 75, 125, 8)
+    assert np.array_equal(one.cpu().numpy(), syn.fpn_level_anchors(64, 75, 125, 8))
+    assert ag.make_anchors(64, (1.0,), (0.5, 1.0, 2.0), 0, 125, 8).shape == (0, 4)
+    with pytest.raises(NotImplementedError):
+        bx.generate_anchors([(2, 2)], [16.0], np.zeros((1, 33, 4), np.float32))
+
+
+def test_rpn_scores_and_fused_proposals(bx, golden):
+    from tf_eager_object_detection_b200 import _lib
+    g = golden
+    sc = bx.rpn_scores(cu(g['rpn_caffe_logits']), _lib.RPN_CAFFE, 9)
+    close(sc[0].cpu().numpy(), g['rpn_caffe_scores'], scale=0.0)                # expf ulps only
+    sp = bx.rpn_scores(cu(g['rpn_pairs_logits']), _lib.RPN_PAIRS)
+    close(sp[0].cpu().numpy(), g['rpn_pairs_scores'], scale=0.0)
+    # C4 (cached keys: softmax inside the proposal kernel), batch of 3 with different logits
+    im = syn.c4_image(1, 0, with_features=False)
+    rng = np.random.default_rng(91)
+    logits = rng.normal(0, 3, (3, 38 * 63, 18)).astype(np.float32)
+    deltas = np.stack([syn.rpn_outputs(np.random.default_rng(92 + i), 21546)[0] for i in range(3)])
+    ob, oi, oc, osc = bx.proposals_rpn(cu(im['anchors']), cu(deltas), cu(logits), _lib.RPN_CAFFE, 9, (600, 1000), 300,
+                                       return_scores=True)
+    assert torch.equal(osc, bx.rpn_scores(cu(logits), _lib.RPN_CAFFE, 9))       # same bits fused and stand-alone
+    rb, ri, rc = bx.proposals(cu(im['anchors']), cu(deltas), osc, (600, 1000), 300)
+    assert torch.equal(oi, ri) and torch.equal(oc, rc) and torch.equal(ob, rb)
+    nb, ni, nc = bx.proposals_rpn(cu(im['anchors']), cu(deltas), cu(logits), _lib.RPN_CAFFE, 9, (600, 1000), 300)
+    assert torch.equal(ni, oi) and torch.equal(nb, ob)                          # without the score output
+    for i in range(3):                                                          # oracle on the device's scores
+        boxes, idx = orc.region_proposal(deltas[i], im['anchors'], osc[i].cpu().numpy(), (600, 1000), 300, 0.7)
+        k = int(oc[i])
+        assert k == idx.shape[0] and np.array_equal(oi[i, :k].cpu().numpy(), idx)
+        close(osc[i].cpu().numpy(), orc.rpn_fg_scores(logits[i], 'caffe', 9), scale=0.0)
+    # min_size path and the streaming (n > 24576) path go through the stand-alone score kernel
+    mb, mi, mc = bx.proposals_rpn(cu(im['anchors']), cu(deltas), cu(logits), _lib.RPN_CAFFE, 9, (600, 1000), 300,
+                                  min_size=16.0)
+    eb, ei, ec = bx.proposals(cu(im['anchors']), cu(deltas), osc, (600, 1000), 300, min_size=16.0)
+    assert torch.equal(mi, ei) and torch.equal(mc, ec)
+    f = syn.fpn_image(3, 0, with_features=False)
+    n = f['anchors'].shape[0]
+    fl = rng.normal(0, 3, (2, n, 2)).astype(np.float32)
+    fd = np.stack([f['deltas'], f['deltas'][::-1].copy()])
+    pb, pi, pc, psc = bx.proposals_rpn(cu(f['anchors']), cu(fd), cu(fl), _lib.RPN_PAIRS, 1, (600, 1000), 1000,
+                                       return_scores=True)
+    qb, qi, qc = bx.proposals(cu(f['anchors']), cu(fd), psc, (600, 1000), 1000)
+    assert torch.equal(pi, qi) and torch.equal(pc, qc) and torch.equal(pb, qb)
+    wb, wi, wc = bx.proposals_rpn(cu(f['anchors']), cu(fd), cu(fl), _lib.RPN_PAIRS, 1, (600, 1000), 1000)
+    assert torch.equal(wi, qi)                                                  # scores staged in the workspace
+    with pytest.raises(ValueError):
+        bx.proposals_rpn(cu(im['anchors']), cu(deltas), cu(logits), _lib.RPN_CAFFE, 8, (600, 1000), 300)

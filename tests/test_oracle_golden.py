@@ -197,3 +197,18 @@ def test_loss_and_roi_gradients_against_torch_autograd(golden):
         out.backward(torch.tensor(go, dtype=torch.float64))
         got = orc.roi_pool_c4_grad(feat, rois, 16, go, 3, max_flag)
         np.testing.assert_allclose(got, ft.grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ f2 RPN score layout
+def test_rpn_score_layouts_match_reference_statements(golden):
+    g = golden
+    assert np.array_equal(orc.rpn_fg_scores(g['rpn_caffe_logits'], 'caffe', 9), g['rpn_caffe_scores'])
+    assert np.array_equal(orc.rpn_fg_scores(g['rpn_pairs_logits'], 'pairs'), g['rpn_pairs_scores'])
+
+
+def test_anchor_generator_mirror_host_tables(golden):
+    from tf_eager_object_detection_b200 import anchor_generator as ag
+    assert np.array_equal(ag.generate_anchor_base(16).astype(np.float32), golden['anchor_base'])
+    off = ag._offsets(32, (1.0,), (0.5, 1.0, 2.0))
+    lvl = syn.fpn_level_anchors(32, 1, 1, 4)                    # one cell at the origin = the offsets themselves
+    assert np.array_equal(off, lvl)

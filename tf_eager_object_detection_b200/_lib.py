@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libboxpath.so')
 
 BX_OK, BX_ERR_INVALID, BX_ERR_CUDA, BX_ERR_UNSUPPORTED, BX_ERR_DLPACK = 0, -1, -2, -3, -4
 ROI_STRIDE_NORM, ROI_IMAGE_NORM, ROI_ALIGN_PAD = 0, 1, 2
+RPN_CAFFE, RPN_PAIRS = 0, 1
 POOL_NONE, POOL_MAX2, POOL_AVG2 = 0, 1, 2
 
 F4 = c_float * 4
@@ -54,6 +55,11 @@ SIGNATURES = {
     'bx_range_filter': (c_int, [c_void_p, P, c_int, c_int, c_int, P, P, c_void_p]),
     'bx_nms': (c_int, [c_void_p, P, P, c_int, c_int, c_int, c_float, P, P, c_void_p]),
     'bx_proposals': (c_int, [c_void_p, P, P, P, c_int, c_int, POINTER(ProposalParams), P, P, P, c_void_p]),
+    'bx_generate_anchors': (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int,
+                                    POINTER(c_float), P, c_void_p]),
+    'bx_rpn_scores': (c_int, [c_void_p, P, c_int, c_int, c_int, c_int, P, c_void_p]),
+    'bx_proposals_rpn': (c_int, [c_void_p, P, P, P, c_int, c_int, c_int, c_int, POINTER(ProposalParams), P, P, P, P,
+                                 c_void_p]),
     'bx_crop_and_resize': (c_int, [c_void_p, P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_float, P,
                                    c_void_p]),
     'bx_roi_pool': (c_int, [c_void_p, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float,

@@ -36,7 +36,32 @@ struct ProposalArgs {
   int* out_idx;           // [batch,post_nms]
   int* out_count;         // [batch]
   int cache_keys;         // 1: keys live in smem
+  // f2: raw RPN logits instead of scores (cached-key kernel only; larger n goes through rpn_scores_kernel first)
+  const float* logits;    // [batch, n*2] in `logit_layout`, or null
+  int logit_layout;       // bx_rpn_layout
+  int anchors_per_cell;   // A (BX_RPN_CAFFE)
+  float* out_scores;      // [batch,n] or null: the foreground probabilities the order was taken from
 };
+
+// Foreground probability of anchor i from the raw RPN logits: tf.nn.softmax over (bg, fg) — exp(x - max) / sum, fp32.
+//   BX_RPN_CAFFE  (faster_rcnn/base_faster_rcnn_model.py:149-152): rows of 2A per cell, [bg x A | fg x A]
+//   BX_RPN_PAIRS  (fpn/base_fpn_model.py:223):                     (bg, fg) per anchor
+__device__ __forceinline__ float rpn_fg_prob(const float* __restrict__ logits, int layout, int A, int i) {
+  float bg, fg;
+  if (layout == BX_RPN_CAFFE) {
+    const int cell = i / A, k = i - cell * A;
+    const float* row = logits + static_cast<size_t>(cell) * 2 * A;
+    bg = row[k];
+    fg = row[A + k];
+  } else {
+    const float2 v = *reinterpret_cast<const float2*>(logits + 2 * static_cast<size_t>(i));
+    bg = v.x;
+    fg = v.y;
+  }
+  const float m = fmaxf(bg, fg);
+  const float e0 = expf(bg - m), e1 = expf(fg - m);
+  return e1 / (e0 + e1);
+}
 
 __device__ __forceinline__ uint64_t composite(uint32_t key, uint32_t idx) {
   return (static_cast<uint64_t>(key) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
@@ -105,6 +130,8 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   const int img = blockIdx.x;
   const int n = a.n;
   const float* scores = a.scores ? a.scores + static_cast<size_t>(img) * n : nullptr;
+  const float* logits = a.logits ? a.logits + static_cast<size_t>(img) * n * 2 : nullptr;
+  float* out_scores = a.out_scores ? a.out_scores + static_cast<size_t>(img) * n : nullptr;
   const uint32_t* gkeys = a.keys ? a.keys + static_cast<size_t>(img) * n : nullptr;
   const float4* deltas = a.deltas ? a.deltas + static_cast<size_t>(img) * n : nullptr;
   const float4* boxes = a.boxes ? a.boxes + static_cast<size_t>(img) * n : nullptr;
@@ -119,7 +146,13 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {   // all loads of the batch in flight before any is consumed
       const int i = base + u * kThreads;
-      kk[u] = (i < n) ? (gkeys ? gkeys[i] : bx_score_key(scores[i] + 0.0f)) : 0u;
+      if (kCache && logits) {           // f2: softmax fused into the key pass
+        const float sc = (i < n) ? rpn_fg_prob(logits, a.logit_layout, a.anchors_per_cell, i) : 0.0f;
+        if (out_scores && i < n) out_scores[i] = sc;
+        kk[u] = (i < n) ? bx_score_key(sc + 0.0f) : 0u;
+      } else {
+        kk[u] = (i < n) ? (gkeys ? gkeys[i] : bx_score_key(scores[i] + 0.0f)) : 0u;
+      }
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -627,10 +660,140 @@ extern "C" int bx_nms(bx_handle* h, const float* boxes, const float* scores, int
   return launch_proposals(h, a, batch, static_cast<cudaStream_t>(stream));
 }
 
+__global__ void __launch_bounds__(256) rpn_scores_kernel(const float* __restrict__ logits, int layout, int A,
+                                                         long long total, float* __restrict__ out) {
+  // logits of consecutive images are contiguous and n is a multiple of A, so the flat index works across the batch
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    if (layout == BX_RPN_CAFFE) {
+      const long long cell = i / A;
+      const int k = static_cast<int>(i - cell * A);
+      const float* row = logits + cell * 2 * A;
+      const float bg = row[k], fg = row[A + k];
+      const float m = fmaxf(bg, fg);
+      const float e0 = expf(bg - m), e1 = expf(fg - m);
+      out[i] = e1 / (e0 + e1);
+    } else {
+      const float2 v = *reinterpret_cast<const float2*>(logits + 2 * i);
+      const float m = fmaxf(v.x, v.y);
+      const float e0 = expf(v.x - m), e1 = expf(v.y - m);
+      out[i] = e1 / (e0 + e1);
+    }
+  }
+}
+
+static int rpn_scores_launch(bx_handle* h, const float* logits, int layout, int A, int batch, int n, float* out,
+                             cudaStream_t st) {
+  const long long total = static_cast<long long>(batch) * n;
+  if (total == 0) return BX_OK;
+  const int grid = static_cast<int>(bx_min_ll(bx_div_up(total, 256), 8ll * h->num_sms));
+  rpn_scores_kernel<<<grid, 256, 0, st>>>(logits, layout, A, total, out);
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}
+
+// ---- f2: anchors on the device (utils/anchor_generator.py:46-60 generate_by_anchor_base_tf, :137-162 make_anchors).
+// Both reduce to (x*stride, y*stride, x*stride, y*stride) + a per-anchor offset quadruple: one exact fp32 add each.
+constexpr int kMaxAnchorLevels = 5;
+constexpr int kMaxAnchorsPerCell = 32;
+struct AnchorGenArgs {
+  int n_levels, a;
+  int fw[kMaxAnchorLevels];
+  float stride[kMaxAnchorLevels];
+  long long first[kMaxAnchorLevels + 1];     // first anchor index of each level
+  float4 off[kMaxAnchorLevels * kMaxAnchorsPerCell];
+  float4* out;
+};
+
+__global__ void __launch_bounds__(256) generate_anchors_kernel(const __grid_constant__ AnchorGenArgs g) {
+  const long long total = g.first[g.n_levels];
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    int l = 0;
+    while (l + 1 < g.n_levels && i >= g.first[l + 1]) ++l;
+    const long long r = i - g.first[l];
+    const int k = static_cast<int>(r % g.a);
+    const long long cell = r / g.a;
+    const float sx = static_cast<float>(cell % g.fw[l]) * g.stride[l];
+    const float sy = static_cast<float>(cell / g.fw[l]) * g.stride[l];
+    const float4 o = g.off[l * g.a + k];
+    g.out[i] = make_float4(sx + o.x, sy + o.y, sx + o.z, sy + o.w);
+  }
+}
+
+extern "C" int bx_generate_anchors(bx_handle* h, int n_levels, const int* fh, const int* fw, const float* stride,
+                                   int anchors_per_cell, const float* offsets, float* out_anchors, void* stream) {
+  BX_REQUIRE(h && fh && fw && stride && offsets, BX_ERR_INVALID, "bx_generate_anchors: NULL argument");
+  BX_REQUIRE(n_levels >= 1 && n_levels <= kMaxAnchorLevels, BX_ERR_UNSUPPORTED,
+             "bx_generate_anchors: n_levels %d not in [1, %d]", n_levels, kMaxAnchorLevels);
+  BX_REQUIRE(anchors_per_cell >= 1 && anchors_per_cell <= kMaxAnchorsPerCell, BX_ERR_UNSUPPORTED,
+             "bx_generate_anchors: anchors_per_cell %d not in [1, %d]", anchors_per_cell, kMaxAnchorsPerCell);
+  BX_REQUIRE(bx_aligned(out_anchors, 16), BX_ERR_INVALID, "bx_generate_anchors: output must be 16-byte aligned");
+  AnchorGenArgs g = {};
+  g.n_levels = n_levels;
+  g.a = anchors_per_cell;
+  g.first[0] = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    BX_REQUIRE(fh[l] >= 0 && fw[l] >= 0 && fw[l] < (1 << 24) && fh[l] < (1 << 24), BX_ERR_INVALID,
+               "bx_generate_anchors: bad feature-map shape at level %d", l);
+    g.fw[l] = fw[l] > 0 ? fw[l] : 1;
+    g.stride[l] = stride[l];
+    g.first[l + 1] = g.first[l] + static_cast<long long>(fh[l]) * fw[l] * anchors_per_cell;
+    for (int k = 0; k < anchors_per_cell; ++k) {
+      const float* o = offsets + (static_cast<size_t>(l) * anchors_per_cell + k) * 4;
+      g.off[l * anchors_per_cell + k] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  g.out = reinterpret_cast<float4*>(out_anchors);
+  const long long total = g.first[n_levels];
+  if (total == 0) return BX_OK;
+  BX_REQUIRE(out_anchors, BX_ERR_INVALID, "bx_generate_anchors: NULL output");
+  const int grid = static_cast<int>(bx_min_ll(bx_div_up(total, 256), 8ll * h->num_sms));
+  generate_anchors_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g);
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}
+
+static int check_rpn(const char* who, const float* logits, int layout, int A, int n) {
+  BX_REQUIRE(logits, BX_ERR_INVALID, "%s: NULL logits", who);
+  BX_REQUIRE(layout == BX_RPN_CAFFE || layout == BX_RPN_PAIRS, BX_ERR_INVALID, "%s: bad rpn layout %d", who, layout);
+  BX_REQUIRE(layout == BX_RPN_PAIRS || (A > 0 && n % A == 0), BX_ERR_INVALID,
+             "%s: n (%d) must be a multiple of anchors_per_cell (%d)", who, n, A);
+  BX_REQUIRE(bx_aligned(logits, 8), BX_ERR_INVALID, "%s: logits must be 8-byte aligned", who);
+  return BX_OK;
+}
+
+extern "C" int bx_rpn_scores(bx_handle* h, const float* logits, int layout, int anchors_per_cell, int batch, int n,
+                             float* out_scores, void* stream) {
+  BX_REQUIRE(h && out_scores, BX_ERR_INVALID, "bx_rpn_scores: NULL argument");
+  BX_REQUIRE(batch >= 0 && n >= 0, BX_ERR_INVALID, "bx_rpn_scores: negative size");
+  if (int rc = check_rpn("bx_rpn_scores", logits, layout, anchors_per_cell, n)) return rc;
+  return rpn_scores_launch(h, logits, layout, anchors_per_cell, batch, n, out_scores, static_cast<cudaStream_t>(stream));
+}
+
+static int proposals_impl(bx_handle* h, const float* anchors, const float* deltas, const float* scores,
+                          const float* logits, int layout, int A, float* out_scores, int batch, int n,
+                          const bx_proposal_params* p, float* out_boxes, int* out_idx, int* out_count, void* stream);
+
 extern "C" int bx_proposals(bx_handle* h, const float* anchors, const float* deltas, const float* scores, int batch,
                             int n, const bx_proposal_params* p, float* out_boxes, int* out_idx, int* out_count,
                             void* stream) {
-  BX_REQUIRE(h && anchors && deltas && scores && p && out_boxes && out_idx && out_count, BX_ERR_INVALID,
+  BX_REQUIRE(scores, BX_ERR_INVALID, "bx_proposals: NULL argument");
+  return proposals_impl(h, anchors, deltas, scores, nullptr, 0, 0, nullptr, batch, n, p, out_boxes, out_idx, out_count,
+                        stream);
+}
+
+extern "C" int bx_proposals_rpn(bx_handle* h, const float* anchors, const float* deltas, const float* logits,
+                                int layout, int anchors_per_cell, int batch, int n, const bx_proposal_params* p,
+                                float* out_boxes, int* out_idx, int* out_count, float* out_scores, void* stream) {
+  BX_REQUIRE(batch >= 0 && n >= 0, BX_ERR_INVALID, "bx_proposals_rpn: negative size");
+  if (int rc = check_rpn("bx_proposals_rpn", logits, layout, anchors_per_cell, n)) return rc;
+  return proposals_impl(h, anchors, deltas, nullptr, logits, layout, anchors_per_cell, out_scores, batch, n, p, out_boxes,
+                        out_idx, out_count, stream);
+}
+
+static int proposals_impl(bx_handle* h, const float* anchors, const float* deltas, const float* scores,
+                          const float* logits, int layout, int A, float* out_scores, int batch, int n,
+                          const bx_proposal_params* p, float* out_boxes, int* out_idx, int* out_count, void* stream) {
+  BX_REQUIRE(h && anchors && deltas && p && out_boxes && out_idx && out_count, BX_ERR_INVALID,
              "bx_proposals: NULL argument");
   BX_REQUIRE(batch >= 0 && n >= 0, BX_ERR_INVALID, "bx_proposals: negative size");
   BX_REQUIRE(p->iou_threshold >= 0.0f && p->iou_threshold <= 1.0f, BX_ERR_INVALID,
@@ -655,12 +818,25 @@ extern "C" int bx_proposals(bx_handle* h, const float* anchors, const float* del
   a.out_boxes = reinterpret_cast<float4*>(out_boxes);
   a.out_idx = out_idx;
   a.out_count = out_count;
+  const size_t total = static_cast<size_t>(batch) * n;
+  const bool fuse = logits && n <= kKeyCacheMax && !(p->min_size > 0.0f);   // softmax inside the key pass
+  const size_t ws_scores = (logits && !fuse && !out_scores) ? total * sizeof(float) : 0;
+  if (int rc = bx_ws_reserve(h, ws_scores + 16 + ((p->min_size > 0.0f) ? total * (sizeof(float4) + sizeof(uint32_t)) : 0)))
+    return rc;
+  if (fuse) {
+    a.logits = logits;
+    a.logit_layout = layout;
+    a.anchors_per_cell = A;
+    a.out_scores = out_scores;
+  } else if (logits) {
+    float* sc = out_scores ? out_scores : reinterpret_cast<float*>(h->ws);
+    if (int rc = rpn_scores_launch(h, logits, layout, A, batch, n, sc, st)) return rc;
+    scores = sc;
+    a.scores = sc;
+  }
   if (p->min_size > 0.0f) {
     // filter -> top-k -> NMS: decode everything once, mask the keys of undersized boxes
-    const size_t total = static_cast<size_t>(batch) * n;
-    int rc = bx_ws_reserve(h, total * (sizeof(float4) + sizeof(uint32_t)));
-    if (rc) return rc;
-    float4* wboxes = reinterpret_cast<float4*>(h->ws);
+    float4* wboxes = reinterpret_cast<float4*>(static_cast<char*>(h->ws) + ((ws_scores + 15) & ~size_t(15)));
     uint32_t* wkeys = reinterpret_cast<uint32_t*>(wboxes + total);
     const int grid = static_cast<int>(bx_min_ll(bx_div_up((long long)total, 256), 8ll * h->num_sms));
     decode_filter_keys_kernel<<<grid, 256, 0, st>>>(a.anchors, a.deltas, scores, batch, n, a.codec, p->min_size,

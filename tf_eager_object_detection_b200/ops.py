@@ -123,6 +123,72 @@ def proposals(anchors, deltas, scores, image_shape, post_nms, iou_threshold=0.7,
     return ob, oi, oc
 
 
+def generate_anchors(feat_shapes, strides, offsets, device=None):
+    """f2: anchors = (x*stride, y*stride, x*stride, y*stride) + offsets[level][k].  feat_shapes [(fh,fw)] per level;
+    offsets [levels, A, 4] (host floats) -> [sum fh*fw*A, 4] on the device."""
+    import numpy as np
+    off = np.ascontiguousarray(np.asarray(offsets, dtype=np.float32))
+    nl = len(feat_shapes)
+    if off.ndim == 2:
+        off = off[None]
+    if off.shape[0] != nl or off.shape[2] != 4 or len(strides) != nl:
+        raise ValueError('generate_anchors: offsets must be [levels, A, 4] with one (shape, stride) per level')
+    a = off.shape[1]
+    dev = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    total = sum(int(h_) * int(w_) for h_, w_ in feat_shapes) * a
+    out = empty((total, 4), f32, dev)
+    st = stream_ptr(dev)
+    h = _lib.handle(dev, st.value)
+    fh = (ctypes.c_int * nl)(*[int(s_[0]) for s_ in feat_shapes])
+    fw = (ctypes.c_int * nl)(*[int(s_[1]) for s_ in feat_shapes])
+    sd = (ctypes.c_float * nl)(*[float(v) for v in strides])
+    _lib.check(_lib.load().bx_generate_anchors(h, nl, fh, fw, sd, a, off.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                               Borrow(dev).ptr(out, FLOAT32, (total, 4), 16) if total else 0, st))
+    return out
+
+
+def rpn_scores(logits, layout, anchors_per_cell=1):
+    """f2: raw RPN logits -> foreground probability.  RPN_CAFFE: [b, cells, 2A] -> [b, cells*A]; RPN_PAIRS: [b, n, 2]
+    -> [b, n]."""
+    logits = to_device(logits, f32)
+    if logits.dim() == 2:
+        logits = logits.unsqueeze(0)
+    b = logits.shape[0]
+    n = logits.shape[1] * (anchors_per_cell if layout == _lib.RPN_CAFFE else 1)
+    if logits.shape[2] != (2 * anchors_per_cell if layout == _lib.RPN_CAFFE else 2):
+        raise ValueError('rpn_scores: logits last dimension does not match the layout')
+    dev, h, bw, st, lib = _ctx(logits)
+    out = empty((b, n), f32, dev)
+    if b * n:
+        _lib.check(lib.bx_rpn_scores(h, bw.ptr(logits, FLOAT32, tuple(logits.shape), 8), layout, anchors_per_cell, b, n,
+                                     bw.ptr(out, FLOAT32, (b, n)), st))
+    return out
+
+
+def proposals_rpn(anchors, deltas, logits, layout, anchors_per_cell, image_shape, post_nms, iou_threshold=0.7,
+                  means=(0, 0, 0, 0), stds=(1, 1, 1, 1), pre_nms_top_k=0, min_size=0.0, return_scores=False):
+    """f2 + a3: proposals straight from the raw RPN logits (softmax fused into the key pass when n <= 24576)."""
+    deltas = to_device(deltas, f32)
+    anchors = to_device(anchors, f32, deltas.device)
+    logits = to_device(logits, f32, deltas.device)
+    b, n = deltas.shape[0], deltas.shape[1]
+    if logits.numel() != 2 * b * n:
+        raise ValueError('proposals_rpn: logits must hold 2 values per anchor')
+    dev, h, bw, st, lib = _ctx(deltas)
+    p = proposal_params(image_shape, post_nms, iou_threshold, means, stds, pre_nms_top_k, min_size)
+    ob, oi, oc = empty((b, post_nms, 4), f32, dev), empty((b, post_nms), i32, dev), empty((b,), i32, dev)
+    osc = empty((b, n), f32, dev) if return_scores else None
+    if n == 0:
+        ob.zero_(); oi.fill_(-1); oc.zero_()
+    else:
+        _lib.check(lib.bx_proposals_rpn(h, bw.ptr(anchors, FLOAT32, (n, 4), 16), bw.ptr(deltas, FLOAT32, (b, n, 4), 16),
+                                        bw.ptr(logits, FLOAT32, tuple(logits.shape), 8), layout, anchors_per_cell, b, n,
+                                        ctypes.byref(p), bw.ptr(ob, FLOAT32, (b, post_nms, 4), 16),
+                                        bw.ptr(oi, INT32, (b, post_nms)), bw.ptr(oc, INT32, (b,)),
+                                        bw.ptr(osc, FLOAT32, (b, n)) if return_scores else None, st))
+    return (ob, oi, oc, osc) if return_scores else (ob, oi, oc)
+
+
 def crop_and_resize(image, boxes, box_ind, crop_size, extrapolation_value=0.0):
     """tf.image.crop_and_resize (bilinear): image [b,h,w,c]; boxes [r,4] (y1,x1,y2,x2) normalised; box_ind [r]."""
     image = to_device(image, f32)
