@@ -80,6 +80,31 @@ def load_fpn_methods():
     return stub
 
 
+def voc_golden():
+    import tempfile
+    if not hasattr(np, 'bool'):
+        np.bool = bool                      # the reference predates numpy 1.24 (detectron_pascal_evaluation_utils.py:150)
+    from object_detection.evaluation.detectron_pascal_evaluation_utils import voc_eval as ref_voc_eval
+    from tf_eager_object_detection_b200 import evaluation as ev
+    from oracle.voc_fixture import synthetic_voc, write_voc_tree
+    classes = ev.PASCAL_CLASSES[:5]
+    gts, det, cnt = synthetic_voc(np.random.default_rng(syn.seed_for(1, 80)))
+    names = ['%06d' % (i + 1) for i in range(len(gts))]
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        write_voc_tree(root, names, gts, classes)
+        ev.write_voc_results(os.path.join(root, 'det_{:s}.txt'), names, det, cnt, classes)
+        for metric07 in (True, False):
+            for c in classes[1:]:
+                rec, prec, ap = ref_voc_eval(os.path.join(root, 'det_{:s}.txt'), os.path.join(root, 'Annotations', '{:s}.xml'),
+                                             os.path.join(root, 'test.txt'), c, os.path.join(root, 'cache'), 0.5, metric07)
+                tag = 'voc_%s_%s' % (c, '07' if metric07 else 'area')
+                out[tag + '_rec'], out[tag + '_prec'], out[tag + '_ap'] = rec, prec, np.float64(ap)
+        out['voc_det_sha'] = np.frombuffer(hashlib.sha256(
+            b''.join(open(os.path.join(root, 'det_%s.txt' % c), 'rb').read() for c in classes[1:])).digest(), np.uint8)
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     g = {}
@@ -222,6 +247,9 @@ def main():
     fpn_score = srng.normal(0, 3, (4096, 2)).astype(np.float32)
     g['rpn_pairs_logits'] = fpn_score
     g['rpn_pairs_scores'] = np.asarray(tf.nn.softmax(tf.constant(fpn_score))[:, 1])     # base_fpn_model.py:223
+
+    # ---- f4: the reference's voc_eval on a synthetic VOC tree; detection files written by the package's writer
+    g.update(voc_golden())
 
     np.savez_compressed(os.path.join(OUT, 'reference_on_shim.npz'), **g)
     sz = os.path.getsize(os.path.join(OUT, 'reference_on_shim.npz'))

@@ -1,0 +1,44 @@
+"""Synthetic PASCAL-VOC tree for the f4 tests (TEST INFRASTRUCTURE ONLY — part of the oracle): ground truth +
+noisy detections in the [B,K,6] record format, shared by oracle/make_golden.py (which feeds it to the reference's
+voc_eval) and tests/test_evaluation.py."""
+import os
+
+import numpy as np
+
+from tf_eager_object_detection_b200 import synthetic as syn
+
+
+def synthetic_voc(rng, n_images=40, n_classes=5):
+    """Ground truth + noisy detections in the [B,K,6] record format; shared by make_golden and the tests."""
+    gts, K = [], 24
+    det = np.zeros((n_images, K, 6), np.float32)
+    cnt = np.zeros(n_images, np.int32)
+    for b in range(n_images):
+        m = int(rng.integers(0, 6))
+        boxes, labels = syn.gt_boxes(rng, m, (375, 500), n_classes)
+        difficult = rng.random(m) < 0.15
+        gts.append((boxes.astype(np.int64), labels, difficult))
+        rows = []
+        for k in range(m):                                       # jittered copies (some duplicated), plus clutter
+            for _ in range(int(rng.integers(0, 3))):
+                rows.append(np.concatenate([boxes[k] + rng.normal(0, 6, 4), [rng.random(), labels[k]]]))
+        for _ in range(int(rng.integers(0, 4))):
+            cb, cl = syn.gt_boxes(rng, 1, (375, 500), n_classes)
+            rows.append(np.concatenate([cb[0], [rng.random() * 0.6, cl[0]]]))
+        rows = sorted(rows, key=lambda r: -r[4])[:K]
+        cnt[b] = len(rows)
+        if rows:
+            det[b, :len(rows)] = np.asarray(rows, np.float32)
+    return gts, det, cnt
+
+
+def write_voc_tree(root, names, gts, class_list):
+    os.makedirs(os.path.join(root, 'Annotations'), exist_ok=True)
+    with open(os.path.join(root, 'test.txt'), 'w') as f:
+        f.write(''.join(n + '\n' for n in names))
+    for n, (boxes, labels, difficult) in zip(names, gts):
+        objs = ''.join('<object><name>%s</name><pose>Unspecified</pose><truncated>0</truncated><difficult>%d</difficult>'
+                       '<bndbox><xmin>%d</xmin><ymin>%d</ymin><xmax>%d</xmax><ymax>%d</ymax></bndbox></object>'
+                       % (class_list[l], d, b[0], b[1], b[2], b[3]) for b, l, d in zip(boxes, labels, difficult))
+        with open(os.path.join(root, 'Annotations', n + '.xml'), 'w') as f:
+            f.write('<annotation>%s</annotation>' % objs)

@@ -778,3 +778,21 @@ def test_rpn_scores_and_fused_proposals(bx, golden):
     assert torch.equal(wi, qi)                                                  # scores staged in the workspace
     with pytest.raises(ValueError):
         bx.proposals_rpn(cu(im['anchors']), cu(deltas), cu(logits), _lib.RPN_CAFFE, 8, (600, 1000), 300)
+
+
+def test_detection_records_to_voc_lines(bx, golden):
+    """f4 on the device's own records: [B,K,6] from post_ops_prediction_batched -> VOC result lines equal the lines
+    built from the reference-on-shim goldens."""
+    from tf_eager_object_detection_b200 import evaluation as ev
+    from tf_eager_object_detection_b200.prediction import post_ops_prediction_batched
+    hs, hd = syn.roi_head_outputs(np.random.default_rng(syn.seed_for(1, 77)), 300, 21)
+    rois = golden['c4_eval_rois']
+    det, cnt = post_ops_prediction_batched(cu(hs)[None], cu(hd)[None], cu(rois)[None], [600, 1000], [0, 0, 0, 0],
+                                           [0.1, 0.1, 0.2, 0.2])
+    lines = ev.voc_result_lines(['000001'], det, cnt)
+    gb, gc, gs = golden['post_boxes'], golden['post_classes'], golden['post_scores']
+    ref = np.concatenate([gb, gs[:, None], gc[:, None].astype(np.float32)], axis=1)[None]
+    want = ev.voc_result_lines(['000001'], ref, np.array([gb.shape[0]]))
+    assert lines == want and sum(len(v) for v in lines.values()) == gb.shape[0]
+    coco = ev.coco_results([7], det, cnt)
+    assert len(coco) == gb.shape[0] and coco[0]['category_id'] == ev.coco_category_ids()[int(gc[0])]
