@@ -218,9 +218,13 @@ def run_ours(args):
     d_in = [dict(deltas=torch.as_tensor(hb['deltas']).to(dev), scores=torch.as_tensor(hb['scores']).to(dev),
                  feat=torch.as_tensor(hb['feat']).to(dev)) for hb in host_batches]
     NSTREAM = max(1, args.streams)
-    outs = [(torch.empty((B, post, 4), device=dev), torch.empty((B, post), dtype=torch.int32, device=dev),
-             torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B * post, P, P, C), device=dev))
-            for _ in range(NSTREAM)]
+    # per-image detection records of a step = kept boxes [B,post,4] fp32 followed by counts [B] int32, in ONE allocation
+    # so that the N>1 all-gather is one collective per step
+    rec_bytes = B * post * 16 + ((B * 4 + 15) // 16) * 16
+    recs = [torch.empty((rec_bytes,), dtype=torch.uint8, device=dev) for _ in range(NSTREAM)]
+    outs = [(r[:B * post * 16].view(torch.float32).view(B, post, 4), torch.empty((B, post), dtype=torch.int32, device=dev),
+             r[B * post * 16:B * post * 16 + B * 4].view(torch.int32), torch.empty((B * post, P, P, C), device=dev))
+            for r in recs]
     params = ops.proposal_params(w['image_hw'], post, w['iou_thr'], pre_nms_top_k=w['pre_nms'])
     streams = [torch.cuda.Stream(dev) for _ in range(NSTREAM)]
     handles = []
@@ -230,8 +234,8 @@ def run_ours(args):
         handles.append(hh)
 
     # N > 1: the only collective of the path — all-gather of the per-image detection records (kept boxes + counts)
-    gathered = [(torch.empty((world * B, post, 4), device=dev), torch.empty((world * B,), dtype=torch.int32, device=dev))
-                for _ in range(NSTREAM)] if world > 1 else None
+    gathered = [torch.empty((world * rec_bytes,), dtype=torch.uint8, device=dev) for _ in range(NSTREAM)] \
+        if world > 1 else None
 
     def launch(step):
         s = step % NSTREAM
@@ -243,8 +247,7 @@ def run_ours(args):
                                           ctypes.c_void_p(streams[s].cuda_stream)))
         if world > 1:
             with torch.cuda.stream(streams[s]):
-                dist.all_gather_into_tensor(gathered[s][0], o[0])
-                dist.all_gather_into_tensor(gathered[s][1], o[2])
+                dist.all_gather_into_tensor(gathered[s], recs[s])
 
     def barrier():
         if world > 1:
@@ -307,6 +310,9 @@ def run_ours(args):
     # ---- sanity inside the bench: every image filled its quota (otherwise the work measured is not the workload)
     for o in outs:
         assert bool((o[2] == post).all()), 'a step kept fewer than post_nms proposals'
+    if world > 1:                                       # the gathered buffer holds this rank's records at its slot
+        for s_ in range(NSTREAM):
+            assert torch.equal(gathered[s_][rank * rec_bytes:(rank + 1) * rec_bytes], recs[s_]), 'all-gather mismatch'
 
     # ---- e2e: the public Python API with HOST (pinned) buffers; H2D inputs + D2H outputs inside the timed region
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
