@@ -1,4 +1,4 @@
-"""Run one op of the path a few times (for ncu captures).  usage: python profiles/micro/run_op.py {fpn_props|train_props|vgg_pool|anchor_target}"""
+"""Run one op of the path a few times (for ncu captures).  usage: python profiles/micro/run_op.py {fpn_props|fpn5_props|train_props|vgg_pool|anchor_target}"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -10,6 +10,11 @@ if which == 'fpn_props':
     f = syn.fpn_image(3, 0, with_features=False)
     a, d, s = cu(f['anchors']), cu(f['deltas'])[None], cu(f['scores'])[None]
     fn = lambda: ops.proposals(a, d, s, (600, 1000), 1000)
+elif which == 'fpn5_props':
+    ims = [syn.fpn_image(5, i, (800, 1333), with_features=False) for i in range(8)]
+    a = cu(ims[0]['anchors'])
+    d = cu(np.stack([im['deltas'] for im in ims])); s = cu(np.stack([im['scores'] for im in ims]))
+    fn = lambda: ops.proposals(a, d, s, (800, 1333), 1000)
 elif which == 'train_props':
     im = syn.c4_image(2, 0, with_features=False)
     a, d, s = cu(im['anchors']), cu(im['deltas'])[None], cu(im['scores'])[None]

@@ -796,3 +796,49 @@ def test_detection_records_to_voc_lines(bx, golden):
     assert lines == want and sum(len(v) for v in lines.values()) == gb.shape[0]
     coco = ev.coco_results([7], det, cnt)
     assert len(coco) == gb.shape[0] and coco[0]['category_id'] == ev.coco_category_ids()[int(gc[0])]
+
+
+# ------------------------------------------------------------------------------------------------ top-set prefilter
+def _topset_case(bx, anchors, deltas, scores, post, **kw):
+    ob, oi, oc = bx.proposals(cu(anchors), cu(deltas)[None], cu(scores)[None], (600, 1000), post, **kw)
+    boxes, idx = orc.region_proposal(deltas, anchors, scores, (600, 1000), post, 0.7, **kw)
+    k = int(oc[0])
+    assert k == idx.shape[0], (k, idx.shape[0])
+    assert np.array_equal(oi[0, :k].cpu().numpy(), idx)
+    assert (oi[0, k:] == -1).all()
+    return k
+
+
+def test_topset_prefilter_paths(bx):
+    """n > 24576 goes through the multi-CTA radix select + compaction; each branch of it against the oracle:
+    one-level thresholds, two- and three-level refinement (clustered scores, heavy ties), more exact ties than the
+    budget (threshold above them, empty list -> full-length redo), a list that runs dry (everything suppressed),
+    and the pre-NMS cut."""
+    rng = np.random.default_rng(123)
+    n = 30000
+    anchors = syn.random_rois(rng, n, (600, 1000))
+    deltas = (rng.normal(0, 1, (n, 4)) * [0.2, 0.2, 0.3, 0.3]).astype(np.float32)
+    uniq = ((rng.permutation(n) + 1) / (n + 1)).astype(np.float32)
+    assert _topset_case(bx, anchors, deltas, uniq, 300) == 300                       # level 0 resolves
+    assert _topset_case(bx, anchors, deltas, uniq, 300, pre_nms_top_k=6000) == 300
+    assert _topset_case(bx, anchors, deltas, uniq, 2000, pre_nms_top_k=12000) == 2000
+    clustered = (1.0 - 1e-4 * rng.random(n)).astype(np.float32)                      # ~1700 distinct keys, all levels
+    assert _topset_case(bx, anchors, deltas, clustered, 300) == 300
+    mid = (0.5 + 0.01 * rng.random(n)).astype(np.float32)                            # two levels
+    assert _topset_case(bx, anchors, deltas, mid, 300) == 300
+    ties = uniq * 0.5
+    ties[rng.permutation(n)[:26000]] = 0.75                                          # 26000 > 24576 exact ties on top
+    assert _topset_case(bx, anchors, deltas, ties, 300) == 300
+    ties2 = uniq * 0.5
+    ties2[rng.permutation(n)[:100]] = 0.9                                            # a few above the tie wall
+    ties2[rng.permutation(n)[100:26100]] = 0.75
+    assert _topset_case(bx, anchors, deltas, ties2, 300) == 300
+    same = np.tile(np.array([[100, 100, 300, 300]], np.float32), (n, 1))             # everything suppressed by the first
+    assert _topset_case(bx, same, np.zeros((n, 4), np.float32), uniq, 50) == 1
+    few = np.zeros(n, np.float32); few[:10] = uniq[:10]                              # scores 0 stay valid candidates
+    assert _topset_case(bx, anchors, deltas, few, 300) == 300
+    # stand-alone NMS entry over the same size
+    boxes = orc.decode_bbox(anchors, deltas)
+    idx_g, cnt_g = bx.nms(cu(boxes)[None], cu(uniq)[None], 300, 0.7)
+    ref = orc.nms_tf(boxes, uniq, 300, 0.7)
+    assert int(cnt_g[0]) == ref.shape[0] and np.array_equal(idx_g[0, :ref.shape[0]].cpu().numpy(), ref)

@@ -41,6 +41,13 @@ struct ProposalArgs {
   int logit_layout;       // bx_rpn_layout
   int anchors_per_cell;   // A (BX_RPN_CAFFE)
   float* out_scores;      // [batch,n] or null: the foreground probabilities the order was taken from
+  // top-set prefilter (n > kKeyCacheMax): `keys` is a compacted [batch, n] list of the largest keys in ascending anchor
+  // order, `src_idx` maps its positions back to anchors, boxes / deltas keep the full stride `src_stride`
+  const int* src_idx;     // [batch,n] or null
+  int src_stride;         // anchors per image in deltas / boxes when src_idx is set
+  const int* topset_info; // [batch,4] (threshold lo, m, n_valid_full, fallback flag) or null
+  int* flag_out;          // &info[0][3]: set to 1 when the compacted list ran dry before the quota was met
+  const int* run_flag;    // fallback launch: images whose flag is 0 return immediately
 };
 
 // Foreground probability of anchor i from the raw RPN logits: tf.nn.softmax over (bg, fg) — exp(x - max) / sum, fp32.
@@ -128,13 +135,16 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const int img = blockIdx.x;
-  const int n = a.n;
-  const float* scores = a.scores ? a.scores + static_cast<size_t>(img) * n : nullptr;
-  const float* logits = a.logits ? a.logits + static_cast<size_t>(img) * n * 2 : nullptr;
-  float* out_scores = a.out_scores ? a.out_scores + static_cast<size_t>(img) * n : nullptr;
-  const uint32_t* gkeys = a.keys ? a.keys + static_cast<size_t>(img) * n : nullptr;
-  const float4* deltas = a.deltas ? a.deltas + static_cast<size_t>(img) * n : nullptr;
-  const float4* boxes = a.boxes ? a.boxes + static_cast<size_t>(img) * n : nullptr;
+  if (a.run_flag && a.run_flag[img * 4] == 0) return;           // fallback launch: nothing to redo for this image
+  const int n = a.topset_info ? min(a.topset_info[img * 4 + 1], a.n) : a.n;
+  const size_t full = a.src_idx ? static_cast<size_t>(a.src_stride) : static_cast<size_t>(a.n);
+  const float* scores = a.scores ? a.scores + static_cast<size_t>(img) * a.n : nullptr;
+  const float* logits = a.logits ? a.logits + static_cast<size_t>(img) * a.n * 2 : nullptr;
+  float* out_scores = a.out_scores ? a.out_scores + static_cast<size_t>(img) * a.n : nullptr;
+  const uint32_t* gkeys = a.keys ? a.keys + static_cast<size_t>(img) * a.n : nullptr;
+  const int* src_idx = a.src_idx ? a.src_idx + static_cast<size_t>(img) * a.n : nullptr;
+  const float4* deltas = a.deltas ? a.deltas + static_cast<size_t>(img) * full : nullptr;
+  const float4* boxes = a.boxes ? a.boxes + static_cast<size_t>(img) * full : nullptr;
   float4* out_boxes = a.out_boxes ? a.out_boxes + static_cast<size_t>(img) * a.post_nms : nullptr;
   int* out_idx = a.out_idx + static_cast<size_t>(img) * a.post_nms;
 
@@ -347,7 +357,8 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
 
     // ---- decode + clip (or gather) the candidates' boxes, normalised corners for the IoU test
     for (int i = tid; i < cnt; i += kThreads) {
-      const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(cand_key[i] & 0xFFFFFFFFull);
+      uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(cand_key[i] & 0xFFFFFFFFull);
+      if (src_idx) idx = static_cast<uint32_t>(src_idx[idx]);
       float4 b;
       if (boxes) b = boxes[idx];
       else b = bx_decode_clip_one(a.anchors[idx], deltas[idx], a.codec);
@@ -431,7 +442,8 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
           const int pos = kept + __popcll(keep & ((1ull << tid) - 1ull));
           const float4 b = cand_box[t0 + tid];
           kept_box[pos] = normalise(b);
-          out_idx[pos] = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(cand_key[t0 + tid] & 0xFFFFFFFFull));
+          const int p = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(cand_key[t0 + tid] & 0xFFFFFFFFull));
+          out_idx[pos] = src_idx ? src_idx[p] : p;
           if (out_boxes) out_boxes[pos] = b;
         }
       }
@@ -449,7 +461,256 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
     out_idx[i] = -1;
     if (out_boxes) out_boxes[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (tid == 0) a.out_count[img] = kept;
+  if (tid == 0) {
+    a.out_count[img] = kept;
+    if (a.flag_out) {
+      // the compacted list is a prefix of the full descending order: the result stands unless it ran dry early
+      const int n_full = a.topset_info[img * 4 + 2];
+      const int limit_full = (a.pre_nms_top_k > 0) ? min(a.pre_nms_top_k, n_full) : n_full;
+      a.flag_out[img * 4] = (kept < a.post_nms && consumed < limit_full) ? 1 : 0;
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------ top-set prefilter (n > kKeyCacheMax)
+// One CTA per image cannot stream a quarter of a million keys several times per chunk at any speed; the whole device
+// can.  A multi-CTA radix select (11 + 11 + 10 bits, later levels only for images whose crossing bin overflows the
+// budget) finds a threshold T with  m_lo <= #{key >= T} <= cap  (fewer only under massive exact ties), a two-pass
+// stable compaction writes those keys in ascending anchor order, and the single-CTA kernel then runs on the compacted
+// list with its keys cached in shared memory.  Its result is the full result unless the list runs dry before the quota
+// is met; that (rare) case raises a per-image flag and the full-length kernel, launched right behind with an
+// early-out on the flag, redoes just those images.
+constexpr int kTopBins = 2048;
+constexpr int kTopThreads = 512;
+constexpr int kTopMaxSlices = 64;
+
+struct TopsetArgs {
+  const float* scores;     // [batch,n] or null
+  const uint32_t* keys;    // [batch,n] or null (precomputed, 0 = excluded)
+  int n, slices, slice_len;
+  int m_lo, cap;
+  uint32_t* hist;          // [batch][3][kTopBins], zeroed
+  int* slice_count;        // [batch][kTopMaxSlices]
+  int* info;               // [batch][4]: threshold (low 32 bits), m, n_valid_full, fallback flag
+  int* t_hi;               // [batch]: 1 when the threshold is 2^32 (nothing taken)
+  uint32_t* out_keys;      // [batch][cap]
+  int* out_src;            // [batch][cap]
+};
+
+struct TopsetResult {
+  unsigned long long T;    // take key >= T (T may be 2^32: take nothing)
+  uint32_t prefix;         // bins fixed so far when !done
+  int done, count, n_valid;
+  int b, above, cb;        // scratch of suffix_find
+};
+
+__device__ __forceinline__ uint32_t topset_key(const TopsetArgs& a, size_t base, int i) {
+  return a.keys ? a.keys[base + i] : bx_score_key(a.scores[base + i] + 0.0f);
+}
+
+// Highest bin b of bins[0..nb) whose inclusive suffix count reaches `need` (need >= 1); r->b = -1 when the total is
+// smaller.  r->above = count strictly above b, r->cb = bins[b], r->n_valid = total.  All kTopThreads threads call it.
+__device__ void suffix_find(const uint32_t* __restrict__ bins, int nb, int need, TopsetResult* r, uint32_t* s_warp) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t c[4], mine = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int bi = tid * 4 + j;
+    c[j] = (bi < nb) ? bins[bi] : 0u;
+    mine += c[j];
+  }
+  uint32_t suf = mine;                                     // inclusive suffix over lanes (lane 31 first)
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_down_sync(0xFFFFFFFFu, suf, d);
+    if (lane + d < 32) suf += o;
+  }
+  if (lane == 0) s_warp[warp] = suf;                       // warp totals
+  if (tid == 0) r->b = -1;
+  __syncthreads();
+  uint32_t higher = 0, total = 0;
+  for (int w = 0; w < kTopThreads / 32; ++w) {
+    const uint32_t t = s_warp[w];
+    total += t;
+    if (w > warp) higher += t;
+  }
+  const uint32_t incl = higher + suf, excl = incl - mine;  // counts at / above this thread's 4 bins
+  if (excl < static_cast<uint32_t>(need) && incl >= static_cast<uint32_t>(need)) {   // exactly one thread
+    uint32_t run = excl;
+    for (int j = 3; j >= 0; --j) {
+      if (run + c[j] >= static_cast<uint32_t>(need)) {
+        r->b = tid * 4 + j;
+        r->above = static_cast<int>(run);
+        r->cb = static_cast<int>(c[j]);
+        break;
+      }
+      run += c[j];
+    }
+  }
+  if (tid == 0) r->n_valid = static_cast<int>(total);
+  __syncthreads();
+}
+
+// Resolves the threshold from the first `levels` histogram levels.  r->done == 0 means level `levels` is still needed
+// (r->prefix = the bins fixed so far).
+__device__ void topset_resolve(const uint32_t* __restrict__ hist, int levels, int m_lo, int cap, TopsetResult* r,
+                               uint32_t* s_warp) {
+  suffix_find(hist, kTopBins, m_lo, r, s_warp);
+  const int n_valid = r->n_valid;
+  int b = r->b, above = r->above, cb = r->cb;
+  __syncthreads();
+  int need = m_lo, budget = cap, acc = 0;
+  unsigned long long T = 1ull;
+  int done = 0, count = n_valid;
+  uint32_t prefix = 0;
+  if (b < 0) {
+    done = 1;                                              // fewer than m_lo valid keys: take them all
+  } else if (above + cb <= budget) {
+    T = static_cast<unsigned long long>(b) << 21;
+    if (T == 0ull) T = 1ull;
+    count = above + cb;
+    done = 1;
+  } else {
+    prefix = static_cast<uint32_t>(b);
+    need -= above; budget -= above; acc += above;
+    if (levels >= 1) {
+      suffix_find(hist + kTopBins, kTopBins, need, r, s_warp);
+      b = r->b; above = r->above; cb = r->cb;
+      __syncthreads();
+      if (above + cb <= budget) {
+        T = (static_cast<unsigned long long>(prefix) << 21) | (static_cast<unsigned long long>(b) << 10);
+        count = acc + above + cb;
+        done = 1;
+      } else {
+        prefix = (prefix << 11) | static_cast<uint32_t>(b);
+        need -= above; budget -= above; acc += above;
+        if (levels >= 2) {
+          suffix_find(hist + 2 * kTopBins, 1024, need, r, s_warp);
+          b = r->b; above = r->above; cb = r->cb;
+          __syncthreads();
+          const unsigned long long key = (static_cast<unsigned long long>(prefix) << 10) | static_cast<unsigned long long>(b);
+          if (above + cb <= budget) {
+            T = key;
+            count = acc + above + cb;
+          } else {                                         // more exact ties than the budget holds: stop above them
+            T = key + 1ull;
+            count = acc + above;
+          }
+          done = 1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    r->T = T; r->done = done; r->count = count; r->prefix = prefix; r->n_valid = n_valid;
+  }
+  __syncthreads();
+}
+
+template <int LEVEL>
+__global__ void __launch_bounds__(kTopThreads) topset_hist_kernel(const TopsetArgs a) {
+  __shared__ uint32_t s_hist[kTopBins];
+  __shared__ uint32_t s_warp[kTopThreads / 32];
+  __shared__ TopsetResult s_r;
+  const int img = blockIdx.y, tid = threadIdx.x;
+  uint32_t* hist = a.hist + static_cast<size_t>(img) * 3 * kTopBins;
+  uint32_t prefix = 0;
+  if (LEVEL > 0) {
+    topset_resolve(hist, LEVEL - 1, a.m_lo, a.cap, &s_r, s_warp);
+    if (s_r.done) return;
+    prefix = s_r.prefix;
+  }
+  for (int i = tid; i < kTopBins; i += kTopThreads) s_hist[i] = 0u;
+  __syncthreads();
+  const size_t base = static_cast<size_t>(img) * a.n;
+  const int lo = blockIdx.x * a.slice_len, hi = min(a.n, lo + a.slice_len);
+  for (int i0 = lo + tid; i0 < hi; i0 += kTopThreads * 4) {
+    uint32_t k[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kTopThreads;
+      k[u] = (i < hi) ? topset_key(a, base, i) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!k[u]) continue;
+      if (LEVEL == 0) atomicAdd(&s_hist[k[u] >> 21], 1u);
+      else if (LEVEL == 1) { if ((k[u] >> 21) == prefix) atomicAdd(&s_hist[(k[u] >> 10) & 2047u], 1u); }
+      else { if ((k[u] >> 10) == prefix) atomicAdd(&s_hist[k[u] & 1023u], 1u); }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kTopBins; i += kTopThreads)
+    if (s_hist[i]) atomicAdd(&hist[LEVEL * kTopBins + i], s_hist[i]);
+}
+
+__global__ void __launch_bounds__(kTopThreads) topset_count_kernel(const TopsetArgs a) {
+  __shared__ uint32_t s_warp[kTopThreads / 32];
+  __shared__ TopsetResult s_r;
+  __shared__ int s_cnt;
+  const int img = blockIdx.y, tid = threadIdx.x;
+  topset_resolve(a.hist + static_cast<size_t>(img) * 3 * kTopBins, 2, a.m_lo, a.cap, &s_r, s_warp);
+  const unsigned long long T = s_r.T;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  const size_t base = static_cast<size_t>(img) * a.n;
+  const int lo = blockIdx.x * a.slice_len, hi = min(a.n, lo + a.slice_len);
+  int cnt = 0;
+  for (int i = lo + tid; i < hi; i += kTopThreads) {
+    const uint32_t k = topset_key(a, base, i);
+    cnt += (k != 0u && static_cast<unsigned long long>(k) >= T) ? 1 : 0;
+  }
+  cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+  if ((tid & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+  __syncthreads();
+  if (tid == 0) {
+    a.slice_count[img * kTopMaxSlices + blockIdx.x] = s_cnt;
+    if (blockIdx.x == 0) {
+      a.info[img * 4 + 0] = static_cast<int>(static_cast<uint32_t>(T & 0xFFFFFFFFull));
+      a.info[img * 4 + 1] = s_r.count;
+      a.info[img * 4 + 2] = s_r.n_valid;
+      a.info[img * 4 + 3] = 0;
+      a.t_hi[img] = (T >> 32) ? 1 : 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTopThreads) topset_write_kernel(const TopsetArgs a) {
+  __shared__ int s_wcnt[kTopThreads / 32];
+  const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long T = (static_cast<unsigned long long>(a.t_hi[img]) << 32) |
+                               static_cast<unsigned long long>(static_cast<uint32_t>(a.info[img * 4 + 0]));
+  int pos = 0;                                             // first output slot of this slice
+  for (int s = 0; s < static_cast<int>(blockIdx.x); ++s) pos += a.slice_count[img * kTopMaxSlices + s];
+  const size_t base = static_cast<size_t>(img) * a.n;
+  uint32_t* out_keys = a.out_keys + static_cast<size_t>(img) * a.cap;
+  int* out_src = a.out_src + static_cast<size_t>(img) * a.cap;
+  const int lo = blockIdx.x * a.slice_len, hi = min(a.n, lo + a.slice_len);
+  for (int i0 = lo; i0 < hi; i0 += kTopThreads) {
+    const int i = i0 + tid;
+    const uint32_t k = (i < hi) ? topset_key(a, base, i) : 0u;
+    const bool take = (k != 0u) && (static_cast<unsigned long long>(k) >= T);
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, take);
+    if (lane == 0) s_wcnt[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < kTopThreads / 32; ++w) {
+      const int c = s_wcnt[w];
+      total += c;
+      if (w < warp) before += c;
+    }
+    if (take) {
+      const int o = pos + before + __popc(m & ((1u << lane) - 1u));
+      if (o < a.cap) {                                     // always true: count <= cap by construction
+        out_keys[o] = k;
+        out_src[o] = i;
+      }
+    }
+    pos += total;
+    __syncthreads();
+  }
 }
 
 size_t proposals_smem_bytes(int n, bool cache) {
@@ -459,7 +720,7 @@ size_t proposals_smem_bytes(int n, bool cache) {
   return (b + 15) & ~static_cast<size_t>(15);
 }
 
-int launch_proposals(bx_handle* h, ProposalArgs& a, int batch, cudaStream_t st) {
+static int launch_proposals_kernel(bx_handle* h, ProposalArgs& a, int batch, cudaStream_t st) {
   const bool cache = a.n <= kKeyCacheMax;
   a.cache_keys = cache ? 1 : 0;
   const size_t smem = proposals_smem_bytes(a.n, cache);
@@ -474,6 +735,67 @@ int launch_proposals(bx_handle* h, ProposalArgs& a, int batch, cudaStream_t st) 
   }
   BX_LAUNCH_CHECK(h);
   return BX_OK;
+}
+
+size_t topset_ws_bytes(int batch, int cap) {
+  return static_cast<size_t>(batch) * (3 * kTopBins * sizeof(uint32_t) + kTopMaxSlices * sizeof(int) + 4 * sizeof(int) +
+                                       sizeof(int) + static_cast<size_t>(cap) * (sizeof(uint32_t) + sizeof(int))) + 256;
+}
+
+// `ws` = workspace region of topset_ws_bytes(batch, cap) bytes reserved by the caller (16-byte aligned)
+int launch_proposals(bx_handle* h, ProposalArgs& a, int batch, cudaStream_t st, void* ws = nullptr) {
+  static const bool no_topset = getenv("BX_NO_TOPSET") != nullptr;          // A/B switch for profiles/micro
+  if (a.n <= kKeyCacheMax || !ws || no_topset) return launch_proposals_kernel(h, a, batch, st);
+  // ---- top-set prefilter over the whole device, then the cached-key kernel on the compacted list
+  const int cap = kKeyCacheMax;
+  int m_lo = 8 * a.post_nms;
+  if (m_lo < 4096) m_lo = 4096;
+  if (a.pre_nms_top_k > 0 && a.pre_nms_top_k < m_lo) m_lo = a.pre_nms_top_k;   // never need more than the pre-NMS cut
+  if (a.pre_nms_top_k > m_lo && a.pre_nms_top_k <= cap) m_lo = a.pre_nms_top_k; // ... and take all of it when it fits
+  if (m_lo > cap) m_lo = cap;
+  TopsetArgs t = {};
+  t.scores = a.scores;
+  t.keys = a.keys;
+  t.n = a.n;
+  int slices = (2 * h->num_sms + batch - 1) / batch;
+  if (slices > kTopMaxSlices) slices = kTopMaxSlices;
+  if (slices < 1) slices = 1;
+  t.slice_len = (a.n + slices - 1) / slices;
+  t.slices = (a.n + t.slice_len - 1) / t.slice_len;
+  t.m_lo = m_lo;
+  t.cap = cap;
+  char* p = static_cast<char*>(ws);
+  t.hist = reinterpret_cast<uint32_t*>(p);          p += static_cast<size_t>(batch) * 3 * kTopBins * sizeof(uint32_t);
+  t.slice_count = reinterpret_cast<int*>(p);        p += static_cast<size_t>(batch) * kTopMaxSlices * sizeof(int);
+  t.info = reinterpret_cast<int*>(p);               p += static_cast<size_t>(batch) * 4 * sizeof(int);
+  t.t_hi = reinterpret_cast<int*>(p);               p += ((static_cast<size_t>(batch) * sizeof(int) + 15) & ~size_t(15));
+  t.out_keys = reinterpret_cast<uint32_t*>(p);      p += static_cast<size_t>(batch) * cap * sizeof(uint32_t);
+  t.out_src = reinterpret_cast<int*>(p);
+  BX_CUDA(cudaMemsetAsync(t.hist, 0, static_cast<size_t>(batch) * 3 * kTopBins * sizeof(uint32_t), st));
+  const dim3 grid(t.slices, batch);
+  topset_hist_kernel<0><<<grid, kTopThreads, 0, st>>>(t);
+  BX_LAUNCH_CHECK(h);
+  topset_hist_kernel<1><<<grid, kTopThreads, 0, st>>>(t);
+  BX_LAUNCH_CHECK(h);
+  topset_hist_kernel<2><<<grid, kTopThreads, 0, st>>>(t);
+  BX_LAUNCH_CHECK(h);
+  topset_count_kernel<<<grid, kTopThreads, 0, st>>>(t);
+  BX_LAUNCH_CHECK(h);
+  topset_write_kernel<<<grid, kTopThreads, 0, st>>>(t);
+  BX_LAUNCH_CHECK(h);
+  ProposalArgs c = a;                     // compacted list: keys cached in smem, boxes / deltas through src_idx
+  c.scores = nullptr;
+  c.logits = nullptr;
+  c.out_scores = nullptr;
+  c.keys = t.out_keys;
+  c.src_idx = t.out_src;
+  c.src_stride = a.n;
+  c.n = cap;
+  c.topset_info = t.info;
+  c.flag_out = t.info + 3;
+  if (int rc = launch_proposals_kernel(h, c, batch, st)) return rc;
+  a.run_flag = t.info + 3;                // full-length redo of the images whose list ran dry (normally none)
+  return launch_proposals_kernel(h, a, batch, st);
 }
 
 // ------------------------------------------------------------------ elementwise helpers
@@ -657,7 +979,12 @@ extern "C" int bx_nms(bx_handle* h, const float* boxes, const float* scores, int
   a.thr = iou_threshold;
   a.out_idx = out_idx;
   a.out_count = out_count;
-  return launch_proposals(h, a, batch, static_cast<cudaStream_t>(stream));
+  void* top_ws = nullptr;
+  if (n > kKeyCacheMax) {
+    if (int rc = bx_ws_reserve(h, topset_ws_bytes(batch, kKeyCacheMax))) return rc;
+    top_ws = h->ws;
+  }
+  return launch_proposals(h, a, batch, static_cast<cudaStream_t>(stream), top_ws);
 }
 
 __global__ void __launch_bounds__(256) rpn_scores_kernel(const float* __restrict__ logits, int layout, int A,
@@ -820,9 +1147,10 @@ static int proposals_impl(bx_handle* h, const float* anchors, const float* delta
   a.out_count = out_count;
   const size_t total = static_cast<size_t>(batch) * n;
   const bool fuse = logits && n <= kKeyCacheMax && !(p->min_size > 0.0f);   // softmax inside the key pass
-  const size_t ws_scores = (logits && !fuse && !out_scores) ? total * sizeof(float) : 0;
-  if (int rc = bx_ws_reserve(h, ws_scores + 16 + ((p->min_size > 0.0f) ? total * (sizeof(float4) + sizeof(uint32_t)) : 0)))
-    return rc;
+  const size_t ws_scores = ((logits && !fuse && !out_scores) ? total * sizeof(float) + 15 : 0) & ~size_t(15);
+  const size_t ws_min = ((p->min_size > 0.0f) ? total * (sizeof(float4) + sizeof(uint32_t)) + 15 : 0) & ~size_t(15);
+  const size_t ws_top = (n > kKeyCacheMax) ? topset_ws_bytes(batch, kKeyCacheMax) : 0;
+  if (int rc = bx_ws_reserve(h, ws_scores + ws_min + ws_top)) return rc;
   if (fuse) {
     a.logits = logits;
     a.logit_layout = layout;
@@ -836,7 +1164,7 @@ static int proposals_impl(bx_handle* h, const float* anchors, const float* delta
   }
   if (p->min_size > 0.0f) {
     // filter -> top-k -> NMS: decode everything once, mask the keys of undersized boxes
-    float4* wboxes = reinterpret_cast<float4*>(static_cast<char*>(h->ws) + ((ws_scores + 15) & ~size_t(15)));
+    float4* wboxes = reinterpret_cast<float4*>(static_cast<char*>(h->ws) + ws_scores);
     uint32_t* wkeys = reinterpret_cast<uint32_t*>(wboxes + total);
     const int grid = static_cast<int>(bx_min_ll(bx_div_up((long long)total, 256), 8ll * h->num_sms));
     decode_filter_keys_kernel<<<grid, 256, 0, st>>>(a.anchors, a.deltas, scores, batch, n, a.codec, p->min_size,
@@ -845,5 +1173,5 @@ static int proposals_impl(bx_handle* h, const float* anchors, const float* delta
     a.boxes = wboxes;
     a.keys = wkeys;
   }
-  return launch_proposals(h, a, batch, st);
+  return launch_proposals(h, a, batch, st, ws_top ? static_cast<char*>(h->ws) + ws_scores + ws_min : nullptr);
 }

@@ -6,28 +6,33 @@
 // Layout: features NHWC fp32, so the channel axis is the coalesced / float4 axis; one CTA produces one output row
 // (roi, py): P pixels x C channels, written once, contiguous.  Sample coordinates follow the TF r1.13 kernel's fp32
 // op order: in_y = y1*(h-1) + y*((y2-y1)*(h-1)/(Q-1)); a sample outside [0,h-1]x[0,w-1] is 0.
+#include <stdlib.h>
+
 #include "bx_roi.cuh"
 
 using namespace bxroi;
 
 namespace {
 
-template <int POOL, typename VecT>
+// kWhole = false: one CTA per (roi, pooled row).  kWhole = true: one CTA per roi, all pooled rows in order — adjacent
+// rows share feature rows, which then hit in L1 instead of crossing L2 -> SM again (the FPN extractor, 16 taps per
+// output, is bound by exactly that traffic).
+template <int POOL, typename VecT, bool kWhole>
 __global__ void __launch_bounds__(256) roi_pool_kernel(const RoiArgs a) {
   constexpr int S = (POOL == BX_POOL_NONE) ? 1 : 2;  // crop samples per output pixel per axis
   constexpr int V = sizeof(VecT) / sizeof(float);
-  __shared__ Axis ax_y[2];
+  __shared__ Axis ax_y[kWhole ? kMaxQ : 2];
   __shared__ Axis ax_x[kMaxQ];
   __shared__ int s_meta[4];  // image index, level, zero-fill flag
 
   const int P = a.P, Q = a.Q;
-  const int j = blockIdx.x / P;   // output roi row
-  const int py = blockIdx.x % P;
+  const int j = kWhole ? blockIdx.x : blockIdx.x / P;   // output roi row
+  const int py = kWhole ? 0 : blockIdx.x % P;
   const int tid = threadIdx.x;
   const int cv = a.c / V;
   VecT* out_row = reinterpret_cast<VecT*>(a.out + (static_cast<size_t>(j) * P + py) * P * a.c);
 
-  if (tid < Q + 2) {
+  if (tid < (kWhole ? 2 * Q : Q + 2)) {
     const int src = a.order ? a.order[j] : j;
     const int lvl = a.level ? a.level[src] - a.level_base : 0;
     int img = a.box_ind ? a.box_ind[src] : 0;
@@ -47,11 +52,13 @@ __global__ void __launch_bounds__(256) roi_pool_kernel(const RoiArgs a) {
     const float y1n = nb.y1, x1n = nb.x1, y2n = nb.y2, x2n = nb.x2;
     const int dimy = nb.dimy, dimx = nb.dimx, pad = nb.pad;
     if (tid < Q) ax_x[tid] = sample_axis(x1n, x2n, tid, Q, dimx, pad);
+    else if (kWhole) ax_y[tid - Q] = sample_axis(y1n, y2n, tid - Q, Q, dimy, pad);
     else if (tid - Q < S) ax_y[tid - Q] = sample_axis(y1n, y2n, py * S + (tid - Q), Q, dimy, pad);
   }
   __syncthreads();
 
-  const int items = P * cv;
+  const int row_items = P * cv;
+  const int items = kWhole ? P * row_items : row_items;
   if (s_meta[2]) {
     VecT z;
     float* zp = reinterpret_cast<float*>(&z);
@@ -65,11 +72,13 @@ __global__ void __launch_bounds__(256) roi_pool_kernel(const RoiArgs a) {
   const float ext = a.extrapolation;
 
   for (int it = tid; it < items; it += 256) {
-    const int px = it / cv, cg = it % cv;
+    const int prow = kWhole ? it / row_items : 0;
+    const int rit = it - prow * row_items;
+    const int px = rit / cv, cg = rit % cv;
     float acc[V];
 #pragma unroll
     for (int sy = 0; sy < S; ++sy) {
-      const Axis ay = ax_y[sy];
+      const Axis ay = ax_y[prow * S + sy];
 #pragma unroll
       for (int sx = 0; sx < S; ++sx) {
         const Axis axx = ax_x[px * S + sx];
@@ -106,6 +115,165 @@ __global__ void __launch_bounds__(256) roi_pool_kernel(const RoiArgs a) {
 #pragma unroll
     for (int v = 0; v < V; ++v) po[v] = (POOL == BX_POOL_AVG2) ? acc[v] / 4.0f : acc[v];
     out_row[it] = o;
+  }
+}
+
+
+// ---- pooled extractors (2x2 max / avg over a 2P x 2P crop) on wide maps: the FPN extractor and every C4 shape the
+// band kernel does not take.  One CTA per roi; thread = (channel group of 4, pixel lane) so that a warp works on one
+// output pixel and every table lookup and branch below is warp-uniform.  Versus the generic kernel it
+//   * x-interpolates each feature row once per pixel and reuses it: the lower row of sample row 2py is the upper row
+//     of sample row 2py+1 whenever the two fall into adjacent pixel intervals (same loads, same operands, same
+//     rounding), likewise the shared pixel column of the two x samples: 9-16 tap loads instead of 16;
+//   * does the lerps as packed fp32x2 (FADD2 / FFMA2 with the -0.0 addend), 32-bit tap offsets from tables that are
+//     pre-multiplied by the row / pixel pitch.
+// Op order per sample is TF's (top = tl + (tr-tl)*lx; bot likewise; top + (bot-top)*ly), pooling order s00,s01,s10,s11.
+#ifndef BX_POOL2_CTAS
+#define BX_POOL2_CTAS 3
+#endif
+struct TapEnt {
+  int lo, hi;    // offsets in float4 units (x: pixel*cv, y: row*fw*cv)
+  float lerp;
+  int valid;
+};
+
+struct F4x2 { ulonglong2 a, b; };   // x-lerped row values for the two x samples of a pixel
+
+template <int POOL>
+__global__ void __launch_bounds__(256, BX_POOL2_CTAS) roi_pool2_kernel(const RoiArgs a, const float neg_zero) {
+  __shared__ __align__(16) TapEnt ytab[kMaxQ];
+  __shared__ __align__(16) TapEnt xtab[kMaxQ];
+  __shared__ int s_meta[4];
+  const int P = a.P, Q = a.Q;
+  const int j = blockIdx.x, tid = threadIdx.x;
+  const int cv = a.c >> 2;
+  if (tid < 2 * Q) {
+    const int src = a.order ? a.order[j] : j;
+    const int lvl = a.level ? a.level[src] - a.level_base : 0;
+    int img = a.box_ind ? a.box_ind[src] : 0;
+    int zero = 0;
+    if (a.roi_counts) {
+      img = src / a.rois_per_image;
+      zero = (src % a.rois_per_image) >= a.roi_counts[img];
+    }
+    if (tid == 0) {
+      s_meta[0] = img;
+      s_meta[1] = lvl;
+      s_meta[2] = zero || img < 0 || img >= a.b;
+    }
+    const int fh = a.lv[lvl].fh, fw = a.lv[lvl].fw;
+    const NormBox nb = roi_norm_box(a, a.rois[src], fh, fw);
+    if (tid < Q) {
+      const Axis ax = sample_axis(nb.x1, nb.x2, tid, Q, nb.dimx, nb.pad);
+      xtab[tid] = {ax.lo * cv, ax.hi * cv, ax.lerp, ax.valid};
+    } else {
+      const Axis ay = sample_axis(nb.y1, nb.y2, tid - Q, Q, nb.dimy, nb.pad);
+      ytab[tid - Q] = {ay.lo * fw * cv, ay.hi * fw * cv, ay.lerp, ay.valid};
+    }
+  }
+  __syncthreads();
+  const int groups = 256 / cv;                   // pixels in flight per CTA (launch guarantees 256 % cv == 0, cv >= 32)
+  const int cg = tid % cv, grp = tid / cv;
+  float4* out = reinterpret_cast<float4*>(a.out) + static_cast<size_t>(j) * P * P * cv + cg;
+  if (s_meta[2]) {
+    for (int pix = grp; pix < P * P; pix += groups) out[static_cast<size_t>(pix) * cv] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const LevelFeat lf = a.lv[s_meta[1]];
+  const ulonglong2* feat = reinterpret_cast<const ulonglong2*>(lf.feat) +
+                           static_cast<size_t>(s_meta[0]) * lf.fh * lf.fw * cv + cg;
+  const unsigned long long nz = f2_splat(neg_zero);
+  const float ext = a.extrapolation;
+
+  for (int pix = grp; pix < P * P; pix += groups) {
+    const int prow = pix / P, px = pix - prow * P;
+    const TapEnt y0 = ytab[2 * prow], y1 = ytab[2 * prow + 1];
+    const TapEnt x0 = xtab[2 * px], x1 = xtab[2 * px + 1];
+    ulonglong2 res;
+    if (y0.valid & y1.valid & x0.valid & x1.valid) {
+      const unsigned long long w0 = f2_splat(x0.lerp), w1 = f2_splat(x1.lerp);
+      const bool xsh = (x0.hi == x1.lo);
+      const bool ysh = (y0.hi == y1.lo);
+      // all taps of the pixel first (9-16 independent 16-byte loads in flight per thread), then the arithmetic
+      const ulonglong2* ra = feat + y0.lo;
+      const ulonglong2* rb = feat + y0.hi;
+      const ulonglong2* rc = feat + y1.lo;
+      const ulonglong2* rd = feat + y1.hi;
+      const ulonglong2 a0 = __ldg(ra + x0.lo), a1 = __ldg(ra + x0.hi), a3 = __ldg(ra + x1.hi);
+      const ulonglong2 b0 = __ldg(rb + x0.lo), b1 = __ldg(rb + x0.hi), b3 = __ldg(rb + x1.hi);
+      const ulonglong2 d0 = __ldg(rd + x0.lo), d1 = __ldg(rd + x0.hi), d3 = __ldg(rd + x1.hi);
+      ulonglong2 a2 = a1, b2 = b1, d2 = d1, c0 = b0, c1 = b1, c2 = b1, c3 = b3;
+      if (!xsh) {
+        a2 = __ldg(ra + x1.lo);
+        b2 = __ldg(rb + x1.lo);
+        d2 = __ldg(rd + x1.lo);
+      }
+      if (!ysh) {
+        c0 = __ldg(rc + x0.lo);
+        c1 = __ldg(rc + x0.hi);
+        c3 = __ldg(rc + x1.hi);
+        c2 = c1;
+        if (!xsh) c2 = __ldg(rc + x1.lo);
+      } else {
+        c2 = b2;
+      }
+      // one feature row, x-interpolated at both x samples of the pixel
+      auto row = [&](const ulonglong2 p0, const ulonglong2 p1, const ulonglong2 p2, const ulonglong2 p3) {
+        F4x2 h;
+        h.a.x = f2_add(p0.x, f2_mul(f2_sub(p1.x, p0.x), w0, nz));
+        h.a.y = f2_add(p0.y, f2_mul(f2_sub(p1.y, p0.y), w0, nz));
+        h.b.x = f2_add(p2.x, f2_mul(f2_sub(p3.x, p2.x), w1, nz));
+        h.b.y = f2_add(p2.y, f2_mul(f2_sub(p3.y, p2.y), w1, nz));
+        return h;
+      };
+      const F4x2 r0 = row(a0, a1, a2, a3), r1 = row(b0, b1, b2, b3);
+      F4x2 r2 = r1;
+      if (!ysh) r2 = row(c0, c1, c2, c3);
+      const F4x2 r3 = row(d0, d1, d2, d3);
+      const unsigned long long v0 = f2_splat(y0.lerp), v1 = f2_splat(y1.lerp);
+      ulonglong2 s00, s01, s10, s11;
+      s00.x = f2_add(r0.a.x, f2_mul(f2_sub(r1.a.x, r0.a.x), v0, nz));
+      s00.y = f2_add(r0.a.y, f2_mul(f2_sub(r1.a.y, r0.a.y), v0, nz));
+      s01.x = f2_add(r0.b.x, f2_mul(f2_sub(r1.b.x, r0.b.x), v0, nz));
+      s01.y = f2_add(r0.b.y, f2_mul(f2_sub(r1.b.y, r0.b.y), v0, nz));
+      s10.x = f2_add(r2.a.x, f2_mul(f2_sub(r3.a.x, r2.a.x), v1, nz));
+      s10.y = f2_add(r2.a.y, f2_mul(f2_sub(r3.a.y, r2.a.y), v1, nz));
+      s11.x = f2_add(r2.b.x, f2_mul(f2_sub(r3.b.x, r2.b.x), v1, nz));
+      s11.y = f2_add(r2.b.y, f2_mul(f2_sub(r3.b.y, r2.b.y), v1, nz));
+      res = pool2<POOL>(pool2<POOL>(pool2<POOL>(s00, s01), s10), s11);
+    } else {
+      // a sample outside the map (extrapolation value): plain per-sample form
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int sy = 0; sy < 2; ++sy) {
+        const TapEnt ye = sy ? y1 : y0;
+#pragma unroll
+        for (int sx = 0; sx < 2; ++sx) {
+          const TapEnt xe = sx ? x1 : x0;
+          float4 v = make_float4(ext, ext, ext, ext);
+          if (ye.valid && xe.valid) {
+            const ulonglong2 tl = __ldg(feat + ye.lo + xe.lo), tr = __ldg(feat + ye.lo + xe.hi);
+            const ulonglong2 bl = __ldg(feat + ye.hi + xe.lo), br = __ldg(feat + ye.hi + xe.hi);
+            const unsigned long long wx = f2_splat(xe.lerp), wy = f2_splat(ye.lerp);
+            ulonglong2 t, b, o;
+            t.x = f2_add(tl.x, f2_mul(f2_sub(tr.x, tl.x), wx, nz));
+            t.y = f2_add(tl.y, f2_mul(f2_sub(tr.y, tl.y), wx, nz));
+            b.x = f2_add(bl.x, f2_mul(f2_sub(br.x, bl.x), wx, nz));
+            b.y = f2_add(bl.y, f2_mul(f2_sub(br.y, bl.y), wx, nz));
+            o.x = f2_add(t.x, f2_mul(f2_sub(b.x, t.x), wy, nz));
+            o.y = f2_add(t.y, f2_mul(f2_sub(b.y, t.y), wy, nz));
+            v = *reinterpret_cast<const float4*>(&o);
+          }
+          if (sy == 0 && sx == 0) acc = v;
+          else if (POOL == BX_POOL_MAX2) acc = make_float4(fmaxf(acc.x, v.x), fmaxf(acc.y, v.y), fmaxf(acc.z, v.z), fmaxf(acc.w, v.w));
+          else acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
+        }
+      }
+      res = *reinterpret_cast<const ulonglong2*>(&acc);
+    }
+    float4 o = *reinterpret_cast<const float4*>(&res);
+    if (POOL == BX_POOL_AVG2) o = make_float4(o.x / 4.0f, o.y / 4.0f, o.z / 4.0f, o.w / 4.0f);
+    out[static_cast<size_t>(pix) * cv] = o;
   }
 }
 
@@ -223,12 +391,35 @@ __global__ void __launch_bounds__(256) roi_pool_grad_kernel(const RoiGradArgs g)
 
 template <typename VecT>
 int launch_roi_v(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
+  static const int whole_env = getenv("BX_ROI_WHOLE") ? atoi(getenv("BX_ROI_WHOLE")) : -1;   // A/B switch
+  // whole-roi CTAs when there are enough rois to fill the device and 2x2 pooling makes adjacent rows share taps
+  const bool whole = whole_env >= 0 ? whole_env != 0 : (pool != BX_POOL_NONE && a.r >= 4 * h->num_sms);
+  if (whole) {
+    if (pool == BX_POOL_NONE) roi_pool_kernel<BX_POOL_NONE, VecT, true><<<a.r, 256, 0, st>>>(a);
+    else if (pool == BX_POOL_MAX2) roi_pool_kernel<BX_POOL_MAX2, VecT, true><<<a.r, 256, 0, st>>>(a);
+    else roi_pool_kernel<BX_POOL_AVG2, VecT, true><<<a.r, 256, 0, st>>>(a);
+    BX_LAUNCH_CHECK(h);
+    return BX_OK;
+  }
   const int grid = a.r * a.P;
-  if (pool == BX_POOL_NONE) roi_pool_kernel<BX_POOL_NONE, VecT><<<grid, 256, 0, st>>>(a);
-  else if (pool == BX_POOL_MAX2) roi_pool_kernel<BX_POOL_MAX2, VecT><<<grid, 256, 0, st>>>(a);
-  else roi_pool_kernel<BX_POOL_AVG2, VecT><<<grid, 256, 0, st>>>(a);
+  if (pool == BX_POOL_NONE) roi_pool_kernel<BX_POOL_NONE, VecT, false><<<grid, 256, 0, st>>>(a);
+  else if (pool == BX_POOL_MAX2) roi_pool_kernel<BX_POOL_MAX2, VecT, false><<<grid, 256, 0, st>>>(a);
+  else roi_pool_kernel<BX_POOL_AVG2, VecT, false><<<grid, 256, 0, st>>>(a);
   BX_LAUNCH_CHECK(h);
   return BX_OK;
+}
+
+// pooled fast kernel: float4-aligned maps whose channel-group count divides the CTA into whole-warp pixel lanes
+bool roi_pool2_ok(const RoiArgs& a, int pool) {
+  static const bool off = getenv("BX_ROI_NO_POOL2") != nullptr;               // A/B switch for profiles/micro
+  if (off || pool == BX_POOL_NONE || (a.c & 3)) return false;
+  const int cv = a.c >> 2;
+  if (cv < 32 || cv > 256 || (256 % cv) != 0 || !bx_aligned(a.out, 16)) return false;
+  for (int l = 0; l < a.n_levels; ++l) {
+    if (!bx_aligned(a.lv[l].feat, 16)) return false;
+    if (static_cast<long long>(a.lv[l].fh) * a.lv[l].fw * cv >= (1ll << 31)) return false;   // 32-bit tap offsets
+  }
+  return true;
 }
 
 int launch_roi(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
@@ -238,6 +429,12 @@ int launch_roi(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
   int used = 0;
   int rc = roi_band_launch(h, a, pool, st, &used);   // TMA band-stationary kernel when the shape allows it
   if (rc) return rc;
+  if (!used && roi_pool2_ok(a, pool)) {
+    if (pool == BX_POOL_MAX2) roi_pool2_kernel<BX_POOL_MAX2><<<a.r, 256, 0, st>>>(a, -0.0f);
+    else roi_pool2_kernel<BX_POOL_AVG2><<<a.r, 256, 0, st>>>(a, -0.0f);
+    BX_LAUNCH_CHECK(h);
+    used = 1;
+  }
   if (!used) {
     bool vec = (a.c % 4 == 0) && bx_aligned(a.out, 16);
     for (int l = 0; l < a.n_levels; ++l) vec = vec && bx_aligned(a.lv[l].feat, 16);

@@ -105,6 +105,45 @@ __device__ __forceinline__ NormBox roi_norm_box(const RoiArgs& a, const float4 r
   return n;
 }
 
+// Packed fp32x2 arithmetic (sm_100 FADD2 / FFMA2): two IEEE fp32 operations per issued instruction, each lane rounded
+// exactly like the scalar op.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (single rounding) even with
+// -fmad=false, so the multiply is written as fma(a, b, -0.0) with the -0.0 arriving as a kernel argument: a * b + (-0.0)
+// is the correctly rounded product (sign of zero included) and cannot be fused with the following add.
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b, unsigned long long nz) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_splat(float v) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
+  return r;
+}
+// running 2x2 pool over packed values: max (Keras MaxPooling2D) or sum (tf.nn.avg_pool, divided by 4 afterwards)
+template <int POOL>
+__device__ __forceinline__ ulonglong2 pool2(const ulonglong2 a, const ulonglong2 b) {
+  ulonglong2 r;
+  if (POOL == BX_POOL_MAX2) {
+    const float4 x = *reinterpret_cast<const float4*>(&a), y = *reinterpret_cast<const float4*>(&b);
+    const float4 m = make_float4(fmaxf(x.x, y.x), fmaxf(x.y, y.y), fmaxf(x.z, y.z), fmaxf(x.w, y.w));
+    r = *reinterpret_cast<const ulonglong2*>(&m);
+  } else {
+    r.x = f2_add(a.x, b.x);
+    r.y = f2_add(a.y, b.y);
+  }
+  return r;
+}
+
 // implemented in bx_roi_band.cu: returns BX_OK and sets *used = 1 when the band kernel handled the launch
 int roi_band_launch(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st, int* used);
 

@@ -316,30 +316,6 @@ __device__ __forceinline__ float4 lerp2(const float4 tl, const float4 tr, const 
   return make_float4(t0 + (b0 - t0) * wy, t1 + (b1 - t1) * wy, t2 + (b2 - t2) * wy, t3 + (b3 - t3) * wy);
 }
 
-// Packed fp32x2 arithmetic (sm_100 FADD2 / FFMA2): two IEEE fp32 operations per issued instruction, each lane rounded
-// exactly like the scalar op.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (single rounding) even with
-// -fmad=false, so the multiply is written as fma(a, b, -0.0) with the -0.0 arriving as a kernel argument: a * b + (-0.0)
-// is the correctly rounded product (sign of zero included) and cannot be fused with the following add.
-__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b, unsigned long long nz) {
-  unsigned long long r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
-  return r;
-}
-__device__ __forceinline__ unsigned long long f2_splat(float v) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
-  return r;
-}
 // t = tl + (tr - tl) * wx ; b = bl + (br - bl) * wx ; out = t + (b - t) * wy     (op order of TF's crop_and_resize)
 __device__ __forceinline__ ulonglong2 lerp2_packed(const ulonglong2 tl, const ulonglong2 tr, const ulonglong2 bl,
                                                    const ulonglong2 br, unsigned long long wx, unsigned long long wy,
@@ -352,21 +328,6 @@ __device__ __forceinline__ ulonglong2 lerp2_packed(const ulonglong2 tl, const ul
   o.x = f2_add(t01, f2_mul(f2_sub(b01, t01), wy, nz));
   o.y = f2_add(t23, f2_mul(f2_sub(b23, t23), wy, nz));
   return o;
-}
-
-// running 2x2 pool over packed values: max (Keras MaxPooling2D) or sum (tf.nn.avg_pool, divided by 4 afterwards)
-template <int POOL>
-__device__ __forceinline__ ulonglong2 pool2(const ulonglong2 a, const ulonglong2 b) {
-  ulonglong2 r;
-  if (POOL == BX_POOL_MAX2) {
-    const float4 x = *reinterpret_cast<const float4*>(&a), y = *reinterpret_cast<const float4*>(&b);
-    const float4 m = make_float4(fmaxf(x.x, y.x), fmaxf(x.y, y.y), fmaxf(x.z, y.z), fmaxf(x.w, y.w));
-    r = *reinterpret_cast<const ulonglong2*>(&m);
-  } else {
-    r.x = f2_add(a.x, b.x);
-    r.y = f2_add(a.y, b.y);
-  }
-  return r;
 }
 
 template <int POOL>
