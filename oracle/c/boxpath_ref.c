@@ -226,3 +226,64 @@ int orc_c4_proposal_roi(const float* anchors, const float* deltas, const float* 
   free(bi);
   return rc;
 }
+
+/* FPN composite on the host (bench.py --workload cfg3|cfg5): per image decode+clip -> NMS over the concatenated P2..P6
+ * anchors (model/region_proposal.py:37-81), then level assignment (fpn/base_fpn_model.py:303-324) and, per level,
+ * crop_and_resize 2P x 2P on boxes normalised by the image size + 2x2 max pool (model/roi_pooling.py:15-42), written
+ * level-major over the whole batch like bx_fpn_roi_features.  feats[l] = [batch, fh[l], fw[l], c], 4 levels. */
+int orc_fpn_proposal_roi(const float* anchors, const float* deltas, const float* scores, const float* const* feats,
+                         const int* fh, const int* fw, int batch, int n, int c, const float* means, const float* stds,
+                         int H, int W, int pre_nms_top_k, int post_nms, float thr, int P, float* out_rois,
+                         int* out_idx, int* out_count, float* out_feat, int* out_order) {
+  int fail = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < batch; ++b) {
+    float* dec = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+    if (!dec) { fail = 1; continue; }
+    orc_decode_clip(anchors, deltas + (size_t)b * n * 4, n, means, stds, H, W, dec);
+    int* idx = out_idx + (size_t)b * post_nms;
+    const int kept = orc_nms(dec, scores + (size_t)b * n, n, pre_nms_top_k, post_nms, thr, idx);
+    out_count[b] = kept;
+    float* ro = out_rois + (size_t)b * post_nms * 4;
+    for (int k = 0; k < post_nms; ++k) {
+      if (k < kept) memcpy(ro + 4*k, dec + 4*(size_t)idx[k], sizeof(float) * 4);
+      else { memset(ro + 4*k, 0, sizeof(float) * 4); idx[k] = -1; }
+    }
+    free(dec);
+  }
+  if (fail) return -1;
+  const int r = batch * post_nms, Q = 2 * P;
+  int* lvl = (int*)malloc(sizeof(int) * (size_t)(r > 0 ? r : 1));
+  float* nb = (float*)malloc(sizeof(float) * 4 * (size_t)(r > 0 ? r : 1));
+  int* bi = (int*)malloc(sizeof(int) * (size_t)(r > 0 ? r : 1));
+  if (!lvl || !nb || !bi) return -1;
+  for (int k = 0; k < r; ++k) {
+    const float* q = out_rois + 4 * (size_t)k;
+    const float hh = fmaxf(0.0f, q[3] - q[1]), ww = fmaxf(0.0f, q[2] - q[0]);
+    float lv = floorf(4.0f + logf(sqrtf(ww * hh + 1e-8f) / 224.0f) / logf(2.0f));
+    lv = fminf(fmaxf(lv, 2.0f), 5.0f);
+    lvl[k] = (int)lv - 2;
+  }
+  int pos = 0, rc = 0;
+  for (int l = 0; l < 4 && !rc; ++l) {
+    int m = 0;
+    for (int k = 0; k < r; ++k)
+      if (lvl[k] == l) {
+        const float* q = out_rois + 4 * (size_t)k;
+        nb[4*m] = q[1] / (float)H; nb[4*m+1] = q[0] / (float)W; nb[4*m+2] = q[3] / (float)H; nb[4*m+3] = q[2] / (float)W;
+        bi[m] = k / post_nms;
+        out_order[pos + m] = k;
+        ++m;
+      }
+    if (m) {
+      float* tmp = (float*)malloc(sizeof(float) * (size_t)m * Q * Q * c);
+      if (!tmp) { rc = -1; break; }
+      orc_crop_and_resize(feats[l], batch, fh[l], fw[l], c, nb, bi, m, Q, Q, 0.0f, tmp);
+      orc_max_pool_2x2(tmp, m, Q, Q, c, out_feat + (size_t)pos * P * P * c);
+      free(tmp);
+    }
+    pos += m;
+  }
+  free(lvl); free(nb); free(bi);
+  return rc;
+}

@@ -110,6 +110,43 @@ def test_c_twin_agrees_with_numpy_oracle():
     assert np.array_equal(o_feat, orc.roi_pool_c4(feat, o_rois[0], 16, P, True))
 
 
+def test_c_twin_fpn_composite_agrees_with_numpy_oracle():
+    """orc_fpn_proposal_roi (the CPU arm of bench_fpn.py) against the numpy oracle: 2 images, C = 8."""
+    so = os.path.join(ROOT, 'oracle', 'c', 'libboxpath_ref.so')
+    subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle', 'c')])
+    lib = ctypes.CDLL(so)
+    hw, b, post, P, c = (600, 1000), 2, 200, 7, 8
+    ims = [syn.fpn_image(3, i, hw, channels=c) for i in range(b)]
+    anchors = ims[0]['anchors']; n = anchors.shape[0]
+    deltas = np.ascontiguousarray(np.stack([im['deltas'] for im in ims]))
+    scores = np.ascontiguousarray(np.stack([im['scores'] for im in ims]))
+    feats = [np.ascontiguousarray(np.stack([im['feats'][l] for im in ims])) for l in range(4)]
+    fptr = (ctypes.c_void_p * 4)(*[f.ctypes.data for f in feats])
+    fh = (ctypes.c_int * 4)(*[f.shape[1] for f in feats]); fw = (ctypes.c_int * 4)(*[f.shape[2] for f in feats])
+    means, stds = np.zeros(4, np.float32), np.ones(4, np.float32)
+    o_rois = np.zeros((b, post, 4), np.float32); o_idx = np.zeros((b, post), np.int32); o_cnt = np.zeros(b, np.int32)
+    o_feat = np.zeros((b * post, P, P, c), np.float32); o_ord = np.zeros(b * post, np.int32)
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)  # noqa: E731
+    rc = lib.orc_fpn_proposal_roi(vp(anchors), vp(deltas), vp(scores), fptr, fh, fw, b, n, c, vp(means), vp(stds), hw[0], hw[1],
+                                  0, post, ctypes.c_float(0.7), P, vp(o_rois), vp(o_idx), vp(o_cnt), vp(o_feat), vp(o_ord))
+    assert rc == 0 and (o_cnt == post).all()
+    for i in range(b):
+        _, idx = orc.region_proposal(deltas[i], anchors, scores[i], hw, post)
+        assert np.array_equal(o_idx[i], idx)
+    rois = o_rois.reshape(-1, 4)
+    lv, _, order = orc.assign_levels(rois)
+    assert np.array_equal(o_ord, order)
+    bi = np.repeat(np.arange(b, dtype=np.int32), post)
+    pos = 0
+    for l in range(4):
+        k = order[lv[order] == l + 2]
+        if k.size:
+            want = orc.roi_pool_fpn(feats[l], rois[k], hw, P, box_ind=bi[k])
+            assert np.array_equal(o_feat[pos:pos + k.size], want)
+        pos += k.size
+    assert pos == b * post
+
+
 @pytest.mark.skipif(not os.path.isdir('/root/reference/object_detection'), reason='reference sources only exist in the build container')
 def test_golden_vectors_regenerate_from_the_reference(tmp_path):
     """Re-run oracle/make_golden.py (reference files on the numpy TF shim) and compare with the committed vectors."""
