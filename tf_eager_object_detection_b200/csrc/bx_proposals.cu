@@ -108,7 +108,54 @@ struct Shared {
   int cand_count;
   int kept;
   int state;
+  // thread-block-cluster sweep (leader = cluster rank 0 publishes, helpers read over DSMEM)
+  int c_cmd;              // 1 = tile, 2 = done
+  int c_t0, c_tn;         // tile start / size in cand_box
+  int c_kept;             // kept count before this tile
+  int p_valid;            // previous tile's result below is valid
+  int p_kept;             // kept count before the previous tile
+  uint64_t p_keepmask;    // previous tile's keep mask
+  uint64_t sup_part[8];   // partial suppression masks written by the helpers
 };
+
+// ---- cluster primitives (no-ops / rank 0 of 1 when the kernel is launched without a cluster dimension)
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem_ptr, uint32_t rank) {
+  const uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(local_smem_ptr));
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ int dsmem_ld_s32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t dsmem_ld_u64(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 dsmem_ld_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void dsmem_st_u64(uint32_t addr, uint64_t v) {
+  asm volatile("st.shared::cluster.u64 [%0], %1;" :: "r"(addr), "l"(static_cast<unsigned long long>(v)) : "memory");
+}
 
 template <bool kCache>
 __device__ __forceinline__ uint32_t load_key(const ProposalArgs& a, const uint32_t* skeys, const float* scores,
@@ -116,6 +163,60 @@ __device__ __forceinline__ uint32_t load_key(const ProposalArgs& a, const uint32
   if (kCache) return skeys[i];
   if (gkeys) return gkeys[i];
   return bx_score_key(scores[i] + 0.0f);
+}
+
+// Helper CTA of a cluster (rank > 0): owns the kept boxes g with g % cs == rank and, for every tile the leader
+// announces, tests the tile's 64 candidates against them.  Two cluster barriers per tile: A = "tile published",
+// B = "partial masks delivered".
+__device__ void nms_cluster_helper(const ProposalArgs& a, float4* tilebuf /* [2][kTile] */, float4* kept_box,
+                                   const Shared* leader_sh_local, const float4* leader_cand_local, uint32_t rank,
+                                   uint32_t cs) {
+  __shared__ int h_cmd, h_t0, h_tn, h_kept, h_pvalid, h_pkept;
+  __shared__ uint64_t h_pmask, h_sup;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lsh = dsmem_addr(leader_sh_local, 0);
+  const uint32_t lcand = dsmem_addr(leader_cand_local, 0);
+  int cur = 0;
+  for (;;) {
+    cluster_sync_all();                                                   // A
+    if (tid == 0) {
+      h_cmd = dsmem_ld_s32(lsh + offsetof(Shared, c_cmd));
+      h_t0 = dsmem_ld_s32(lsh + offsetof(Shared, c_t0));
+      h_tn = dsmem_ld_s32(lsh + offsetof(Shared, c_tn));
+      h_kept = dsmem_ld_s32(lsh + offsetof(Shared, c_kept));
+      h_pvalid = dsmem_ld_s32(lsh + offsetof(Shared, p_valid));
+      h_pkept = dsmem_ld_s32(lsh + offsetof(Shared, p_kept));
+      h_pmask = dsmem_ld_u64(lsh + offsetof(Shared, p_keepmask));
+      h_sup = 0ull;
+    }
+    __syncthreads();
+    if (h_cmd != 1) {
+      cluster_sync_all();                                                 // B (the leader stays alive until here)
+      return;
+    }
+    const int t0 = h_t0, tn = h_tn, kept = h_kept;
+    if (tid < tn) tilebuf[cur * kTile + tid] = dsmem_ld_f4(lcand + static_cast<uint32_t>(t0 + tid) * 16u);
+    if (h_pvalid && tid < kTile && ((h_pmask >> tid) & 1ull)) {            // adopt this CTA's share of the last keeps
+      const uint32_t g = static_cast<uint32_t>(h_pkept) + __popcll(h_pmask & ((1ull << tid) - 1ull));
+      if (g % cs == rank) kept_box[g / cs] = normalise(tilebuf[(cur ^ 1) * kTile + tid]);
+    }
+    __syncthreads();
+    const int kl = (kept > static_cast<int>(rank)) ? (kept - static_cast<int>(rank) + static_cast<int>(cs) - 1) / static_cast<int>(cs) : 0;
+    const int c = tid & 63;
+    bool sflag = false;
+    if (c < tn) {
+      const float4 cb = normalise(tilebuf[cur * kTile + c]);
+      const float ca = (cb.z - cb.x) * (cb.w - cb.y);
+      for (int j = tid >> 6; j < kl && !sflag; j += 16) sflag = iou_gt(cb, ca, kept_box[j], a.thr);
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, sflag);
+    if (lane == 0 && m) atomicOr(reinterpret_cast<unsigned long long*>(&h_sup),
+                                 static_cast<unsigned long long>(m) << ((warp & 1) * 32));
+    __syncthreads();
+    if (tid == 0) dsmem_st_u64(lsh + offsetof(Shared, sup_part) + rank * 8u, h_sup);
+    cluster_sync_all();                                                   // B
+    cur ^= 1;
+  }
 }
 
 template <bool kCache>
@@ -134,8 +235,14 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int img = blockIdx.x;
+  const uint32_t cs = cluster_size(), crank = cluster_rank();   // 1, 0 unless launched with a cluster dimension
+  const int img = blockIdx.x / cs;
   if (a.run_flag && a.run_flag[img * 4] == 0) return;           // fallback launch: nothing to redo for this image
+  if (crank != 0) {
+    nms_cluster_helper(a, cand_box, kept_box, sh, cand_box, crank, cs);
+    return;
+  }
+  if (cs > 1 && tid == 0) sh->p_valid = 0;
   const int n = a.topset_info ? min(a.topset_info[img * 4 + 1], a.n) : a.n;
   const size_t full = a.src_idx ? static_cast<size_t>(a.src_stride) : static_cast<size_t>(a.n);
   const float* scores = a.scores ? a.scores + static_cast<size_t>(img) * a.n : nullptr;
@@ -370,8 +477,20 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
     for (int t0 = 0; t0 < cnt && sh->kept < a.post_nms; t0 += kTile) {
       const int tn = min(kTile, cnt - t0);
       const int kept = sh->kept;
-      if (tid == 0) sh->sup = 0ull;
+      if (tid == 0) {
+        sh->sup = 0ull;
+        if (cs > 1) {                        // publish the tile (the previous tile's keeps ride along in p_*)
+          sh->c_cmd = 1;
+          sh->c_t0 = t0;
+          sh->c_tn = tn;
+          sh->c_kept = kept;
+        }
+      }
+      if (cs > 1 && tid < 8) sh->sup_part[tid] = 0ull;
       __syncthreads();
+      if (cs > 1) cluster_sync_all();        // A: helpers start on this tile
+      // kept boxes are dealt round-robin over the cluster: this CTA holds g = 0, cs, 2cs, ... at kept_box[g / cs]
+      const int kl = (cs > 1) ? (kept + static_cast<int>(cs) - 1) / static_cast<int>(cs) : kept;
       {
         // (1) tile candidates vs kept list: candidate c = tid & 63, kept subset j = tid>>6 (mod 16)
         const int c = tid & 63;
@@ -379,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         if (c < tn) {
           const float4 cb = normalise(cand_box[t0 + c]);
           const float ca = (cb.z - cb.x) * (cb.w - cb.y);
-          for (int j = tid >> 6; j < kept && !s; j += 16) s = iou_gt(cb, ca, kept_box[j], a.thr);
+          for (int j = tid >> 6; j < kl && !s; j += 16) s = iou_gt(cb, ca, kept_box[j], a.thr);
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, s);
         if (lane == 0 && m) atomicOr(reinterpret_cast<unsigned long long*>(&sh->sup),
@@ -403,11 +522,16 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         if (part == 0) rowmask[i] = bits;
       }
       __syncthreads();
+      if (cs > 1) cluster_sync_all();        // B: the helpers' partial masks have landed in sup_part
       if (warp == 0) {
         // greedy resolve of the tile by warp 0, every lane redundantly: the 64 mask rows are transposed into registers
         // with independent shuffles (rows 0-31 then 32-63, 32 columns at a time), so the dependent chain is register-only
         const uint64_t my_lo = rowmask[lane], my_hi = rowmask[lane + 32];
         uint64_t removed = sh->sup;
+        if (cs > 1) {
+#pragma unroll
+          for (int r = 1; r < 8; ++r) removed |= sh->sup_part[r];
+        }
         if (tn < 64) removed |= ~((1ull << tn) - 1ull);
         int room = a.post_nms - kept;
         uint32_t rem = static_cast<uint32_t>(removed), keep_lo = 0u, keep_hi = 0u;
@@ -433,6 +557,9 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
           const uint64_t keep = static_cast<uint64_t>(keep_lo) | (static_cast<uint64_t>(keep_hi) << 32);
           sh->keepmask = keep;
           sh->kept = kept + __popcll(keep);
+          sh->p_valid = 1;
+          sh->p_kept = kept;
+          sh->p_keepmask = keep;
         }
       }
       __syncthreads();
@@ -441,7 +568,8 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         if ((keep >> tid) & 1ull) {
           const int pos = kept + __popcll(keep & ((1ull << tid) - 1ull));
           const float4 b = cand_box[t0 + tid];
-          kept_box[pos] = normalise(b);
+          if (cs == 1) kept_box[pos] = normalise(b);
+          else if (pos % cs == 0) kept_box[pos / cs] = normalise(b);
           const int p = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(cand_key[t0 + tid] & 0xFFFFFFFFull));
           out_idx[pos] = src_idx ? src_idx[p] : p;
           if (out_boxes) out_boxes[pos] = b;
@@ -455,6 +583,12 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
     __syncthreads();
   }
 
+  if (cs > 1) {                              // release the helpers; stay until they have read the command
+    if (tid == 0) sh->c_cmd = 2;
+    __syncthreads();
+    cluster_sync_all();
+    cluster_sync_all();
+  }
   // ---- pad the tail, publish the count
   const int kept = sh->kept;
   for (int i = kept + tid; i < a.post_nms; i += kThreads) {
@@ -728,7 +862,34 @@ static int launch_proposals_kernel(bx_handle* h, ProposalArgs& a, int batch, cud
              h->smem_optin);
   if (cache) {
     BX_CUDA(cudaFuncSetAttribute(proposals_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    proposals_kernel<true><<<batch, kThreads, smem, st>>>(a);
+    // large quotas: the sweep against the kept list dominates -> spread it over a thread-block cluster per image
+    static const int cs_env = getenv("BX_NMS_CLUSTER") ? atoi(getenv("BX_NMS_CLUSTER")) : 0;   // A/B switch
+    int cs = (a.post_nms >= 512) ? 8 : 1;
+    if (cs_env > 0) cs = cs_env > 8 ? 8 : cs_env;
+    for (; cs > 1; cs >>= 1) {             // largest cluster size whose clusters are all co-resident (one wave)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(batch * cs);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int max_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, proposals_kernel<true>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        continue;
+      }
+      if (max_clusters < batch && cs_env <= 0) continue;
+      if (max_clusters < 1) continue;
+      BX_CUDA(cudaLaunchKernelEx(&cfg, proposals_kernel<true>, a));
+      break;
+    }
+    if (cs == 1) proposals_kernel<true><<<batch, kThreads, smem, st>>>(a);
   } else {
     BX_CUDA(cudaFuncSetAttribute(proposals_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     proposals_kernel<false><<<batch, kThreads, smem, st>>>(a);
