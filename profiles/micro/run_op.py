@@ -25,6 +25,14 @@ elif which == 'vgg_pool':
     rois, _, _ = ops.proposals(a, d, s, (600, 1000), 300)
     feat = torch.randn((1, 38, 63, 512), device=dev)
     fn = lambda: ops.roi_pool(_lib.ROI_STRIDE_NORM, _lib.POOL_MAX2, 7, feat, rois[0])
+elif which == 'anchor_target':
+    B = 16
+    rng = np.random.default_rng(syn.seed_for(4, 1))
+    anc = syn.c4_anchors(38, 63)
+    gts = np.stack([syn.gt_boxes(rng, 100, (600, 1000))[0] for _ in range(B)])
+    perm = np.stack([rng.permutation(anc.shape[0]).astype(np.int32) for _ in range(B)])
+    a_, g_, p_ = cu(anc), cu(gts), cu(perm)
+    fn = lambda: ops.anchor_target(a_, g_, p_, (600, 1000))
 else:
     raise SystemExit('unknown op')
 for _ in range(5):

@@ -29,24 +29,32 @@ __global__ void __launch_bounds__(256) pairwise_iou_kernel(const float4* __restr
 // Block-wide: among elements i in [0,n) with flag(i) true, find the threshold composite T such that exactly k elements
 // have comp(i) <= T, comp(i) = (prio[i] << 32) | i  (all distinct).  Adaptive 1024-bin radix refinement.
 // All threads of the block must call; `hist` has kSelBins entries, `sc` 8 uint64 scratch words.  Requires 1 <= k <= #flagged.
-template <typename FlagFn>
-__device__ uint64_t block_select_k_smallest(int n, const int* __restrict__ prio, FlagFn flag, int k, uint32_t* hist,
-                                            uint64_t* sc) {
+// `val(i, v)` returns whether element i takes part and, if so, its composite in v.
+template <typename ValFn>
+__device__ uint64_t block_select_k_smallest_fn(int n, ValFn val, int k, uint32_t* hist, uint64_t* sc) {
   const int tid = threadIdx.x, nt = blockDim.x;
   uint64_t lo = 0ull, hi = 0xFFFFFFFFFFFFFFFFull;
   // tighten the range to [min,max] of the flagged composites
   {
     uint64_t mn = 0xFFFFFFFFFFFFFFFFull, mx = 0ull;
-    for (int i = tid; i < n; i += nt)
-      if (flag(i)) {
-        const uint64_t v = (static_cast<uint64_t>(static_cast<uint32_t>(prio[i])) << 32) | static_cast<uint32_t>(i);
+    for (int i = tid; i < n; i += nt) {
+      uint64_t v;
+      if (val(i, v)) {
         mn = min(mn, v);
         mx = max(mx, v);
       }
+    }
     if (tid == 0) { sc[0] = 0xFFFFFFFFFFFFFFFFull; sc[1] = 0ull; }
     __syncthreads();
-    atomicMin(reinterpret_cast<unsigned long long*>(&sc[0]), static_cast<unsigned long long>(mn));
-    atomicMax(reinterpret_cast<unsigned long long*>(&sc[1]), static_cast<unsigned long long>(mx));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {                    // warp reduce first: 64-bit shared atomics are CAS loops
+      mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+      mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+    }
+    if ((tid & 31) == 0) {
+      atomicMin(reinterpret_cast<unsigned long long*>(&sc[0]), static_cast<unsigned long long>(mn));
+      atomicMax(reinterpret_cast<unsigned long long*>(&sc[1]), static_cast<unsigned long long>(mx));
+    }
     __syncthreads();
     lo = sc[0];
     hi = sc[1];
@@ -59,30 +67,54 @@ __device__ uint64_t block_select_k_smallest(int n, const int* __restrict__ prio,
     while ((span >> shift) >= static_cast<uint64_t>(kSelBins)) ++shift;
     for (int i = tid; i < kSelBins; i += nt) hist[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += nt)
-      if (flag(i)) {
-        const uint64_t v = (static_cast<uint64_t>(static_cast<uint32_t>(prio[i])) << 32) | static_cast<uint32_t>(i);
-        if (v >= lo && v <= hi) atomicAdd(&hist[static_cast<uint32_t>((v - lo) >> shift)], 1u);
-      }
+    for (int i = tid; i < n; i += nt) {
+      uint64_t v;
+      if (val(i, v) && v >= lo && v <= hi) atomicAdd(&hist[static_cast<uint32_t>((v - lo) >> shift)], 1u);
+    }
     __syncthreads();
-    if (tid == 0) {
-      int run = 0, b = 0;
-      for (; b < kSelBins; ++b) {
-        const int c = static_cast<int>(hist[b]);
-        if (run + c > need) break;
-        run += c;
+    {
+      // first bin b whose count does not fit entirely (run + c > need): block-wide exclusive scan, one bin per thread
+      // (blockDim.x == kSelBins)
+      __shared__ uint32_t wtot[32];
+      const int lane = tid & 31, warp = tid >> 5;
+      const uint32_t c = hist[tid];
+      uint32_t pre = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, pre, d);
+        if (lane >= d) pre += o;
       }
-      // b: first bin that does not fit entirely (b == kSelBins: everything fits, then run == need by the precondition)
-      if (run == need) {
-        sc[2] = 1ull;                                              // done
-        sc[3] = (b == 0) ? (lo - 1ull) : (lo + (static_cast<uint64_t>(b) << shift) - 1ull);  // T = last value below bin b
-        if (b == kSelBins) sc[3] = hi;
-      } else {
-        sc[2] = 0ull;
-        sc[4] = lo + (static_cast<uint64_t>(b) << shift);
-        uint64_t nhi = sc[4] + ((1ull << shift) - 1ull);
-        sc[5] = nhi > hi ? hi : nhi;
-        sc[6] = static_cast<uint64_t>(need - run);
+      if (lane == 31) wtot[warp] = pre;
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t t = wtot[lane];
+        uint32_t p2 = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, p2, d);
+          if (lane >= d) p2 += o;
+        }
+        wtot[lane] = p2 - t;                                        // exclusive warp offsets
+      }
+      __syncthreads();
+      const uint32_t before = wtot[warp] + pre - c;                 // count in bins < tid
+      const bool crossing = (before <= static_cast<uint32_t>(need)) && (before + c > static_cast<uint32_t>(need));
+      const bool none = (tid == kSelBins - 1) && (before + c <= static_cast<uint32_t>(need));
+      if (crossing || none) {
+        const int b = crossing ? tid : kSelBins;
+        const int run = static_cast<int>(crossing ? before : before + c);
+        // b: first bin that does not fit entirely (b == kSelBins: everything fits, then run == need by the precondition)
+        if (run == need) {
+          sc[2] = 1ull;                                              // done
+          sc[3] = (b == 0) ? (lo - 1ull) : (lo + (static_cast<uint64_t>(b) << shift) - 1ull);  // T = last value below bin b
+          if (b == kSelBins) sc[3] = hi;
+        } else {
+          sc[2] = 0ull;
+          sc[4] = lo + (static_cast<uint64_t>(b) << shift);
+          uint64_t nhi = sc[4] + ((1ull << shift) - 1ull);
+          sc[5] = nhi > hi ? hi : nhi;
+          sc[6] = static_cast<uint64_t>(need - run);
+        }
       }
     }
     __syncthreads();
@@ -98,6 +130,16 @@ __device__ uint64_t block_select_k_smallest(int n, const int* __restrict__ prio,
   }
 }
 
+template <typename FlagFn>
+__device__ uint64_t block_select_k_smallest(int n, const int* __restrict__ prio, FlagFn flag, int k, uint32_t* hist,
+                                            uint64_t* sc) {
+  return block_select_k_smallest_fn(n, [&](int i, uint64_t& v) {
+    if (!flag(i)) return false;
+    v = (static_cast<uint64_t>(static_cast<uint32_t>(prio[i])) << 32) | static_cast<uint32_t>(i);
+    return true;
+  }, k, hist, sc);
+}
+
 // ------------------------------------------------------------------------------------------- anchor target
 struct ATArgs {
   const float4* anchors;  // [n]
@@ -111,6 +153,7 @@ struct ATArgs {
   float* row_max;         // [batch,n]
   int* row_arg;           // [batch,n]
   int* col_max;           // [batch,max_gt] (fp32 bits, iou >= 0 so int order == float order)
+  int* warp_max;          // [batch, ceil(n/256)*8, max_gt] per-warp maxima of pass A (fp32 bits)
   int* label;             // [batch,n] pre-sampling then final label (-1/0/1), -2 = outside image
   int* counts;            // [batch,4] = #fg, #bg before sampling; after sampling: fg_final, bg_final
   // outputs
@@ -125,18 +168,29 @@ __device__ __forceinline__ bool anchor_inside(const float4 a, float max_x, float
   return (a.x >= 0.0f) && (a.y >= 0.0f) && (a.z <= max_x) && (a.w <= max_y);  // utils/bbox_tf.py:95-100
 }
 
-// pass A: row max / argmax per inside anchor, column max per gt over inside anchors
+// IoU of one (anchor, gt) pair exactly as bx_iou_plus1, with the division skipped for disjoint pairs (most of them)
+__device__ __forceinline__ float at_iou(const float4 a, const float area_a, const float4 b, const float area_b) {
+  const float ih = fmaxf(0.0f, fminf(a.w, b.w) - fmaxf(a.y, b.y) + 1.0f);
+  const float iw = fmaxf(0.0f, fminf(a.z, b.z) - fmaxf(a.x, b.x) + 1.0f);
+  const float inter = ih * iw;
+  float v = 0.0f;
+  if (inter != 0.0f) v = inter / (area_a + area_b - inter);
+  return v;
+}
+
+// pass A: row max / argmax per inside anchor; per (warp, gt) maxima kept for pass B; column max per gt.
+// dynamic smem: gt [m] float4 | area [m] float | warp maxima [8][m] int
 __global__ void __launch_bounds__(256) at_rowstats_kernel(const ATArgs a) {
-  __shared__ float4 s_gt[kMaxGt];
-  __shared__ float s_area[kMaxGt];
-  __shared__ int s_col[kMaxGt];
-  const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  extern __shared__ __align__(16) unsigned char at_smem[];
+  const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = a.gt_counts ? a.gt_counts[img] : a.max_gt;
+  float4* s_gt = reinterpret_cast<float4*>(at_smem);
+  float* s_area = reinterpret_cast<float*>(s_gt + a.max_gt);
+  int* s_w = reinterpret_cast<int*>(s_area + a.max_gt);          // [8][max_gt]
   for (int j = tid; j < m; j += 256) {
     const float4 g = a.gt[static_cast<size_t>(img) * a.max_gt + j];
     s_gt[j] = g;
     s_area[j] = bx_area_plus1(g);
-    s_col[j] = 0;
   }
   __syncthreads();
   const int i = blockIdx.x * 256 + tid;
@@ -146,11 +200,15 @@ __global__ void __launch_bounds__(256) at_rowstats_kernel(const ATArgs a) {
   const float area = bx_area_plus1(anc);
   float best = -1.0f;
   int arg = 0;
+  const bool any_inside = __any_sync(0xFFFFFFFFu, inside);
   for (int j = 0; j < m; ++j) {
-    float v = inside ? bx_iou_plus1(anc, area, s_gt[j], s_area[j]) : 0.0f;
-    if (inside && v > best) { best = v; arg = j; }        // first max, like tf.argmax
-    const int wmax = __reduce_max_sync(0xFFFFFFFFu, __float_as_int(v));  // int order == float order for v >= 0
-    if (lane == 0) atomicMax(&s_col[j], wmax);
+    int wmax = 0;
+    if (any_inside) {
+      const float v = inside ? at_iou(anc, area, s_gt[j], s_area[j]) : 0.0f;
+      if (inside && v > best) { best = v; arg = j; }        // first max, like tf.argmax
+      wmax = __reduce_max_sync(0xFFFFFFFFu, __float_as_int(v));  // int order == float order for v >= 0
+    }
+    if (lane == 0) s_w[warp * a.max_gt + j] = wmax;
   }
   if (live) {
     const size_t o = static_cast<size_t>(img) * a.n + i;
@@ -158,33 +216,51 @@ __global__ void __launch_bounds__(256) at_rowstats_kernel(const ATArgs a) {
     a.row_arg[o] = arg;
   }
   __syncthreads();
-  for (int j = tid; j < m; j += 256) atomicMax(&a.col_max[static_cast<size_t>(img) * a.max_gt + j], s_col[j]);
+  int* g_w = a.warp_max + (static_cast<size_t>(img) * gridDim.x + blockIdx.x) * 8 * a.max_gt;
+  for (int e = tid; e < 8 * m; e += 256) {
+    const int w = e / m, j = e - w * m;
+    g_w[w * a.max_gt + j] = s_w[w * a.max_gt + j];
+  }
+  for (int j = tid; j < m; j += 256) {
+    int c = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) c = max(c, s_w[w * a.max_gt + j]);
+    if (c) atomicMax(&a.col_max[static_cast<size_t>(img) * a.max_gt + j], c);
+  }
 }
 
-// pass B: labels before subsampling (anchor_target.py:59-69) + fg/bg counts
+// pass B: labels before subsampling (anchor_target.py:59-69) + fg/bg counts.  "anchor i attains the column maximum of
+// gt j" (:64) is only possible in a warp whose own maximum for j equals the column maximum, so only those (warp, gt)
+// pairs — about one per gt — recompute their IoUs.
 __global__ void __launch_bounds__(256) at_label_kernel(const ATArgs a) {
-  __shared__ float4 s_gt[kMaxGt];
-  __shared__ float s_area[kMaxGt];
-  __shared__ float s_col[kMaxGt];
-  const int img = blockIdx.y, tid = threadIdx.x;
+  const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = a.gt_counts ? a.gt_counts[img] : a.max_gt;
-  for (int j = tid; j < m; j += 256) {
-    const float4 g = a.gt[static_cast<size_t>(img) * a.max_gt + j];
-    s_gt[j] = g;
-    s_area[j] = bx_area_plus1(g);
-    s_col[j] = __int_as_float(a.col_max[static_cast<size_t>(img) * a.max_gt + j]);
-  }
-  __syncthreads();
   const int i = blockIdx.x * 256 + tid;
+  const bool live = i < a.n;
+  const float4 anc = live ? a.anchors[i] : make_float4(0, 0, 0, 0);
+  const bool inside = live && anchor_inside(anc, static_cast<float>(a.p.image_w - 1), static_cast<float>(a.p.image_h - 1));
+  const float area = bx_area_plus1(anc);
+  const int* g_w = a.warp_max + ((static_cast<size_t>(img) * gridDim.x + blockIdx.x) * 8 + warp) * a.max_gt;
+  const int* colmax = a.col_max + static_cast<size_t>(img) * a.max_gt;
+  const float4* gt = a.gt + static_cast<size_t>(img) * a.max_gt;
+  bool is_gt_arg = false;
+  if (__any_sync(0xFFFFFFFFu, inside)) {
+    for (int j0 = 0; j0 < m; j0 += 32) {
+      const int j = j0 + lane;
+      uint32_t hit = __ballot_sync(0xFFFFFFFFu, j < m && g_w[j] == colmax[j]);
+      while (hit) {
+        const int jj = j0 + __ffs(hit) - 1;
+        hit &= hit - 1u;
+        const float4 g = gt[jj];
+        const float v = inside ? at_iou(anc, area, g, bx_area_plus1(g)) : -1.0f;
+        is_gt_arg |= (__float_as_int(v) == colmax[jj]);                                       // :64
+      }
+    }
+  }
   int lab = -2;
-  if (i < a.n) {
-    const float4 anc = a.anchors[i];
-    if (anchor_inside(anc, static_cast<float>(a.p.image_w - 1), static_cast<float>(a.p.image_h - 1))) {
-      const size_t o = static_cast<size_t>(img) * a.n + i;
-      const float mx = a.row_max[o];
-      const float area = bx_area_plus1(anc);
-      bool is_gt_arg = false;
-      for (int j = 0; j < m; ++j) is_gt_arg |= (bx_iou_plus1(anc, area, s_gt[j], s_area[j]) == s_col[j]);  // :64
+  if (live) {
+    if (inside) {
+      const float mx = a.row_max[static_cast<size_t>(img) * a.n + i];
       lab = -1;
       if (m > 0) {
         if (mx < a.p.neg_iou_threshold) lab = 0;      // :67
@@ -195,23 +271,99 @@ __global__ void __launch_bounds__(256) at_label_kernel(const ATArgs a) {
     a.label[static_cast<size_t>(img) * a.n + i] = lab;
   }
   const uint32_t fg = __ballot_sync(0xFFFFFFFFu, lab == 1), bg = __ballot_sync(0xFFFFFFFFu, lab == 0);
-  if ((tid & 31) == 0) {
+  if (lane == 0) {
     if (fg) atomicAdd(&a.counts[img * 4 + 0], __popc(fg));
     if (bg) atomicAdd(&a.counts[img * 4 + 1], __popc(bg));
   }
 }
 
-// pass C: subsample fg then bg by priority (anchor_target.py:72-84); one CTA per image
-__global__ void __launch_bounds__(1024) at_sample_kernel(const ATArgs a) {
+// pass C: subsample fg then bg by priority (anchor_target.py:72-84); one CTA per image.  kCompact: the (priority, index)
+// composites of the fg and bg anchors are compacted into shared memory in one pass over the labels and every selection
+// pass runs over those short lists ((nfg + nbg) * 8 bytes must fit); otherwise the passes stream labels from global.
+template <bool kCompact>
+__global__ void __launch_bounds__(1024) at_sample_kernel(const ATArgs a, const int cap) {
+  extern __shared__ __align__(16) unsigned char at_smem[];
   __shared__ uint32_t hist[kSelBins];
   __shared__ uint64_t sc[8];
-  const int img = blockIdx.x, tid = threadIdx.x;
+  __shared__ int s_cnt[2];
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   int* label = a.label + static_cast<size_t>(img) * a.n;
   const int* perm = a.perm + static_cast<size_t>(img) * a.n;
   const int nfg = a.counts[img * 4 + 0], nbg = a.counts[img * 4 + 1];
-  int fg_final = nfg;
-  if (nfg > a.p.max_pos_samples) {
-    fg_final = a.p.max_pos_samples;
+  const bool cut_fg = nfg > a.p.max_pos_samples;
+  const int fg_final = cut_fg ? a.p.max_pos_samples : nfg;
+  const int num_bg = a.p.total_num_samples - fg_final;   // :78
+  const bool cut_bg = nbg > num_bg;
+  const int bg_final = cut_bg ? max(num_bg, 0) : nbg;
+  if (tid == 0) {
+    a.counts[img * 4 + 2] = fg_final;
+    a.counts[img * 4 + 3] = bg_final;
+    if (a.out_counts) {
+      a.out_counts[img * 2 + 0] = fg_final;
+      a.out_counts[img * 2 + 1] = bg_final;
+    }
+  }
+  if (!cut_fg && !cut_bg) return;
+  if (kCompact && nfg + nbg <= cap) {
+    uint64_t* fgc = reinterpret_cast<uint64_t*>(at_smem);
+    uint64_t* bgc = fgc + nfg;
+    if (tid < 2) s_cnt[tid] = 0;
+    __syncthreads();
+    constexpr int kU = 8;                                // independent label / priority loads in flight per thread
+    for (int i0 = 0; i0 < a.n; i0 += 1024 * kU) {
+      int labs[kU], prs[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * 1024 + tid;
+        labs[u] = (i < a.n) ? label[i] : -2;
+        prs[u] = (i < a.n) ? perm[i] : 0;
+      }
+      uint32_t mf[kU], mb[kU];
+      int tf = 0, tb = 0;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        mf[u] = __ballot_sync(0xFFFFFFFFu, labs[u] == 1);
+        mb[u] = __ballot_sync(0xFFFFFFFFu, labs[u] == 0);
+        tf += __popc(mf[u]);
+        tb += __popc(mb[u]);
+      }
+      int pf = 0, pb = 0;                                 // one reservation per warp and batch
+      if (lane == 0) {
+        if (tf) pf = atomicAdd(&s_cnt[0], tf);
+        if (tb) pb = atomicAdd(&s_cnt[1], tb);
+      }
+      pf = __shfl_sync(0xFFFFFFFFu, pf, 0);
+      pb = __shfl_sync(0xFFFFFFFFu, pb, 0);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * 1024 + tid;
+        const uint64_t v = (static_cast<uint64_t>(static_cast<uint32_t>(prs[u])) << 32) | static_cast<uint32_t>(i);
+        if (labs[u] == 1) fgc[pf + __popc(mf[u] & ((1u << lane) - 1u))] = v;
+        if (labs[u] == 0) bgc[pb + __popc(mb[u] & ((1u << lane) - 1u))] = v;
+        pf += __popc(mf[u]);
+        pb += __popc(mb[u]);
+      }
+    }
+    __syncthreads();
+    if (cut_fg) {
+      uint64_t T = 0ull;
+      if (fg_final > 0) T = block_select_k_smallest_fn(nfg, [&](int i, uint64_t& v) { v = fgc[i]; return true; }, fg_final, hist, sc);
+      for (int i = tid; i < nfg; i += 1024) {
+        const uint64_t v = fgc[i];
+        if (fg_final == 0 || v > T) label[static_cast<uint32_t>(v)] = -1;
+      }
+    }
+    if (cut_bg) {
+      uint64_t T = 0ull;
+      if (bg_final > 0) T = block_select_k_smallest_fn(nbg, [&](int i, uint64_t& v) { v = bgc[i]; return true; }, bg_final, hist, sc);
+      for (int i = tid; i < nbg; i += 1024) {
+        const uint64_t v = bgc[i];
+        if (bg_final == 0 || v > T) label[static_cast<uint32_t>(v)] = -1;
+      }
+    }
+    return;
+  }
+  if (cut_fg) {
     uint64_t T = 0ull;
     if (fg_final > 0) T = block_select_k_smallest(a.n, perm, [&](int i) { return label[i] == 1; }, fg_final, hist, sc);
     for (int i = tid; i < a.n; i += 1024)
@@ -221,10 +373,7 @@ __global__ void __launch_bounds__(1024) at_sample_kernel(const ATArgs a) {
       }
     __syncthreads();
   }
-  const int num_bg = a.p.total_num_samples - fg_final;   // :78
-  int bg_final = nbg;
-  if (nbg > num_bg) {
-    bg_final = max(num_bg, 0);
+  if (cut_bg) {
     uint64_t T = 0ull;
     if (bg_final > 0) T = block_select_k_smallest(a.n, perm, [&](int i) { return label[i] == 0; }, bg_final, hist, sc);
     for (int i = tid; i < a.n; i += 1024)
@@ -233,14 +382,6 @@ __global__ void __launch_bounds__(1024) at_sample_kernel(const ATArgs a) {
         if (bg_final == 0 || v > T) label[i] = -1;
       }
     __syncthreads();
-  }
-  if (tid == 0) {
-    a.counts[img * 4 + 2] = fg_final;
-    a.counts[img * 4 + 3] = bg_final;
-    if (a.out_counts) {
-      a.out_counts[img * 2 + 0] = fg_final;
-      a.out_counts[img * 2 + 1] = bg_final;
-    }
   }
 }
 
@@ -460,7 +601,10 @@ extern "C" int bx_anchor_target(bx_handle* h, const float* anchors, int n, const
   if (batch == 0) return BX_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t bn = static_cast<size_t>(batch) * n;
-  const size_t ws = bn * (sizeof(float) + 2 * sizeof(int)) + static_cast<size_t>(batch) * (max_gt + 4) * sizeof(int);
+  const int nblk = static_cast<int>(bx_div_up(n, 256));
+  const size_t wm = static_cast<size_t>(batch) * nblk * 8 * (max_gt > 0 ? max_gt : 1);
+  const size_t ws = bn * (sizeof(float) + 2 * sizeof(int)) + static_cast<size_t>(batch) * (max_gt + 4) * sizeof(int) +
+                    wm * sizeof(int);
   int rc = bx_ws_reserve(h, ws);
   if (rc) return rc;
   ATArgs a = {};
@@ -477,18 +621,28 @@ extern "C" int bx_anchor_target(bx_handle* h, const float* anchors, int n, const
   a.label = a.row_arg + bn;
   a.col_max = a.label + bn;
   a.counts = a.col_max + static_cast<size_t>(batch) * max_gt;
+  a.warp_max = a.counts + static_cast<size_t>(batch) * 4;
   a.out_labels = out_labels;
   a.out_targets = reinterpret_cast<float4*>(out_targets);
   a.out_in_w = reinterpret_cast<float4*>(out_in_w);
   a.out_out_w = reinterpret_cast<float4*>(out_out_w);
   a.out_counts = out_counts;
   BX_CUDA(cudaMemsetAsync(a.col_max, 0, static_cast<size_t>(batch) * (max_gt + 4) * sizeof(int), st));
-  const dim3 grid(bx_div_up(n, 256), batch);
-  at_rowstats_kernel<<<grid, 256, 0, st>>>(a);
+  const dim3 grid(nblk, batch);
+  const size_t smem_a = static_cast<size_t>(max_gt) * (sizeof(float4) + sizeof(float) + 8 * sizeof(int));
+  if (smem_a > 48 * 1024)
+    BX_CUDA(cudaFuncSetAttribute(at_rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+  at_rowstats_kernel<<<grid, 256, smem_a, st>>>(a);
   BX_LAUNCH_CHECK(h);
   at_label_kernel<<<grid, 256, 0, st>>>(a);
   BX_LAUNCH_CHECK(h);
-  at_sample_kernel<<<batch, 1024, 0, st>>>(a);
+  // compaction lists of pass C: as many (priority, index) composites as shared memory holds, at most one per anchor
+  const size_t room = h->smem_optin > 16 * 1024 ? h->smem_optin - 16 * 1024 : 0;
+  int cap = static_cast<int>(room / sizeof(uint64_t));
+  if (cap > n) cap = n;
+  const size_t smem_c = static_cast<size_t>(cap) * sizeof(uint64_t);
+  BX_CUDA(cudaFuncSetAttribute(at_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+  at_sample_kernel<true><<<batch, 1024, smem_c, st>>>(a, cap);
   BX_LAUNCH_CHECK(h);
   at_finalize_kernel<<<grid, 256, 0, st>>>(a);
   BX_LAUNCH_CHECK(h);
