@@ -79,6 +79,22 @@ rows.append(('cfg4 anchor_target B=16 N=21546 M=100', t(lambda: ops.anchor_targe
 tr, _, tc = ops.proposals(anchors, deltas.repeat(2, 1, 1), scores.repeat(2, 1), (600, 1000), 2000)
 permr = cu(np.stack([rng.permutation(2000) for _ in range(16)]).astype(np.int32))
 rows.append(('cfg4 proposal_target B=16 K=2000 M=100 S=128', t(lambda: ops.proposal_target(tr, gtc, glc, permr, neg_iou_threshold=0.0, stds=(.1, .1, .2, .2), roi_counts=tc)), 16 * (16 * 2100 + 400 + 128 * (20 + 48 * 21))))
+# ---- "next" rows f1-f3
+hs, hd = syn.roi_head_outputs(np.random.default_rng(7), 16 * 300, 21)
+hs_c, hd_c = cu(hs.reshape(16, 300, 21)), cu(hd.reshape(16, 300, 21, 4))
+rois16 = ob.repeat(2, 1, 1)
+rows.append(('f1 post_ops_prediction B=16 R=300 C=21', t(lambda: ops.post_ops_prediction(hs_c, hd_c, rois16, (600, 1000), stds=(.1, .1, .2, .2))), 16 * 300 * (21 * 20 + 16)))
+lg = torch.randn((8, 38 * 63, 18), device=dev)
+rows.append(('f2 proposals_rpn  B=8 raw logits 6000->300 (softmax fused)', t(lambda: ops.proposals_rpn(anchors, deltas, lg, _lib.RPN_CAFFE, 9, (600, 1000), 300, pre_nms_top_k=6000)), 8 * (40 * 21546 + 20 * 300)))
+rows.append(('f2 generate_anchors FPN 800x1333 (267069 anchors)', t(lambda: __import__('tf_eager_object_detection_b200.anchor_generator', fromlist=['x']).make_fpn_anchors((800, 1333))), 16 * 267069))
+go = torch.randn((2400, 7, 7, 1024), device=dev)
+rows.append(('f3 roi_pool_grad 7x7x1024 R=2400 -> [8,38,63,1024]', t(lambda: ops.roi_pool_grad(_lib.ROI_STRIDE_NORM, _lib.POOL_NONE, 7, feat, ob.reshape(-1, 4), go, roi_counts=oc), n=10), 4 * 2400 * 49 * 1024 + 2 * 8 * 4 * 1024 * 38 * 63))
+gfp = [torch.randn((1, h, w, 256), device=dev) for (h, w) in syn.fpn_feature_shapes((600, 1000))[:1]]
+lab = torch.randint(-1, 2, (16 * 21546,), device=dev).float()
+lg2 = torch.randn((16 * 21546, 2), device=dev)
+rows.append(('f3 cls_loss + grad 344736 x 2 (RPN, labels -1/0/1)', t(lambda: ops.cls_loss(lg2, lab, with_grad=True)), 16 * 21546 * (8 + 4 + 8)))
+pr = torch.randn((16 * 21546, 4), device=dev)
+rows.append(('f3 smooth_l1_loss + grad 344736 x 4 (RPN)', t(lambda: ops.smooth_l1_loss(pr, pr * 0.5, torch.ones_like(pr), torch.ones_like(pr), 3.0, (0, 1), with_grad=True)), 16 * 21546 * 16 * 5))
 peak = 6538.3
 print('%-58s %10s %9s %12s %8s' % ('op', 'us/call', 'host us', 'alg. MB', 'of HBM'))
 for name, (us, host), b in rows:
