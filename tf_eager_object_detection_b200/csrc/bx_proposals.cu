@@ -503,7 +503,8 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, s);
         if (lane == 0 && m) atomicOr(reinterpret_cast<unsigned long long*>(&sh->sup),
                                      static_cast<unsigned long long>(m) << ((warp & 1) * 32));
-        // (2) intra-tile masks: row i = tid>>4, columns part*4 .. part*4+3 ; bit j set iff j > i and IoU(i,j) > thr
+        // (2) intra-tile masks: row i = tid>>4, columns part*4 .. part*4+3 ; bit j set iff j != i and IoU(i,j) > thr
+        //     (the test is symmetric bit for bit, so the bits below i are "the earlier candidates that suppress i")
         const int i = tid >> 4, part = tid & 15;
         uint64_t bits = 0ull;
         if (i < tn) {
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int j = part * 4 + q;
-            if (j > i && j < tn) {
+            if (j != i && j < tn) {
               if (iou_gt(ib, ia, normalise(cand_box[t0 + j]), a.thr)) bits |= (1ull << j);
             }
           }
@@ -524,35 +525,36 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
       __syncthreads();
       if (cs > 1) cluster_sync_all();        // B: the helpers' partial masks have landed in sup_part
       if (warp == 0) {
-        // greedy resolve of the tile by warp 0, every lane redundantly: the 64 mask rows are transposed into registers
-        // with independent shuffles (rows 0-31 then 32-63, 32 columns at a time), so the dependent chain is register-only
-        const uint64_t my_lo = rowmask[lane], my_hi = rowmask[lane + 32];
+        // greedy resolve of the tile by warp 0 as a fixed point: candidate i is kept iff it is alive and no KEPT earlier
+        // candidate suppresses it.  Iterating K <- {i alive : full[i] & below(i) & K == 0} from K = alive fixes
+        // candidates in index order (after t rounds every i < t is final), the greedy set is its only fixed point,
+        // and suppression chains inside a tile are short: a few ballot rounds instead of a 64-step dependent chain.
+        const uint64_t f0 = rowmask[lane], f1 = rowmask[lane + 32];
         uint64_t removed = sh->sup;
         if (cs > 1) {
 #pragma unroll
           for (int r = 1; r < 8; ++r) removed |= sh->sup_part[r];
         }
         if (tn < 64) removed |= ~((1ull << tn) - 1ull);
-        int room = a.post_nms - kept;
-        uint32_t rem = static_cast<uint32_t>(removed), keep_lo = 0u, keep_hi = 0u;
-        uint32_t rows[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) rows[i] = __shfl_sync(0xFFFFFFFFu, static_cast<uint32_t>(my_lo), i);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const bool k = !((rem >> i) & 1u) && room > 0;
-          if (k) { keep_lo |= 1u << i; rem |= rows[i]; --room; }
+        const uint64_t alive = ~removed;
+        const uint64_t below0 = (1ull << lane) - 1ull, below1 = (1ull << (lane + 32)) - 1ull;
+        const bool a0 = (alive >> lane) & 1ull, a1 = (alive >> (lane + 32)) & 1ull;
+        uint64_t K = alive;
+        for (;;) {
+          const bool k0 = a0 && ((f0 & below0 & K) == 0ull);
+          const bool k1 = a1 && ((f1 & below1 & K) == 0ull);
+          const uint64_t Kn = static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, k0)) |
+                              (static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, k1)) << 32);
+          if (Kn == K) break;
+          K = Kn;
         }
-        // columns 32-63 suppressed by the kept rows 0-31
-        const uint32_t contrib = ((keep_lo >> lane) & 1u) ? static_cast<uint32_t>(my_lo >> 32) : 0u;
-        rem = static_cast<uint32_t>(removed >> 32) | __reduce_or_sync(0xFFFFFFFFu, contrib);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) rows[i] = __shfl_sync(0xFFFFFFFFu, static_cast<uint32_t>(my_hi >> 32), i);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const bool k = !((rem >> i) & 1u) && room > 0;
-          if (k) { keep_hi |= 1u << i; rem |= rows[i]; --room; }
+        const int room = a.post_nms - kept;                      // quota: only the first `room` keeps count
+        if (__popcll(K) > room) {
+          const bool k0 = ((K >> lane) & 1ull) && __popcll(K & below0) < room;
+          const bool k1 = ((K >> (lane + 32)) & 1ull) && __popcll(K & below1) < room;
+          K = static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, k0)) | (static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, k1)) << 32);
         }
+        const uint32_t keep_lo = static_cast<uint32_t>(K), keep_hi = static_cast<uint32_t>(K >> 32);
         if (lane == 0) {
           const uint64_t keep = static_cast<uint64_t>(keep_lo) | (static_cast<uint64_t>(keep_hi) << 32);
           sh->keepmask = keep;
