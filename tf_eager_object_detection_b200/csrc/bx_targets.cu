@@ -429,6 +429,8 @@ struct PTArgs {
   float* out_out_w;
   int* out_keep;           // [batch,S]
   int* out_counts;         // [batch,2]
+  float* ws_best;          // [batch,k] row max of the roi x gt IoU matrix (pt_rowstats_kernel)
+  int* ws_arg;             // [batch,k] its first argmax
 };
 
 __device__ void bitonic_sort_asc(uint64_t* v, int pow2) {
@@ -444,6 +446,33 @@ __device__ void bitonic_sort_asc(uint64_t* v, int pow2) {
       }
       __syncthreads();
     }
+}
+
+// roi x gt IoU rows over the whole device (proposal_target.py:56-58): row max and first argmax per roi
+__global__ void __launch_bounds__(256) pt_rowstats_kernel(const PTArgs a) {
+  __shared__ float4 s_gt[kMaxGt];
+  __shared__ float s_area[kMaxGt];
+  const int img = blockIdx.y, tid = threadIdx.x;
+  const int m = a.gt_counts ? a.gt_counts[img] : a.max_gt;
+  const int k = a.roi_counts ? min(a.roi_counts[img], a.k) : a.k;
+  for (int j = tid; j < m; j += 256) {
+    const float4 g = a.gt[static_cast<size_t>(img) * a.max_gt + j];
+    s_gt[j] = g;
+    s_area[j] = bx_area_plus1(g);
+  }
+  __syncthreads();
+  const int i = blockIdx.x * 256 + tid;
+  if (i >= k) return;
+  const float4 r = a.rois[static_cast<size_t>(img) * a.k + i];
+  const float ar = bx_area_plus1(r);
+  float best = -1.0f;
+  int arg = 0;
+  for (int j = 0; j < m; ++j) {
+    const float v = at_iou(r, ar, s_gt[j], s_area[j]);
+    if (v > best) { best = v; arg = j; }
+  }
+  a.ws_best[static_cast<size_t>(img) * a.k + i] = best;
+  a.ws_arg[static_cast<size_t>(img) * a.k + i] = arg;
 }
 
 __global__ void __launch_bounds__(1024) proposal_target_kernel(const PTArgs a) {
@@ -477,15 +506,8 @@ __global__ void __launch_bounds__(1024) proposal_target_kernel(const PTArgs a) {
     const int i = i0 + tid;
     bool fg = false, bg = false;
     if (i < k) {
-      const float4 r = rois[i];
-      const float ar = bx_area_plus1(r);
-      float best = -1.0f;
-      int arg = 0;
-      for (int j = 0; j < m; ++j) {
-        const float v = bx_iou_plus1(r, ar, s_gt[j], s_area[j]);
-        if (v > best) { best = v; arg = j; }
-      }
-      s_assign[i] = static_cast<unsigned short>(arg);
+      const float best = a.ws_best[static_cast<size_t>(img) * a.k + i];
+      s_assign[i] = static_cast<unsigned short>(a.ws_arg[static_cast<size_t>(img) * a.k + i]);
       if (m > 0) {
         fg = best >= a.p.pos_iou_threshold;
         bg = (best < a.p.pos_iou_threshold) && (best >= a.p.neg_iou_threshold);
@@ -684,6 +706,13 @@ extern "C" int bx_proposal_target(bx_handle* h, const float* rois, const int* ro
   a.out_counts = out_counts;
   const size_t smem = sizeof(float4) * kMaxGt + 2 * sizeof(uint64_t) * kMaxRois + sizeof(float) * kMaxGt +
                       sizeof(unsigned short) * kMaxRois;
+  if (int rc = bx_ws_reserve(h, static_cast<size_t>(batch) * (k > 0 ? k : 1) * (sizeof(float) + sizeof(int)))) return rc;
+  a.ws_best = reinterpret_cast<float*>(h->ws);
+  a.ws_arg = reinterpret_cast<int*>(a.ws_best + static_cast<size_t>(batch) * k);
+  if (k > 0) {
+    pt_rowstats_kernel<<<dim3(bx_div_up(k, 256), batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    BX_LAUNCH_CHECK(h);
+  }
   BX_CUDA(cudaFuncSetAttribute(proposal_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   proposal_target_kernel<<<batch, 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
   BX_LAUNCH_CHECK(h);
