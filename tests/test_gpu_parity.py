@@ -475,11 +475,18 @@ def test_band_kernel_matches_direct_kernel_and_oracle(bx, monkeypatch, mode, poo
     m = {'stride': _lib.ROI_STRIDE_NORM, 'image': _lib.ROI_IMAGE_NORM, 'align': _lib.ROI_ALIGN_PAD}[mode]
     p = {'none': _lib.POOL_NONE, 'max': _lib.POOL_MAX2, 'avg': _lib.POOL_AVG2}[pool]
     kw = dict(stride=16.0, image_shape=(H, W), box_ind=None if bi is None else cu(bi))
-    monkeypatch.delenv('BX_ROI_DIRECT', raising=False)
+    for k in ('BX_ROI_DIRECT', 'BX_ROI_NO_POOL2'):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv('BX_ROI_BAND_POOLED', '1')                 # pooled crops default to the roi-stationary kernel
     band = bx.roi_pool(m, p, 7, cu(feat), cu(rois), **kw).cpu().numpy()
+    monkeypatch.delenv('BX_ROI_BAND_POOLED', raising=False)
+    default = bx.roi_pool(m, p, 7, cu(feat), cu(rois), **kw).cpu().numpy()       # band (plain) / roi_pool2 (pooled)
     monkeypatch.setenv('BX_ROI_DIRECT', '1')
-    direct = bx.roi_pool(m, p, 7, cu(feat), cu(rois), **kw).cpu().numpy()
+    monkeypatch.setenv('BX_ROI_NO_POOL2', '1')
+    direct = bx.roi_pool(m, p, 7, cu(feat), cu(rois), **kw).cpu().numpy()        # generic gather kernel
     monkeypatch.delenv('BX_ROI_DIRECT', raising=False)
+    monkeypatch.delenv('BX_ROI_NO_POOL2', raising=False)
+    assert np.array_equal(band, default)
     assert np.array_equal(band, direct)
     if mode == 'stride' and pool != 'avg':
         ref = orc.roi_pool_c4(feat, rois, 16, 7, pool == 'max', box_ind=bi)

@@ -411,7 +411,7 @@ int launch_roi_v(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
 
 // pooled fast kernel: float4-aligned maps whose channel-group count divides the CTA into whole-warp pixel lanes
 bool roi_pool2_ok(const RoiArgs& a, int pool) {
-  static const bool off = getenv("BX_ROI_NO_POOL2") != nullptr;               // A/B switch for profiles/micro
+  const bool off = getenv("BX_ROI_NO_POOL2") != nullptr;                      // A/B / test switch (read per call)
   if (off || pool == BX_POOL_NONE || (a.c & 3)) return false;
   const int cv = a.c >> 2;
   if (cv < 32 || cv > 256 || (256 % cv) != 0 || !bx_aligned(a.out, 16)) return false;
@@ -426,9 +426,14 @@ int launch_roi(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
   if (a.r == 0) return BX_OK;
   const bool prof = h->prof_on && h->prof_n < h->prof_cap;
   if (prof) BX_CUDA(cudaEventRecord(h->prof_ev[2 * h->prof_n], st));
-  int used = 0;
-  int rc = roi_band_launch(h, a, pool, st, &used);   // TMA band-stationary kernel when the shape allows it
-  if (rc) return rc;
+  int used = 0, rc = 0;
+  // pooled crops (2x2 max / avg): the roi-stationary kernel with tap reuse wins on every measured shape (VGG16
+  // 14x14+max C=512: 36 vs 76 us at B=1, 168 vs 225 us at B=8; profiles/micro/vgg_ab.py), plain crops go to the band kernel
+  const bool band_pooled = getenv("BX_ROI_BAND_POOLED") != nullptr;             // A/B / test switch (read per call)
+  if (pool == BX_POOL_NONE || band_pooled || !roi_pool2_ok(a, pool)) {
+    rc = roi_band_launch(h, a, pool, st, &used);     // TMA band-stationary kernel when the shape allows it
+    if (rc) return rc;
+  }
   if (!used && roi_pool2_ok(a, pool)) {
     if (pool == BX_POOL_MAX2) roi_pool2_kernel<BX_POOL_MAX2><<<a.r, 256, 0, st>>>(a, -0.0f);
     else roi_pool2_kernel<BX_POOL_AVG2><<<a.r, 256, 0, st>>>(a, -0.0f);
