@@ -259,6 +259,17 @@ int bx_c4_proposal_roi_host(bx_handle* h, const float* anchors_dev, const float*
                             float* out_rois_host, int* out_idx_host, int* out_count_host, float* out_feat_host,
                             void* stream);
 
+/* ---- e (multi-GPU): the path's only exchange — all-gather of the per-image detection records for evaluation, which
+ *      replaces the single-process accumulation loops of evaluation/pascal_eval_files_utils.py:73-107 and
+ *      scripts/eval_coco.py:116-164.  `nccl_comm` is the host framework's ncclComm_t (torch:
+ *      ProcessGroupNCCL._comm_ptr()); NCCL is not linked: ncclAllGather / ncclGroupStart / ncclGroupEnd are resolved
+ *      from the libnccl already loaded in the process (BX_ERR_UNSUPPORTED if there is none).  Every rank passes the same
+ *      b_local (pad uneven shards first).  records [b_local,kmax,fields] fp32 + counts [b_local] int32 ->
+ *      out_records [world*b_local,kmax,fields], out_counts [world*b_local] in rank order; one fused NCCL group on
+ *      `stream`. */
+int bx_allgather_detections(bx_handle* h, void* nccl_comm, const float* records, const int* counts, int b_local,
+                            int kmax, int fields, int world, float* out_records, int* out_counts, void* stream);
+
 /* number of kernels launched by this handle since creation (bench.py "gpu_launches") */
 long long bx_launch_count(const bx_handle* h);
 

@@ -849,3 +849,17 @@ def test_topset_prefilter_paths(bx):
     idx_g, cnt_g = bx.nms(cu(boxes)[None], cu(uniq)[None], 300, 0.7)
     ref = orc.nms_tf(boxes, uniq, 300, 0.7)
     assert int(cnt_g[0]) == ref.shape[0] and np.array_equal(idx_g[0, :ref.shape[0]].cpu().numpy(), ref)
+
+
+def test_native_allgather_on_two_ranks():
+    """bx_allgather_detections on torch's own ncclComm_t against torch.distributed collectives (uneven shards), two
+    processes on two GPUs; skipped on single-GPU boxes (the gloo tests cover the host logic)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_allgather_ranks.py')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29541', script], capture_output=True, text=True,
+                         timeout=240)
+    assert out.returncode == 0 and 'allgather ok' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

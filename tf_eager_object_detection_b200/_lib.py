@@ -66,6 +66,7 @@ SIGNATURES = {
                             c_int, c_int, P, c_void_p]),
     'bx_roi_pool_grad': (c_int, [c_void_p, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float,
                                  c_int, c_int, P, P, c_void_p]),
+    'bx_allgather_detections': (c_int, [c_void_p, c_void_p, P, P, c_int, c_int, c_int, c_int, P, P, c_void_p]),
     'bx_smooth_l1_loss': (c_int, [c_void_p, P, P, P, P, c_longlong, c_int, c_float, c_int, P, P, c_void_p]),
     'bx_cls_loss': (c_int, [c_void_p, P, P, c_int, c_int, c_float, P, P, P, c_void_p]),
     'bx_fpn_assign_levels': (c_int, [c_void_p, P, c_int, c_int, c_int, P, P, P, c_void_p]),

@@ -191,3 +191,53 @@ extern "C" int bx_c4_proposal_roi_host(bx_handle* h, const float* anchors_dev, c
   BX_CUDA(cudaMemcpyAsync(out_feat_host, d_out, sizeof(float) * k * pool_size * pool_size * c, cudaMemcpyDeviceToHost, st));
   return BX_OK;
 }
+
+// ---- multi-GPU exchange: detection records all-gather over the host framework's NCCL communicator
+#include <dlfcn.h>
+namespace {
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*nccl_group_fn)(void);
+typedef const char* (*nccl_errstr_fn)(int);
+struct NcclApi {
+  nccl_allgather_fn all_gather = nullptr;
+  nccl_group_fn group_start = nullptr, group_end = nullptr;
+  nccl_errstr_fn err = nullptr;
+  bool tried = false;
+};
+NcclApi g_nccl;
+
+// Only a libnccl that is ALREADY loaded is acceptable: the communicator was created by that copy.
+bool nccl_resolve() {
+  if (g_nccl.tried) return true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_NOLOAD);
+  void* src = lib ? lib : RTLD_DEFAULT;
+  g_nccl.all_gather = reinterpret_cast<nccl_allgather_fn>(dlsym(src, "ncclAllGather"));
+  g_nccl.group_start = reinterpret_cast<nccl_group_fn>(dlsym(src, "ncclGroupStart"));
+  g_nccl.group_end = reinterpret_cast<nccl_group_fn>(dlsym(src, "ncclGroupEnd"));
+  g_nccl.err = reinterpret_cast<nccl_errstr_fn>(dlsym(src, "ncclGetErrorString"));
+  g_nccl.tried = g_nccl.all_gather && g_nccl.group_start && g_nccl.group_end;   // a failure is retried next call
+  return g_nccl.tried;
+}
+}  // namespace
+
+extern "C" int bx_allgather_detections(bx_handle* h, void* nccl_comm, const float* records, const int* counts,
+                                       int b_local, int kmax, int fields, int world, float* out_records,
+                                       int* out_counts, void* stream) {
+  BX_REQUIRE(h && nccl_comm && out_records && out_counts, BX_ERR_INVALID, "bx_allgather_detections: NULL argument");
+  BX_REQUIRE(b_local >= 0 && kmax >= 0 && fields > 0 && world >= 1, BX_ERR_INVALID, "bx_allgather_detections: bad size");
+  BX_REQUIRE(b_local == 0 || (records && counts), BX_ERR_INVALID, "bx_allgather_detections: NULL input");
+  BX_REQUIRE(nccl_resolve(), BX_ERR_UNSUPPORTED,
+             "bx_allgather_detections: no NCCL library is loaded in this process (the communicator's own libnccl is required)");
+  if (b_local == 0) return BX_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int kFloat32 = 7, kInt32 = 2;                      // ncclDataType_t
+  int rc = g_nccl.group_start();
+  if (rc == 0) rc = g_nccl.all_gather(records, out_records, static_cast<size_t>(b_local) * kmax * fields, kFloat32, nccl_comm, st);
+  if (rc == 0) rc = g_nccl.all_gather(counts, out_counts, static_cast<size_t>(b_local), kInt32, nccl_comm, st);
+  const int rc_end = g_nccl.group_end();
+  if (rc == 0) rc = rc_end;
+  BX_REQUIRE(rc == 0, BX_ERR_CUDA, "bx_allgather_detections: NCCL error %d (%s)", rc, g_nccl.err ? g_nccl.err(rc) : "?");
+  h->launches++;
+  return BX_OK;
+}

@@ -30,6 +30,37 @@ def pack_detections(boxes, scores, labels):
                       labels.to(torch.float32).unsqueeze(-1)], dim=-1).contiguous()
 
 
+def nccl_comm_ptr(group=None):
+    """Raw ncclComm_t of the group's NCCL backend on the current CUDA device, or None (gloo / no NCCL / not initialised)."""
+    try:
+        pg = group if group is not None else dist.distributed_c10d._get_default_group()
+        backend = pg._get_backend(torch.device('cuda', torch.cuda.current_device()))
+        ptr = backend._comm_ptr()
+        return int(ptr) if ptr else None
+    except Exception:
+        return None
+
+
+def _allgather_native(records, counts, rec_all, cnt_all, world, group):
+    """bx_allgather_detections on the framework's own communicator: both tensors in one fused NCCL group on the current
+    stream.  Returns False when the group is not NCCL-backed (the gloo CPU tests), so the caller uses torch.distributed."""
+    if not (records.is_cuda and records.dtype == torch.float32 and counts.dtype == torch.int32 and records.dim() == 3):
+        return False
+    comm = nccl_comm_ptr(group)
+    if comm is None:
+        return False
+    import ctypes
+    from . import _lib
+    from ._tensor import stream_ptr
+    dev = records.device.index
+    st = stream_ptr(dev)
+    h = _lib.handle(dev, st.value)
+    b, k, f = records.shape
+    _lib.check(_lib.load().bx_allgather_detections(h, ctypes.c_void_p(comm), records.data_ptr(), counts.data_ptr(), b, k, f,
+                                                   world, rec_all.data_ptr(), cnt_all.data_ptr(), st))
+    return True
+
+
 def allgather_detections(records, counts, group=None, max_images_per_rank=None):
     """records [b_local, kmax, f] fp32 (zero padded), counts [b_local] int32 ->
     (records_all [b_total, kmax, f], counts_all [b_total]) in rank order, identical on every rank.
@@ -52,8 +83,9 @@ def allgather_detections(records, counts, group=None, max_images_per_rank=None):
     rec_all = torch.empty((world * max_images_per_rank,) + tuple(records.shape[1:]), dtype=records.dtype,
                           device=records.device)
     cnt_all = torch.empty((world * max_images_per_rank,), dtype=counts.dtype, device=counts.device)
-    dist.all_gather_into_tensor(rec_all, records.contiguous(), group=group)
-    dist.all_gather_into_tensor(cnt_all, counts.contiguous(), group=group)
+    if not _allgather_native(records.contiguous(), counts.contiguous(), rec_all, cnt_all, world, group):
+        dist.all_gather_into_tensor(rec_all, records.contiguous(), group=group)
+        dist.all_gather_into_tensor(cnt_all, counts.contiguous(), group=group)
     sizes = sizes.tolist()
     if all(s == max_images_per_rank for s in sizes):
         return rec_all, cnt_all
