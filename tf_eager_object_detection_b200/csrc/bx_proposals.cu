@@ -621,6 +621,7 @@ constexpr int kTopBins = 2048;
 constexpr int kTopThreads = 512;
 constexpr int kTopMaxSlices = 64;
 
+struct TopsetResult;
 struct TopsetArgs {
   const float* scores;     // [batch,n] or null
   const uint32_t* keys;    // [batch,n] or null (precomputed, 0 = excluded)
@@ -630,6 +631,8 @@ struct TopsetArgs {
   int* slice_count;        // [batch][kTopMaxSlices]
   int* info;               // [batch][4]: threshold (low 32 bits), m, n_valid_full, fallback flag
   int* t_hi;               // [batch]: 1 when the threshold is 2^32 (nothing taken)
+  int* ticket;             // [batch][3], zeroed: CTAs of an image that finished histogram level L
+  struct TopsetResult* state;  // [batch]: threshold search state after the last finished level
   uint32_t* out_keys;      // [batch][cap]
   int* out_src;            // [batch][cap]
 };
@@ -653,7 +656,7 @@ __device__ void suffix_find(const uint32_t* __restrict__ bins, int nb, int need,
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int bi = tid * 4 + j;
-    c[j] = (bi < nb) ? bins[bi] : 0u;
+    c[j] = (bi < nb) ? __ldcg(bins + bi) : 0u;               // written by other CTAs' atomics: read at L2
     mine += c[j];
   }
   uint32_t suf = mine;                                     // inclusive suffix over lanes (lane 31 first)
@@ -752,11 +755,11 @@ __global__ void __launch_bounds__(kTopThreads) topset_hist_kernel(const TopsetAr
   __shared__ TopsetResult s_r;
   const int img = blockIdx.y, tid = threadIdx.x;
   uint32_t* hist = a.hist + static_cast<size_t>(img) * 3 * kTopBins;
+  __shared__ int s_last;
   uint32_t prefix = 0;
-  if (LEVEL > 0) {
-    topset_resolve(hist, LEVEL - 1, a.m_lo, a.cap, &s_r, s_warp);
-    if (s_r.done) return;
-    prefix = s_r.prefix;
+  if (LEVEL > 0) {                                   // state left by the last CTA of the previous level
+    if (a.state[img].done) return;
+    prefix = a.state[img].prefix;
   }
   for (int i = tid; i < kTopBins; i += kTopThreads) s_hist[i] = 0u;
   __syncthreads();
@@ -780,16 +783,25 @@ __global__ void __launch_bounds__(kTopThreads) topset_hist_kernel(const TopsetAr
   __syncthreads();
   for (int i = tid; i < kTopBins; i += kTopThreads)
     if (s_hist[i]) atomicAdd(&hist[LEVEL * kTopBins + i], s_hist[i]);
+  // the image's last CTA to get here resolves the threshold search once for everybody downstream
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&a.ticket[img * 3 + LEVEL], 1) == static_cast<int>(gridDim.x) - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    topset_resolve(hist, LEVEL, a.m_lo, a.cap, &s_r, s_warp);
+    if (tid == 0) a.state[img] = s_r;
+  }
 }
 
 __global__ void __launch_bounds__(kTopThreads) topset_count_kernel(const TopsetArgs a) {
-  __shared__ uint32_t s_warp[kTopThreads / 32];
   __shared__ TopsetResult s_r;
   __shared__ int s_cnt;
   const int img = blockIdx.y, tid = threadIdx.x;
-  topset_resolve(a.hist + static_cast<size_t>(img) * 3 * kTopBins, 2, a.m_lo, a.cap, &s_r, s_warp);
+  if (tid == 0) { s_r = a.state[img]; s_cnt = 0; }     // final: level 2 always terminates the search
+  __syncthreads();
   const unsigned long long T = s_r.T;
-  if (tid == 0) s_cnt = 0;
   __syncthreads();
   const size_t base = static_cast<size_t>(img) * a.n;
   const int lo = blockIdx.x * a.slice_len, hi = min(a.n, lo + a.slice_len);
@@ -814,6 +826,8 @@ __global__ void __launch_bounds__(kTopThreads) topset_count_kernel(const TopsetA
 }
 
 __global__ void __launch_bounds__(kTopThreads) topset_write_kernel(const TopsetArgs a) {
+  // stable compaction of the slice: every warp owns a contiguous sub-chunk, counts its takes, and after one block-wide
+  // scan of the 16 warp counts writes them in order — no block barrier inside the element loops
   __shared__ int s_wcnt[kTopThreads / 32];
   const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long T = (static_cast<unsigned long long>(a.t_hi[img]) << 32) |
@@ -824,28 +838,44 @@ __global__ void __launch_bounds__(kTopThreads) topset_write_kernel(const TopsetA
   uint32_t* out_keys = a.out_keys + static_cast<size_t>(img) * a.cap;
   int* out_src = a.out_src + static_cast<size_t>(img) * a.cap;
   const int lo = blockIdx.x * a.slice_len, hi = min(a.n, lo + a.slice_len);
-  for (int i0 = lo; i0 < hi; i0 += kTopThreads) {
-    const int i = i0 + tid;
-    const uint32_t k = (i < hi) ? topset_key(a, base, i) : 0u;
-    const bool take = (k != 0u) && (static_cast<unsigned long long>(k) >= T);
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, take);
-    if (lane == 0) s_wcnt[warp] = __popc(m);
-    __syncthreads();
-    int before = 0, total = 0;
-    for (int w = 0; w < kTopThreads / 32; ++w) {
-      const int c = s_wcnt[w];
-      total += c;
-      if (w < warp) before += c;
+  constexpr int kWarps = kTopThreads / 32;
+  const int wlen = ((hi - lo + kWarps - 1) / kWarps + 31) & ~31;      // multiple of 32: whole-warp steps
+  const int wlo = min(hi, lo + warp * wlen), whi = min(hi, wlo + wlen);
+  int mine = 0;
+  for (int i0 = wlo; i0 < whi; i0 += 32 * 4) {
+    uint32_t k[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 32 + lane;
+      k[u] = (i < whi) ? topset_key(a, base, i) : 0u;
     }
-    if (take) {
-      const int o = pos + before + __popc(m & ((1u << lane) - 1u));
-      if (o < a.cap) {                                     // always true: count <= cap by construction
-        out_keys[o] = k;
-        out_src[o] = i;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) mine += (k[u] != 0u && static_cast<unsigned long long>(k[u]) >= T) ? 1 : 0;
+  }
+  mine = __reduce_add_sync(0xFFFFFFFFu, mine);
+  if (lane == 0) s_wcnt[warp] = mine;
+  __syncthreads();
+  for (int w = 0; w < warp; ++w) pos += s_wcnt[w];
+  for (int i0 = wlo; i0 < whi; i0 += 32 * 4) {
+    uint32_t k[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 32 + lane;
+      k[u] = (i < whi) ? topset_key(a, base, i) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool take = (k[u] != 0u) && (static_cast<unsigned long long>(k[u]) >= T);
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, take);
+      if (take) {
+        const int o = pos + __popc(m & ((1u << lane) - 1u));
+        if (o < a.cap) {                                   // always true: count <= cap by construction
+          out_keys[o] = k[u];
+          out_src[o] = i0 + u * 32 + lane;
+        }
       }
+      pos += __popc(m);
     }
-    pos += total;
-    __syncthreads();
   }
 }
 
@@ -901,8 +931,9 @@ static int launch_proposals_kernel(bx_handle* h, ProposalArgs& a, int batch, cud
 }
 
 size_t topset_ws_bytes(int batch, int cap) {
-  return static_cast<size_t>(batch) * (3 * kTopBins * sizeof(uint32_t) + kTopMaxSlices * sizeof(int) + 4 * sizeof(int) +
-                                       sizeof(int) + static_cast<size_t>(cap) * (sizeof(uint32_t) + sizeof(int))) + 256;
+  return static_cast<size_t>(batch) * (3 * kTopBins * sizeof(uint32_t) + 4 * sizeof(int) + kTopMaxSlices * sizeof(int) +
+                                       4 * sizeof(int) + sizeof(int) + sizeof(TopsetResult) +
+                                       static_cast<size_t>(cap) * (sizeof(uint32_t) + sizeof(int))) + 512;
 }
 
 // `ws` = workspace region of topset_ws_bytes(batch, cap) bytes reserved by the caller (16-byte aligned)
@@ -929,12 +960,14 @@ int launch_proposals(bx_handle* h, ProposalArgs& a, int batch, cudaStream_t st, 
   t.cap = cap;
   char* p = static_cast<char*>(ws);
   t.hist = reinterpret_cast<uint32_t*>(p);          p += static_cast<size_t>(batch) * 3 * kTopBins * sizeof(uint32_t);
+  t.ticket = reinterpret_cast<int*>(p);             p += static_cast<size_t>(batch) * 4 * sizeof(int);   // zeroed with hist
   t.slice_count = reinterpret_cast<int*>(p);        p += static_cast<size_t>(batch) * kTopMaxSlices * sizeof(int);
   t.info = reinterpret_cast<int*>(p);               p += static_cast<size_t>(batch) * 4 * sizeof(int);
   t.t_hi = reinterpret_cast<int*>(p);               p += ((static_cast<size_t>(batch) * sizeof(int) + 15) & ~size_t(15));
+  t.state = reinterpret_cast<TopsetResult*>(p);     p += ((static_cast<size_t>(batch) * sizeof(TopsetResult) + 15) & ~size_t(15));
   t.out_keys = reinterpret_cast<uint32_t*>(p);      p += static_cast<size_t>(batch) * cap * sizeof(uint32_t);
   t.out_src = reinterpret_cast<int*>(p);
-  BX_CUDA(cudaMemsetAsync(t.hist, 0, static_cast<size_t>(batch) * 3 * kTopBins * sizeof(uint32_t), st));
+  BX_CUDA(cudaMemsetAsync(t.hist, 0, static_cast<size_t>(batch) * (3 * kTopBins * sizeof(uint32_t) + 4 * sizeof(int)), st));
   const dim3 grid(t.slices, batch);
   topset_hist_kernel<0><<<grid, kTopThreads, 0, st>>>(t);
   BX_LAUNCH_CHECK(h);
