@@ -97,6 +97,15 @@ __device__ __forceinline__ float4 normalise(const float4 b) {
   return make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
 }
 
+// what a helper needs to know about a tile (32 bytes, pushed with two 16-byte remote stores)
+struct ClusterCmd {
+  int cmd;                // 1 = tile, 2 = done
+  int t0, tn;             // tile start / size in the leader's cand_box
+  int kept;               // kept count before this tile
+  int p_valid, p_kept;    // previous tile: valid flag, kept count before it
+  uint64_t p_keepmask;    // previous tile: keep mask
+};
+
 struct Shared {
   uint64_t lo, hi;        // current select range (inclusive)
   uint64_t prev;          // exclusive upper bound: composites already consumed are >= prev
@@ -108,14 +117,11 @@ struct Shared {
   int cand_count;
   int kept;
   int state;
-  // thread-block-cluster sweep (leader = cluster rank 0 publishes, helpers read over DSMEM)
-  int c_cmd;              // 1 = tile, 2 = done
-  int c_t0, c_tn;         // tile start / size in cand_box
-  int c_kept;             // kept count before this tile
-  int p_valid;            // previous tile's result below is valid
-  int p_kept;             // kept count before the previous tile
-  uint64_t p_keepmask;    // previous tile's keep mask
-  uint64_t sup_part[8];   // partial suppression masks written by the helpers
+  // thread-block-cluster sweep: the leader (cluster rank 0) pushes this block into every helper's copy of Shared
+  alignas(16) ClusterCmd cc;
+  int p_valid, p_kept;    // leader: result of the previous tile (copied into cc for the next one)
+  uint64_t p_keepmask;
+  uint64_t sup_part[8];   // partial suppression masks pushed by the helpers
 };
 
 // ---- cluster primitives (no-ops / rank 0 of 1 when the kernel is launched without a cluster dimension)
@@ -138,20 +144,8 @@ __device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem_ptr, uint3
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
   return ra;
 }
-__device__ __forceinline__ int dsmem_ld_s32(uint32_t addr) {
-  int v;
-  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint64_t dsmem_ld_u64(uint32_t addr) {
-  unsigned long long v;
-  asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 dsmem_ld_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
+__device__ __forceinline__ void dsmem_st_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void dsmem_st_u64(uint32_t addr, uint64_t v) {
   asm volatile("st.shared::cluster.u64 [%0], %1;" :: "r"(addr), "l"(static_cast<unsigned long long>(v)) : "memory");
@@ -166,38 +160,25 @@ __device__ __forceinline__ uint32_t load_key(const ProposalArgs& a, const uint32
 }
 
 // Helper CTA of a cluster (rank > 0): owns the kept boxes g with g % cs == rank and, for every tile the leader
-// announces, tests the tile's 64 candidates against them.  Two cluster barriers per tile: A = "tile published",
-// B = "partial masks delivered".
+// announces, tests the tile's 64 candidates against them.  Two cluster barriers per tile: A = "tile pushed" (the leader
+// has written the command block and the tile's boxes into this CTA's shared memory), B = "partial masks delivered".
 __device__ void nms_cluster_helper(const ProposalArgs& a, float4* tilebuf /* [2][kTile] */, float4* kept_box,
-                                   const Shared* leader_sh_local, const float4* leader_cand_local, uint32_t rank,
-                                   uint32_t cs) {
-  __shared__ int h_cmd, h_t0, h_tn, h_kept, h_pvalid, h_pkept;
-  __shared__ uint64_t h_pmask, h_sup;
+                                   Shared* sh, uint32_t rank, uint32_t cs) {
+  __shared__ uint64_t h_sup;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t lsh = dsmem_addr(leader_sh_local, 0);
-  const uint32_t lcand = dsmem_addr(leader_cand_local, 0);
+  const uint32_t lsup = dsmem_addr(&sh->sup_part[rank], 0);
   int cur = 0;
   for (;;) {
     cluster_sync_all();                                                   // A
-    if (tid == 0) {
-      h_cmd = dsmem_ld_s32(lsh + offsetof(Shared, c_cmd));
-      h_t0 = dsmem_ld_s32(lsh + offsetof(Shared, c_t0));
-      h_tn = dsmem_ld_s32(lsh + offsetof(Shared, c_tn));
-      h_kept = dsmem_ld_s32(lsh + offsetof(Shared, c_kept));
-      h_pvalid = dsmem_ld_s32(lsh + offsetof(Shared, p_valid));
-      h_pkept = dsmem_ld_s32(lsh + offsetof(Shared, p_kept));
-      h_pmask = dsmem_ld_u64(lsh + offsetof(Shared, p_keepmask));
-      h_sup = 0ull;
-    }
-    __syncthreads();
-    if (h_cmd != 1) {
-      cluster_sync_all();                                                 // B (the leader stays alive until here)
+    const ClusterCmd cc = sh->cc;
+    if (tid == 0) h_sup = 0ull;
+    if (cc.cmd != 1) {
+      cluster_sync_all();                                                 // B
       return;
     }
-    const int t0 = h_t0, tn = h_tn, kept = h_kept;
-    if (tid < tn) tilebuf[cur * kTile + tid] = dsmem_ld_f4(lcand + static_cast<uint32_t>(t0 + tid) * 16u);
-    if (h_pvalid && tid < kTile && ((h_pmask >> tid) & 1ull)) {            // adopt this CTA's share of the last keeps
-      const uint32_t g = static_cast<uint32_t>(h_pkept) + __popcll(h_pmask & ((1ull << tid) - 1ull));
+    const int tn = cc.tn, kept = cc.kept;
+    if (cc.p_valid && tid < kTile && ((cc.p_keepmask >> tid) & 1ull)) {    // adopt this CTA's share of the last keeps
+      const uint32_t g = static_cast<uint32_t>(cc.p_kept) + __popcll(cc.p_keepmask & ((1ull << tid) - 1ull));
       if (g % cs == rank) kept_box[g / cs] = normalise(tilebuf[(cur ^ 1) * kTile + tid]);
     }
     __syncthreads();
@@ -213,7 +194,7 @@ __device__ void nms_cluster_helper(const ProposalArgs& a, float4* tilebuf /* [2]
     if (lane == 0 && m) atomicOr(reinterpret_cast<unsigned long long*>(&h_sup),
                                  static_cast<unsigned long long>(m) << ((warp & 1) * 32));
     __syncthreads();
-    if (tid == 0) dsmem_st_u64(lsh + offsetof(Shared, sup_part) + rank * 8u, h_sup);
+    if (tid == 0) dsmem_st_u64(lsup, h_sup);
     cluster_sync_all();                                                   // B
     cur ^= 1;
   }
@@ -230,7 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   uint32_t* hist = reinterpret_cast<uint32_t*>(rowmask + kTile);                    // kBins
   uint32_t* red = hist + kBins;                                                     // 64 (block reductions)
   Shared* sh = reinterpret_cast<Shared*>(red + 64);
-  uint32_t* skeys = reinterpret_cast<uint32_t*>(sh + 1);                            // n (when cached)
+  uint16_t* kept_ci = reinterpret_cast<uint16_t*>(sh + 1);                          // kMaxPost: chunk position of each keep
+  uint32_t* skeys = reinterpret_cast<uint32_t*>(kept_ci + kMaxPost);                // n (when cached)
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -239,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   const int img = blockIdx.x / cs;
   if (a.run_flag && a.run_flag[img * 4] == 0) return;           // fallback launch: nothing to redo for this image
   if (crank != 0) {
-    nms_cluster_helper(a, cand_box, kept_box, sh, cand_box, crank, cs);
+    nms_cluster_helper(a, cand_box, kept_box, sh, crank, cs);
     return;
   }
   if (cs > 1 && tid == 0) sh->p_valid = 0;
@@ -310,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   const int limit = (a.pre_nms_top_k > 0) ? min(a.pre_nms_top_k, n_valid) : n_valid;
   const uint64_t global_lo = static_cast<uint64_t>(sh->kmin) << 32;
   int consumed = 0;
+  int tile_seq = 0;                        // tiles announced to the helpers so far (double-buffer parity)
 
   // first round: a chunk about 1.5x the quota (NMS usually fills it from there); later rounds take full chunks
   int round_cap = 512;
@@ -474,21 +457,44 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
     __syncthreads();
 
     // ---- greedy sweep in tiles of 64
+    const int chunk_kept0 = sh->kept;
     for (int t0 = 0; t0 < cnt && sh->kept < a.post_nms; t0 += kTile) {
       const int tn = min(kTile, cnt - t0);
       const int kept = sh->kept;
       if (tid == 0) {
         sh->sup = 0ull;
-        if (cs > 1) {                        // publish the tile (the previous tile's keeps ride along in p_*)
-          sh->c_cmd = 1;
-          sh->c_t0 = t0;
-          sh->c_tn = tn;
-          sh->c_kept = kept;
+        if (cs > 1) {                        // the tile's command block (the previous tile's keeps ride along)
+          sh->cc.cmd = 1;
+          sh->cc.t0 = t0;
+          sh->cc.tn = tn;
+          sh->cc.kept = kept;
+          sh->cc.p_valid = sh->p_valid;
+          sh->cc.p_kept = sh->p_kept;
+          sh->cc.p_keepmask = sh->p_keepmask;
         }
       }
       if (cs > 1 && tid < 8) sh->sup_part[tid] = 0ull;
       __syncthreads();
-      if (cs > 1) cluster_sync_all();        // A: helpers start on this tile
+      if (cs > 1) {
+        // push the tile's boxes and the command block into every helper's shared memory, then barrier A
+        const int n_push = kTile * (static_cast<int>(cs) - 1);
+        if (tid < n_push) {
+          const uint32_t helper = 1u + static_cast<uint32_t>(tid) / kTile;
+          const int c = tid % kTile;
+          if (c < tn) {
+            const float4 b = cand_box[t0 + c];
+            dsmem_st_v4(dsmem_addr(&cand_box[(tile_seq & 1) * kTile + c], helper),
+                        make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
+          }
+        } else if (tid >= 512 && tid < 512 + 2 * (static_cast<int>(cs) - 1)) {
+          const int e = tid - 512;
+          const uint32_t helper = 1u + static_cast<uint32_t>(e >> 1);
+          const uint4* src = reinterpret_cast<const uint4*>(&sh->cc) + (e & 1);
+          dsmem_st_v4(dsmem_addr(reinterpret_cast<const uint4*>(&sh->cc) + (e & 1), helper), *src);
+        }
+        cluster_sync_all();                  // A: helpers start on this tile
+        ++tile_seq;
+      }
       // kept boxes are dealt round-robin over the cluster: this CTA holds g = 0, cs, 2cs, ... at kept_box[g / cs]
       const int kl = (cs > 1) ? (kept + static_cast<int>(cs) - 1) / static_cast<int>(cs) : kept;
       {
@@ -572,13 +578,19 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
           const float4 b = cand_box[t0 + tid];
           if (cs == 1) kept_box[pos] = normalise(b);
           else if (pos % cs == 0) kept_box[pos / cs] = normalise(b);
-          const int p = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(cand_key[t0 + tid] & 0xFFFFFFFFull));
-          out_idx[pos] = src_idx ? src_idx[p] : p;
-          if (out_boxes) out_boxes[pos] = b;
+          kept_ci[pos] = static_cast<uint16_t>(t0 + tid);        // outputs are written once per chunk, below
         }
       }
       __syncthreads();
     }
+    // ---- this chunk's keeps -> global (kept off the per-tile critical path: src_idx is a dependent global load)
+    for (int pos = chunk_kept0 + tid; pos < sh->kept; pos += kThreads) {
+      const int ci = kept_ci[pos];
+      const int p = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(cand_key[ci] & 0xFFFFFFFFull));
+      out_idx[pos] = src_idx ? src_idx[p] : p;
+      if (out_boxes) out_boxes[pos] = cand_box[ci];
+    }
+    __syncthreads();
 
     consumed += cnt;
     if (tid == 0) sh->prev = T;
@@ -586,8 +598,13 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   }
 
   if (cs > 1) {                              // release the helpers; stay until they have read the command
-    if (tid == 0) sh->c_cmd = 2;
+    if (tid == 0) sh->cc.cmd = 2;
     __syncthreads();
+    if (tid >= 512 && tid < 512 + 2 * (static_cast<int>(cs) - 1)) {
+      const int e = tid - 512;
+      dsmem_st_v4(dsmem_addr(reinterpret_cast<const uint4*>(&sh->cc) + (e & 1), 1u + static_cast<uint32_t>(e >> 1)),
+                  *(reinterpret_cast<const uint4*>(&sh->cc) + (e & 1)));
+    }
     cluster_sync_all();
     cluster_sync_all();
   }
@@ -881,7 +898,7 @@ __global__ void __launch_bounds__(kTopThreads) topset_write_kernel(const TopsetA
 
 size_t proposals_smem_bytes(int n, bool cache) {
   size_t b = sizeof(float4) * (kChunk + kMaxPost) + sizeof(uint64_t) * (kChunk + kTile) +
-             sizeof(uint32_t) * (kBins + 64) + sizeof(Shared);
+             sizeof(uint32_t) * (kBins + 64) + sizeof(Shared) + sizeof(uint16_t) * kMaxPost;
   if (cache) b += sizeof(uint32_t) * static_cast<size_t>(n);
   return (b + 15) & ~static_cast<size_t>(15);
 }
