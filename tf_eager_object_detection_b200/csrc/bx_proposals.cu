@@ -122,6 +122,8 @@ struct Shared {
   int p_valid, p_kept;    // leader: result of the previous tile (copied into cc for the next one)
   uint64_t p_keepmask;
   uint64_t sup_part[8];   // partial suppression masks pushed by the helpers
+  uint64_t mb_tile;       // helpers: "tile pushed" (1 arrival per tile, from the leader)
+  uint64_t mb_part;       // leader: "partial masks delivered" (cs - 1 arrivals per tile)
 };
 
 // ---- cluster primitives (no-ops / rank 0 of 1 when the kernel is launched without a cluster dimension)
@@ -147,6 +149,30 @@ __device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem_ptr, uint3
 __device__ __forceinline__ void dsmem_st_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// mbarrier signalling across the cluster: one thread arrives (release at cluster scope) on a barrier that lives in
+// another CTA's shared memory; the waiters acquire at cluster scope, so the remote stores issued before the arrive
+// (ordered behind a __syncthreads when other threads made them) are visible after the wait.
+__device__ __forceinline__ void cmbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void cmbar_arrive_remote(uint64_t* local_bar, uint32_t rank) {
+  const uint32_t ra = dsmem_addr(local_bar, rank);
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(ra) : "memory");
+}
+__device__ __forceinline__ void cmbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "CM_WAIT:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra CM_DONE;\n"
+      "bra CM_WAIT;\n"
+      "CM_DONE:\n"
+      "}\n" :: "r"(a), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void dsmem_st_u64(uint32_t addr, uint64_t v) {
   asm volatile("st.shared::cluster.u64 [%0], %1;" :: "r"(addr), "l"(static_cast<unsigned long long>(v)) : "memory");
 }
@@ -160,8 +186,9 @@ __device__ __forceinline__ uint32_t load_key(const ProposalArgs& a, const uint32
 }
 
 // Helper CTA of a cluster (rank > 0): owns the kept boxes g with g % cs == rank and, for every tile the leader
-// announces, tests the tile's 64 candidates against them.  Two cluster barriers per tile: A = "tile pushed" (the leader
-// has written the command block and the tile's boxes into this CTA's shared memory), B = "partial masks delivered".
+// announces, tests the tile's 64 candidates against them.  Two mbarrier signals per tile instead of whole-cluster
+// barriers: A = "tile pushed" (the leader has written the command block and the tile's boxes into this CTA's shared
+// memory and arrives on this CTA's mb_tile), B = "partial mask delivered" (this CTA arrives on the leader's mb_part).
 __device__ void nms_cluster_helper(const ProposalArgs& a, float4* tilebuf /* [2][kTile] */, float4* kept_box,
                                    Shared* sh, uint32_t rank, uint32_t cs) {
   __shared__ uint64_t h_sup;
@@ -169,13 +196,10 @@ __device__ void nms_cluster_helper(const ProposalArgs& a, float4* tilebuf /* [2]
   const uint32_t lsup = dsmem_addr(&sh->sup_part[rank], 0);
   int cur = 0;
   for (;;) {
-    cluster_sync_all();                                                   // A
+    cmbar_wait(&sh->mb_tile, static_cast<uint32_t>(cur));                  // A: the leader pushed a tile (or "done")
     const ClusterCmd cc = sh->cc;
     if (tid == 0) h_sup = 0ull;
-    if (cc.cmd != 1) {
-      cluster_sync_all();                                                 // B
-      return;
-    }
+    if (cc.cmd != 1) return;
     const int tn = cc.tn, kept = cc.kept;
     if (cc.p_valid && tid < kTile && ((cc.p_keepmask >> tid) & 1ull)) {    // adopt this CTA's share of the last keeps
       const uint32_t g = static_cast<uint32_t>(cc.p_kept) + __popcll(cc.p_keepmask & ((1ull << tid) - 1ull));
@@ -194,8 +218,10 @@ __device__ void nms_cluster_helper(const ProposalArgs& a, float4* tilebuf /* [2]
     if (lane == 0 && m) atomicOr(reinterpret_cast<unsigned long long*>(&h_sup),
                                  static_cast<unsigned long long>(m) << ((warp & 1) * 32));
     __syncthreads();
-    if (tid == 0) dsmem_st_u64(lsup, h_sup);
-    cluster_sync_all();                                                   // B
+    if (tid == 0) {
+      dsmem_st_u64(lsup, h_sup);
+      cmbar_arrive_remote(&sh->mb_part, 0);                                // B: this helper's partial mask is in
+    }
     cur ^= 1;
   }
 }
@@ -220,11 +246,19 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   const uint32_t cs = cluster_size(), crank = cluster_rank();   // 1, 0 unless launched with a cluster dimension
   const int img = blockIdx.x / cs;
   if (a.run_flag && a.run_flag[img * 4] == 0) return;           // fallback launch: nothing to redo for this image
+  if (cs > 1) {
+    if (tid == 0) {
+      cmbar_init(&sh->mb_tile, 1);
+      cmbar_init(&sh->mb_part, cs - 1);
+      sh->p_valid = 0;
+    }
+    __syncthreads();
+    cluster_sync_all();                      // every CTA's barriers exist before anybody signals
+  }
   if (crank != 0) {
     nms_cluster_helper(a, cand_box, kept_box, sh, crank, cs);
     return;
   }
-  if (cs > 1 && tid == 0) sh->p_valid = 0;
   const int n = a.topset_info ? min(a.topset_info[img * 4 + 1], a.n) : a.n;
   const size_t full = a.src_idx ? static_cast<size_t>(a.src_stride) : static_cast<size_t>(a.n);
   const float* scores = a.scores ? a.scores + static_cast<size_t>(img) * a.n : nullptr;
@@ -492,7 +526,8 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
           const uint4* src = reinterpret_cast<const uint4*>(&sh->cc) + (e & 1);
           dsmem_st_v4(dsmem_addr(reinterpret_cast<const uint4*>(&sh->cc) + (e & 1), helper), *src);
         }
-        cluster_sync_all();                  // A: helpers start on this tile
+        __syncthreads();                     // every push is issued before the signal
+        if (tid < static_cast<int>(cs) - 1) cmbar_arrive_remote(&sh->mb_tile, 1u + static_cast<uint32_t>(tid));   // A
         ++tile_seq;
       }
       // kept boxes are dealt round-robin over the cluster: this CTA holds g = 0, cs, 2cs, ... at kept_box[g / cs]
@@ -529,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         if (part == 0) rowmask[i] = bits;
       }
       __syncthreads();
-      if (cs > 1) cluster_sync_all();        // B: the helpers' partial masks have landed in sup_part
+      if (cs > 1) cmbar_wait(&sh->mb_part, static_cast<uint32_t>((tile_seq - 1) & 1));   // B: all partial masks are in
       if (warp == 0) {
         // greedy resolve of the tile by warp 0 as a fixed point: candidate i is kept iff it is alive and no KEPT earlier
         // candidate suppresses it.  Iterating K <- {i alive : full[i] & below(i) & K == 0} from K = alive fixes
@@ -605,8 +640,8 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
       dsmem_st_v4(dsmem_addr(reinterpret_cast<const uint4*>(&sh->cc) + (e & 1), 1u + static_cast<uint32_t>(e >> 1)),
                   *(reinterpret_cast<const uint4*>(&sh->cc) + (e & 1)));
     }
-    cluster_sync_all();
-    cluster_sync_all();
+    __syncthreads();
+    if (tid < static_cast<int>(cs) - 1) cmbar_arrive_remote(&sh->mb_tile, 1u + static_cast<uint32_t>(tid));
   }
   // ---- pad the tail, publish the count
   const int kept = sh->kept;
