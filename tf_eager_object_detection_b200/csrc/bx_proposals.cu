@@ -18,6 +18,7 @@ constexpr int kChunk = 2048;        // candidates sorted + swept per round
 constexpr int kBins = 2048;         // histogram bins per select level
 constexpr int kMaxPost = 2048;      // kept-box list capacity (post_nms limit)
 constexpr int kTile = 64;           // NMS tile: one 64-bit mask word
+constexpr int kPairs = kTile * (kTile - 1) / 2;   // unordered candidate pairs of a tile
 constexpr int kUnroll = 8;          // independent key loads in flight per thread in the streaming passes
 constexpr int kKeyCacheMax = 24576; // keys cached in smem when n <= this (C4 600x1000: 21 546)
 
@@ -238,7 +239,10 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   uint32_t* red = hist + kBins;                                                     // 64 (block reductions)
   Shared* sh = reinterpret_cast<Shared*>(red + 64);
   uint16_t* kept_ci = reinterpret_cast<uint16_t*>(sh + 1);                          // kMaxPost: chunk position of each keep
-  uint32_t* skeys = reinterpret_cast<uint32_t*>(kept_ci + kMaxPost);                // n (when cached)
+  float4* tile_nb = reinterpret_cast<float4*>(kept_ci + kMaxPost);                  // kTile: normalised tile boxes
+  float* tile_area = reinterpret_cast<float*>(tile_nb + kTile);                     // kTile
+  uint16_t* pair_tab = reinterpret_cast<uint16_t*>(tile_area + kTile);              // kTile*(kTile-1)/2: (i | j << 8), i < j
+  uint32_t* skeys = reinterpret_cast<uint32_t*>(pair_tab + kPairs);                 // n (when cached)
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -258,6 +262,10 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   if (crank != 0) {
     nms_cluster_helper(a, cand_box, kept_box, sh, crank, cs);
     return;
+  }
+  if (tid < kTile - 1) {                      // row tid of the upper triangle: pairs (tid, tid+1 .. 63)
+    int o = tid * (2 * kTile - 1 - tid) / 2;
+    for (int j = tid + 1; j < kTile; ++j) pair_tab[o++] = static_cast<uint16_t>(tid | (j << 8));
   }
   const int n = a.topset_info ? min(a.topset_info[img * 4 + 1], a.n) : a.n;
   const size_t full = a.src_idx ? static_cast<size_t>(a.src_stride) : static_cast<size_t>(a.n);
@@ -508,6 +516,13 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         }
       }
       if (cs > 1 && tid < 8) sh->sup_part[tid] = 0ull;
+      if (tid >= 64 && tid < 64 + kTile) {   // normalised corners + area of the tile's candidates, masks cleared
+        const int c = tid - 64;
+        const float4 nb = normalise(cand_box[t0 + min(c, tn - 1)]);
+        tile_nb[c] = nb;
+        tile_area[c] = (nb.z - nb.x) * (nb.w - nb.y);
+        rowmask[c] = 0ull;
+      }
       __syncthreads();
       if (cs > 1) {
         // push the tile's boxes and the command block into every helper's shared memory, then barrier A
@@ -537,31 +552,26 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         const int c = tid & 63;
         bool s = false;
         if (c < tn) {
-          const float4 cb = normalise(cand_box[t0 + c]);
-          const float ca = (cb.z - cb.x) * (cb.w - cb.y);
+          const float4 cb = tile_nb[c];
+          const float ca = tile_area[c];
           for (int j = tid >> 6; j < kl && !s; j += 16) s = iou_gt(cb, ca, kept_box[j], a.thr);
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, s);
         if (lane == 0 && m) atomicOr(reinterpret_cast<unsigned long long*>(&sh->sup),
                                      static_cast<unsigned long long>(m) << ((warp & 1) * 32));
-        // (2) intra-tile masks: row i = tid>>4, columns part*4 .. part*4+3 ; bit j set iff j != i and IoU(i,j) > thr
-        //     (the test is symmetric bit for bit, so the bits below i are "the earlier candidates that suppress i")
-        const int i = tid >> 4, part = tid & 15;
-        uint64_t bits = 0ull;
-        if (i < tn) {
-          const float4 ib = normalise(cand_box[t0 + i]);
-          const float ia = (ib.z - ib.x) * (ib.w - ib.y);
+        // (2) intra-tile masks: every unordered pair (i < j) once — the test is symmetric bit for bit, so a hit sets
+        //     bit j of row i and bit i of row j (the bits below i are "the earlier candidates that suppress i")
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int j = part * 4 + q;
-            if (j != i && j < tn) {
-              if (iou_gt(ib, ia, normalise(cand_box[t0 + j]), a.thr)) bits |= (1ull << j);
+        for (int q = 0; q < 2; ++q) {
+          const int p = tid + q * kThreads;
+          if (p < kPairs) {
+            const int e = pair_tab[p], i = e & 0xFF, j = e >> 8;
+            if (j < tn && iou_gt(tile_nb[i], tile_area[i], tile_nb[j], a.thr)) {
+              atomicOr(reinterpret_cast<unsigned long long*>(&rowmask[i]), 1ull << j);
+              atomicOr(reinterpret_cast<unsigned long long*>(&rowmask[j]), 1ull << i);
             }
           }
         }
-#pragma unroll
-        for (int d = 1; d < 16; d <<= 1) bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, d);
-        if (part == 0) rowmask[i] = bits;
       }
       __syncthreads();
       if (cs > 1) cmbar_wait(&sh->mb_part, static_cast<uint32_t>((tile_seq - 1) & 1));   // B: all partial masks are in
@@ -933,7 +943,8 @@ __global__ void __launch_bounds__(kTopThreads) topset_write_kernel(const TopsetA
 
 size_t proposals_smem_bytes(int n, bool cache) {
   size_t b = sizeof(float4) * (kChunk + kMaxPost) + sizeof(uint64_t) * (kChunk + kTile) +
-             sizeof(uint32_t) * (kBins + 64) + sizeof(Shared) + sizeof(uint16_t) * kMaxPost;
+             sizeof(uint32_t) * (kBins + 64) + sizeof(Shared) + sizeof(uint16_t) * kMaxPost +
+             sizeof(float4) * kTile + sizeof(float) * kTile + sizeof(uint16_t) * kPairs;
   if (cache) b += sizeof(uint32_t) * static_cast<size_t>(n);
   return (b + 15) & ~static_cast<size_t>(15);
 }
