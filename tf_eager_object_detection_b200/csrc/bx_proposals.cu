@@ -16,6 +16,7 @@ namespace {
 constexpr int kThreads = 1024;
 constexpr int kChunk = 2048;        // candidates sorted + swept per round
 constexpr int kBins = 2048;         // histogram bins per select level
+static_assert(kBins == 2 * kThreads, "the select scan gives every thread two bins");
 constexpr int kMaxPost = 2048;      // kept-box list capacity (post_nms limit)
 constexpr int kTile = 64;           // NMS tile: one 64-bit mask word
 constexpr int kPairs = kTile * (kTile - 1) / 2;   // unordered candidate pairs of a tile
@@ -373,61 +374,44 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         }
       }
       __syncthreads();
-      // suffix scan from the top bin: largest suffix whose count <= want
-      if (warp == 0) {
-        // each lane owns kBins/32 consecutive bins, highest lane = highest bins
-        constexpr int per = kBins / 32;
-        uint32_t mine = 0;
-        for (int j = 0; j < per; ++j) mine += hist[lane * per + j];
-        // inclusive suffix sum over lanes (lane 31 first)
-        uint32_t suf = mine;
+      // suffix scan from the top bin: largest suffix whose count <= want.  Block-wide: thread t owns bins 2t, 2t+1
+      // (kBins == 2 * kThreads); warp suffix by shuffles, warp totals through `red`.
+      {
+        const uint32_t c0 = hist[2 * tid], c1 = hist[2 * tid + 1];
+        const uint32_t mine = c0 + c1;
+        uint32_t suf = mine;                                  // inclusive suffix over the lanes of the warp
+#pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           const uint32_t o = __shfl_down_sync(0xFFFFFFFFu, suf, d);
           if (lane + d < 32) suf += o;
         }
-        const uint32_t higher = suf - mine;  // count in lanes above
-        // walk own bins from the top
-        int over_bin = -1;        // first (highest) bin where the running count exceeds want
-        uint32_t run = higher;
-        if (run <= static_cast<uint32_t>(want)) {
-          for (int j = per - 1; j >= 0; --j) {
-            const uint32_t c = hist[lane * per + j];
-            if (run + c <= static_cast<uint32_t>(want)) {
-              run += c;
-            } else {
-              over_bin = lane * per + j;
-              break;
-            }
-          }
-        }
-        // the crossing happens in exactly one lane: the highest lane with over_bin >= 0 ... or nowhere (all fit)
-        const uint32_t has_over = __ballot_sync(0xFFFFFFFFu, over_bin >= 0);
-        if (has_over == 0u) {
-          // everything in [lo,hi] fits
-          if (lane == 0) {
-            sh->thresh = lo;
+        if (lane == 0) red[warp] = suf;                       // warp totals
+        __syncthreads();
+        uint32_t above_warp = 0;
+        for (int w = warp + 1; w < kThreads / 32; ++w) above_warp += red[w];
+        const uint32_t higher = above_warp + suf - mine;      // count in the bins above this thread's two
+        const uint32_t w32 = static_cast<uint32_t>(want);
+        if (higher <= w32 && higher + mine > w32) {           // the crossing is here (exactly one thread, if any)
+          int ob;
+          uint32_t cnt_above;
+          if (higher + c1 > w32) { ob = 2 * tid + 1; cnt_above = higher; }
+          else { ob = 2 * tid; cnt_above = higher + c1; }
+          if (cnt_above > 0) {
+            // a non-empty suffix fits: T = lower edge of bin ob+1
+            sh->thresh = lo + (static_cast<uint64_t>(ob + 1) << shift);
             sh->state = 1;
+          } else {
+            // the top non-empty bin alone holds more than `want`: refine inside it
+            const uint64_t nlo = lo + (static_cast<uint64_t>(ob) << shift);
+            uint64_t nhi = nlo + ((1ull << shift) - 1ull);
+            if (nhi > hi) nhi = hi;
+            sh->lo = nlo;
+            sh->hi = nhi;
+            sh->state = 0;
           }
-        } else {
-          const int src = 31 - __clz(has_over);
-          const int ob = __shfl_sync(0xFFFFFFFFu, over_bin, src);
-          // count of the suffix strictly above bin `ob`: take it from the crossing lane's walk
-          uint32_t cnt_above = __shfl_sync(0xFFFFFFFFu, run, src);
-          if (lane == 0) {
-            if (cnt_above > 0) {
-              // a non-empty suffix fits: T = lower edge of bin ob+1
-              sh->thresh = lo + (static_cast<uint64_t>(ob + 1) << shift);
-              sh->state = 1;
-            } else {
-              // the top non-empty bin alone holds more than `want`: refine inside it
-              const uint64_t nlo = lo + (static_cast<uint64_t>(ob) << shift);
-              uint64_t nhi = nlo + ((1ull << shift) - 1ull);
-              if (nhi > hi) nhi = hi;
-              sh->lo = nlo;
-              sh->hi = nhi;
-              sh->state = 0;
-            }
-          }
+        } else if (tid == 0 && higher + mine <= w32) {        // everything in [lo,hi] fits
+          sh->thresh = lo;
+          sh->state = 1;
         }
       }
       __syncthreads();
