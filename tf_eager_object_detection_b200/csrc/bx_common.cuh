@@ -134,4 +134,56 @@ __device__ __forceinline__ uint32_t bx_score_key(float s) {
   const uint32_t k = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
   return k == 0u ? 1u : k;
 }
+// Bitonic sort of v[0..pow2) in shared memory by the whole CTA (pow2 a power of two >= 64, blockDim.x a multiple of 32).
+// Each thread keeps two adjacent elements in registers: compare-exchange distance 1 is inside the thread, 2..32 by
+// shuffles inside the warp, so only the distances >= 64 go through shared memory with a CTA barrier (21 barriers for
+// 2048 elements instead of 66).  kDesc: descending, else ascending.
+template <bool kDesc>
+__device__ __forceinline__ void bx_bitonic_reg_steps(unsigned long long& e0, unsigned long long& e1, int k, int jstart, int i0) {
+  const bool first_big = kDesc ? ((i0 & k) == 0) : ((i0 & k) != 0);   // same for i0 and i0 + 1 (k >= 2)
+  for (int j = jstart; j >= 2; j >>= 1) {
+    const unsigned long long p0 = __shfl_xor_sync(0xFFFFFFFFu, e0, j >> 1), p1 = __shfl_xor_sync(0xFFFFFFFFu, e1, j >> 1);
+    const bool take_max = (first_big == ((i0 & j) == 0));            // the lower index of a "big first" pair keeps the larger
+    e0 = take_max ? max(e0, p0) : min(e0, p0);
+    e1 = take_max ? max(e1, p1) : min(e1, p1);
+  }
+  const unsigned long long hi = max(e0, e1), lo = min(e0, e1);
+  e0 = first_big ? hi : lo;
+  e1 = first_big ? lo : hi;
+}
+
+template <bool kDesc>
+__device__ void bx_bitonic_sort(unsigned long long* v, int pow2) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i0 = 2 * tid; i0 < pow2; i0 += 2 * nt) {                   // whole warps: pow2 is a multiple of 64
+    unsigned long long e0 = v[i0], e1 = v[i0 + 1];
+    for (int k = 2; k <= 64; k <<= 1) bx_bitonic_reg_steps<kDesc>(e0, e1, k, k >> 1, i0);
+    v[i0] = e0;
+    v[i0 + 1] = e1;
+  }
+  __syncthreads();
+  for (int k = 128; k <= pow2; k <<= 1) {
+    for (int j = k >> 1; j >= 64; j >>= 1) {
+      for (int t = tid; t < (pow2 >> 1); t += nt) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));          // index with bit j clear
+        const int p = i | j;
+        const unsigned long long x = v[i], y = v[p];
+        const bool first_big = kDesc ? ((i & k) == 0) : ((i & k) != 0);
+        if ((x < y) == first_big) {
+          v[i] = y;
+          v[p] = x;
+        }
+      }
+      __syncthreads();
+    }
+    for (int i0 = 2 * tid; i0 < pow2; i0 += 2 * nt) {
+      unsigned long long e0 = v[i0], e1 = v[i0 + 1];
+      bx_bitonic_reg_steps<kDesc>(e0, e1, k, 32, i0);
+      v[i0] = e0;
+      v[i0 + 1] = e1;
+    }
+    __syncthreads();
+  }
+}
 #endif
+

@@ -77,16 +77,7 @@ __global__ void __launch_bounds__(1024) prediction_topk_kernel(const TopkArgs a)
   mine = __reduce_add_sync(0xFFFFFFFFu, mine);
   if ((tid & 31) == 0 && mine) atomicAdd(&s_total, mine);
   __syncthreads();
-  for (int k = 2; k <= pow2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (pow2 >> 1); t += 1024) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int p = i | j;
-        const unsigned long long x = comp[i], y = comp[p];
-        if ((x < y) == ((i & k) == 0)) { comp[i] = y; comp[p] = x; }
-      }
-      __syncthreads();
-    }
+  bx_bitonic_sort<true>(comp, pow2);
   const int keep = min(s_total, a.max_per_image);
   float* det = a.out_det + static_cast<size_t>(b) * a.max_per_image * 6;
   for (int t = tid; t < a.max_per_image; t += 1024) {

@@ -99,60 +99,6 @@ __device__ __forceinline__ float4 normalise(const float4 b) {
   return make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
 }
 
-// Bitonic sort of v[0..pow2) (pow2 a power of two in [64, 2 * kThreads]), descending, by the whole CTA.  Thread t keeps
-// elements 2t and 2t+1 in registers: every compare-exchange distance below 64 stays inside a warp (distance 1 inside the
-// thread, 2..32 by shuffles), so only the distances >= 64 go through shared memory with a CTA barrier — 21 barriers for
-// 2048 elements instead of 66.
-__device__ __forceinline__ void bitonic_reg_steps(uint64_t& e0, uint64_t& e1, int k, int jstart, int tid) {
-  const int i0 = 2 * tid;
-  const bool desc = ((i0 & k) == 0);                    // same for 2t and 2t+1 (k >= 2)
-  for (int j = jstart; j >= 2; j >>= 1) {
-    const uint64_t p0 = __shfl_xor_sync(0xFFFFFFFFu, e0, j >> 1), p1 = __shfl_xor_sync(0xFFFFFFFFu, e1, j >> 1);
-    const bool take_max = (desc == ((i0 & j) == 0));    // the lower index of a descending pair keeps the larger
-    e0 = take_max ? max(e0, p0) : min(e0, p0);
-    e1 = take_max ? max(e1, p1) : min(e1, p1);
-  }
-  const uint64_t hi = max(e0, e1), lo = min(e0, e1);    // distance 1: inside the thread
-  e0 = desc ? hi : lo;
-  e1 = desc ? lo : hi;
-}
-
-__device__ void bitonic_sort_desc(uint64_t* v, int pow2) {
-  const int tid = threadIdx.x;
-  const bool active = (tid >> 5) * 64 < pow2;            // whole warps: pow2 is a multiple of 64
-  uint64_t e0 = 0ull, e1 = 0ull;
-  if (active) {
-    e0 = v[2 * tid];
-    e1 = v[2 * tid + 1];
-    for (int k = 2; k <= 64; k <<= 1) bitonic_reg_steps(e0, e1, k, k >> 1, tid);
-    v[2 * tid] = e0;
-    v[2 * tid + 1] = e1;
-  }
-  __syncthreads();
-  for (int k = 128; k <= pow2; k <<= 1) {
-    for (int j = k >> 1; j >= 64; j >>= 1) {
-      for (int t = tid; t < (pow2 >> 1); t += kThreads) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
-        const int p = i | j;
-        const uint64_t x = v[i], y = v[p];
-        if ((x < y) == ((i & k) == 0)) {
-          v[i] = y;
-          v[p] = x;
-        }
-      }
-      __syncthreads();
-    }
-    if (active) {
-      e0 = v[2 * tid];
-      e1 = v[2 * tid + 1];
-      bitonic_reg_steps(e0, e1, k, 32, tid);
-      v[2 * tid] = e0;
-      v[2 * tid + 1] = e1;
-    }
-    __syncthreads();
-  }
-}
-
 // what a helper needs to know about a tile (32 bytes, pushed with two 16-byte remote stores)
 struct ClusterCmd {
   int cmd;                // 1 = tile, 2 = done
@@ -509,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
     __syncthreads();
 
     // ---- bitonic sort, descending
-    bitonic_sort_desc(cand_key, pow2);
+    bx_bitonic_sort<true>(reinterpret_cast<unsigned long long*>(cand_key), pow2);
 
     // ---- decode + clip (or gather) the candidates' boxes, normalised corners for the IoU test
     for (int i = tid; i < cnt; i += kThreads) {

@@ -433,21 +433,6 @@ struct PTArgs {
   int* ws_arg;             // [batch,k] its first argmax
 };
 
-__device__ void bitonic_sort_asc(uint64_t* v, int pow2) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int k = 2; k <= pow2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (pow2 >> 1); t += nt) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int q = i | j;
-        const uint64_t x = v[i], y = v[q];
-        const bool asc = ((i & k) == 0);
-        if ((x > y) == asc) { v[i] = y; v[q] = x; }
-      }
-      __syncthreads();
-    }
-}
-
 // roi x gt IoU rows over the whole device (proposal_target.py:56-58): row max and first argmax per roi
 __global__ void __launch_bounds__(256) pt_rowstats_kernel(const PTArgs a) {
   __shared__ float4 s_gt[kMaxGt];
@@ -538,8 +523,8 @@ __global__ void __launch_bounds__(1024) proposal_target_kernel(const PTArgs a) {
       s_bg[i] = (static_cast<uint64_t>(static_cast<uint32_t>(perm[i])) << 32) | static_cast<uint32_t>(i);
   }
   __syncthreads();
-  bitonic_sort_asc(s_fg, pow2);
-  bitonic_sort_asc(s_bg, pow2);
+  bx_bitonic_sort<false>(reinterpret_cast<unsigned long long*>(s_fg), pow2);
+  bx_bitonic_sort<false>(reinterpret_cast<unsigned long long*>(s_bg), pow2);
 
   const int status = (want > 0 && nbg_all == 0) ? 1 : 0;   // np.random.choice on an empty set raises (:77)
   if (tid == 0) {
