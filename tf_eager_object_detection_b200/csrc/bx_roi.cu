@@ -139,6 +139,17 @@ struct TapEnt {
 
 struct F4x2 { ulonglong2 a, b; };   // x-lerped row values for the two x samples of a pixel
 
+// everything one output pixel needs, precomputed once per roi so that the per-pixel dependency chain in front of the
+// tap loads is one 64-byte shared-memory record (no division, no table indexing, no compares)
+constexpr int kPool2MaxPix = 64;    // P * P
+struct __align__(16) PixRec {
+  int yo[4];                        // row offsets: y0.lo, y0.hi, y1.lo, y1.hi   (float4 units)
+  int xo[4];                        // pixel offsets: x0.lo, x0.hi, x1.lo, x1.hi
+  float wx0, wx1, wy0, wy1;
+  int flags;                        // 1: all four samples valid, 2: x0.hi == x1.lo, 4: y0.hi == y1.lo, 16/32/64/128: y0/y1/x0/x1 valid
+  int pad[3];
+};
+
 template <int POOL>
 __global__ void __launch_bounds__(256, BX_POOL2_CTAS) roi_pool2_kernel(const RoiArgs a, const float neg_zero) {
   __shared__ __align__(16) TapEnt ytab[kMaxQ];
@@ -172,8 +183,23 @@ __global__ void __launch_bounds__(256, BX_POOL2_CTAS) roi_pool2_kernel(const Roi
     }
   }
   __syncthreads();
-  const int groups = 256 / cv;                   // pixels in flight per CTA (launch guarantees 256 % cv == 0, cv >= 32)
+  __shared__ PixRec recs[kPool2MaxPix];
+  if (tid < P * P) {
+    const int prow = tid / P, px = tid - prow * P;
+    const TapEnt y0 = ytab[2 * prow], y1 = ytab[2 * prow + 1];
+    const TapEnt x0 = xtab[2 * px], x1 = xtab[2 * px + 1];
+    PixRec r;
+    r.yo[0] = y0.lo; r.yo[1] = y0.hi; r.yo[2] = y1.lo; r.yo[3] = y1.hi;
+    r.xo[0] = x0.lo; r.xo[1] = x0.hi; r.xo[2] = x1.lo; r.xo[3] = x1.hi;
+    r.wx0 = x0.lerp; r.wx1 = x1.lerp; r.wy0 = y0.lerp; r.wy1 = y1.lerp;
+    r.flags = ((y0.valid & y1.valid & x0.valid & x1.valid) ? 1 : 0) | ((x0.hi == x1.lo) ? 2 : 0) | ((y0.hi == y1.lo) ? 4 : 0) |
+              (y0.valid ? 16 : 0) | (y1.valid ? 32 : 0) | (x0.valid ? 64 : 0) | (x1.valid ? 128 : 0);
+    r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    recs[tid] = r;
+  }
+  __syncthreads();
   const int cg = tid % cv, grp = tid / cv;
+  const int groups = 256 / cv;                   // pixels in flight per CTA (launch guarantees 256 % cv == 0, cv >= 32)
   float4* out = reinterpret_cast<float4*>(a.out) + static_cast<size_t>(j) * P * P * cv + cg;
   if (s_meta[2]) {
     for (int pix = grp; pix < P * P; pix += groups) out[static_cast<size_t>(pix) * cv] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -186,14 +212,14 @@ __global__ void __launch_bounds__(256, BX_POOL2_CTAS) roi_pool2_kernel(const Roi
   const float ext = a.extrapolation;
 
   for (int pix = grp; pix < P * P; pix += groups) {
-    const int prow = pix / P, px = pix - prow * P;
-    const TapEnt y0 = ytab[2 * prow], y1 = ytab[2 * prow + 1];
-    const TapEnt x0 = xtab[2 * px], x1 = xtab[2 * px + 1];
+    const PixRec rec = recs[pix];
+    const TapEnt y0 = {rec.yo[0], rec.yo[1], rec.wy0, rec.flags & 16}, y1 = {rec.yo[2], rec.yo[3], rec.wy1, rec.flags & 32};
+    const TapEnt x0 = {rec.xo[0], rec.xo[1], rec.wx0, rec.flags & 64}, x1 = {rec.xo[2], rec.xo[3], rec.wx1, rec.flags & 128};
     ulonglong2 res;
-    if (y0.valid & y1.valid & x0.valid & x1.valid) {
+    if (rec.flags & 1) {
       const unsigned long long w0 = f2_splat(x0.lerp), w1 = f2_splat(x1.lerp);
-      const bool xsh = (x0.hi == x1.lo);
-      const bool ysh = (y0.hi == y1.lo);
+      const bool xsh = (rec.flags & 2) != 0;
+      const bool ysh = (rec.flags & 4) != 0;
       // all taps of the pixel first (9-16 independent 16-byte loads in flight per thread), then the arithmetic
       const ulonglong2* ra = feat + y0.lo;
       const ulonglong2* rb = feat + y0.hi;
@@ -414,7 +440,7 @@ bool roi_pool2_ok(const RoiArgs& a, int pool) {
   const bool off = getenv("BX_ROI_NO_POOL2") != nullptr;                      // A/B / test switch (read per call)
   if (off || pool == BX_POOL_NONE || (a.c & 3)) return false;
   const int cv = a.c >> 2;
-  if (cv < 32 || cv > 256 || (256 % cv) != 0 || !bx_aligned(a.out, 16)) return false;
+  if (cv < 32 || cv > 256 || (256 % cv) != 0 || !bx_aligned(a.out, 16) || a.P * a.P > kPool2MaxPix) return false;
   for (int l = 0; l < a.n_levels; ++l) {
     if (!bx_aligned(a.lv[l].feat, 16)) return false;
     if (static_cast<long long>(a.lv[l].fh) * a.lv[l].fw * cv >= (1ll << 31)) return false;   // 32-bit tap offsets
