@@ -152,13 +152,12 @@ struct __align__(16) PixRec {
 
 template <int POOL>
 __global__ void __launch_bounds__(256, BX_POOL2_CTAS) roi_pool2_kernel(const RoiArgs a, const float neg_zero) {
-  __shared__ __align__(16) TapEnt ytab[kMaxQ];
-  __shared__ __align__(16) TapEnt xtab[kMaxQ];
+  __shared__ PixRec recs[kPool2MaxPix];
   __shared__ int s_meta[4];
   const int P = a.P, Q = a.Q;
   const int j = blockIdx.x, tid = threadIdx.x;
   const int cv = a.c >> 2;
-  if (tid < 2 * Q) {
+  if (tid < P * P) {                             // one thread per output pixel builds its record (single barrier)
     const int src = a.order ? a.order[j] : j;
     const int lvl = a.level ? a.level[src] - a.level_base : 0;
     int img = a.box_ind ? a.box_ind[src] : 0;
@@ -174,26 +173,21 @@ __global__ void __launch_bounds__(256, BX_POOL2_CTAS) roi_pool2_kernel(const Roi
     }
     const int fh = a.lv[lvl].fh, fw = a.lv[lvl].fw;
     const NormBox nb = roi_norm_box(a, a.rois[src], fh, fw);
-    if (tid < Q) {
-      const Axis ax = sample_axis(nb.x1, nb.x2, tid, Q, nb.dimx, nb.pad);
-      xtab[tid] = {ax.lo * cv, ax.hi * cv, ax.lerp, ax.valid};
-    } else {
-      const Axis ay = sample_axis(nb.y1, nb.y2, tid - Q, Q, nb.dimy, nb.pad);
-      ytab[tid - Q] = {ay.lo * fw * cv, ay.hi * fw * cv, ay.lerp, ay.valid};
-    }
-  }
-  __syncthreads();
-  __shared__ PixRec recs[kPool2MaxPix];
-  if (tid < P * P) {
     const int prow = tid / P, px = tid - prow * P;
-    const TapEnt y0 = ytab[2 * prow], y1 = ytab[2 * prow + 1];
-    const TapEnt x0 = xtab[2 * px], x1 = xtab[2 * px + 1];
+    const Axis y0 = sample_axis(nb.y1, nb.y2, 2 * prow, Q, nb.dimy, nb.pad);
+    const Axis y1 = sample_axis(nb.y1, nb.y2, 2 * prow + 1, Q, nb.dimy, nb.pad);
+    const Axis x0 = sample_axis(nb.x1, nb.x2, 2 * px, Q, nb.dimx, nb.pad);
+    const Axis x1 = sample_axis(nb.x1, nb.x2, 2 * px + 1, Q, nb.dimx, nb.pad);
+    const int pitch = fw * cv;
     PixRec r;
-    r.yo[0] = y0.lo; r.yo[1] = y0.hi; r.yo[2] = y1.lo; r.yo[3] = y1.hi;
-    r.xo[0] = x0.lo; r.xo[1] = x0.hi; r.xo[2] = x1.lo; r.xo[3] = x1.hi;
+    r.yo[0] = y0.valid ? y0.lo * pitch : 0; r.yo[1] = y0.valid ? y0.hi * pitch : 0;
+    r.yo[2] = y1.valid ? y1.lo * pitch : 0; r.yo[3] = y1.valid ? y1.hi * pitch : 0;
+    r.xo[0] = x0.valid ? x0.lo * cv : 0; r.xo[1] = x0.valid ? x0.hi * cv : 0;
+    r.xo[2] = x1.valid ? x1.lo * cv : 0; r.xo[3] = x1.valid ? x1.hi * cv : 0;
     r.wx0 = x0.lerp; r.wx1 = x1.lerp; r.wy0 = y0.lerp; r.wy1 = y1.lerp;
-    r.flags = ((y0.valid & y1.valid & x0.valid & x1.valid) ? 1 : 0) | ((x0.hi == x1.lo) ? 2 : 0) | ((y0.hi == y1.lo) ? 4 : 0) |
-              (y0.valid ? 16 : 0) | (y1.valid ? 32 : 0) | (x0.valid ? 64 : 0) | (x1.valid ? 128 : 0);
+    r.flags = ((y0.valid && y1.valid && x0.valid && x1.valid) ? 1 : 0) | ((r.xo[1] == r.xo[2]) ? 2 : 0) |
+              ((r.yo[1] == r.yo[2]) ? 4 : 0) | (y0.valid ? 16 : 0) | (y1.valid ? 32 : 0) | (x0.valid ? 64 : 0) |
+              (x1.valid ? 128 : 0);
     r.pad[0] = r.pad[1] = r.pad[2] = 0;
     recs[tid] = r;
   }
