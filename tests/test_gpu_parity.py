@@ -863,3 +863,32 @@ def test_native_allgather_on_two_ranks():
                           '--master-addr', '127.0.0.1', '--master-port', '29541', script], capture_output=True, text=True,
                          timeout=240)
     assert out.returncode == 0 and 'allgather ok' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_nms_long_suppression_chains_and_cluster_sweep(bx):
+    """Adversarial tiles for the fixed-point resolve and the cluster sweep: (a) a chain of boxes each suppressing only
+    its successor (greedy keeps every other one: the dependency chain spans whole 64-candidate tiles), (b) heavy
+    near-duplicate suppression with a large quota, so that many tiles run against a long, cluster-distributed kept
+    list and the list runs dry before the quota."""
+    w = 100.0
+    k = np.arange(1500, dtype=np.float32)
+    chain = np.stack([k * 12.0, np.zeros_like(k), k * 12.0 + w, np.full_like(k, 80.0)], axis=1)   # IoU(i,i+1)=.786, (i,i+2)=.61
+    sc = (1.0 - k / 2000.0).astype(np.float32)
+    for post in (300, 700):                                       # single CTA / cluster of 8
+        idx, cnt = bx.nms(cu(chain)[None], cu(sc)[None], post, 0.7)
+        ref = orc.nms_tf(chain, sc, post, 0.7)
+        assert int(cnt[0]) == ref.shape[0] == post and np.array_equal(idx[0, :post].cpu().numpy(), ref)
+        assert np.array_equal(ref, 2 * np.arange(post))           # every other box
+    rng = np.random.default_rng(77)
+    centers = rng.uniform(50, 900, (400, 2)).astype(np.float32)
+    pick = rng.integers(0, 400, 20000)
+    jit = rng.normal(0, 2.0, (20000, 4)).astype(np.float32)
+    half = rng.uniform(20, 60, (400, 2)).astype(np.float32)
+    boxes = np.concatenate([centers[pick] - half[pick], centers[pick] + half[pick]], axis=1) + jit
+    scores = ((rng.permutation(20000) + 1) / 20001.0).astype(np.float32)
+    for post in (600, 2000):
+        idx, cnt = bx.nms(cu(boxes)[None], cu(scores)[None], post, 0.7)
+        ref = orc.nms_tf(boxes, scores, post, 0.7)
+        n = int(cnt[0])
+        assert n == ref.shape[0] and n < post                      # the list runs dry: every candidate was visited
+        assert np.array_equal(idx[0, :n].cpu().numpy(), ref) and (idx[0, n:] == -1).all()
