@@ -112,10 +112,22 @@ def run_cpu_baseline(w, batch_np, budget_s=12.0):
         el = time.perf_counter() - t0
         if el > budget_s or reps >= 50:
             break
-    return dict(value=round(reps * w['batch'] / el, 2), unit=UNIT, cores=cores, kind='port',
-                sample='%d passes over one %d-image batch of the same workload (%.1f s), oracle C twin: '
-                       'single-thread NMS per image, crop_and_resize sharded over boxes with OpenMP'
-                       % (reps, w['batch'], el))
+    out = dict(value=round(reps * w['batch'] / el, 2), unit=UNIT, cores=cores, kind='port',
+               sample='%d passes over one %d-image batch of the same workload (%.1f s), oracle C twin: '
+                      'single-thread NMS per image, crop_and_resize sharded over boxes with OpenMP'
+                      % (reps, w['batch'], el))
+    # second CPU form: the numpy restatement with the reference's eager-style temporaries, one image
+    try:
+        from oracle import boxpath_oracle as orc
+        t0 = time.perf_counter()
+        rois, _ = orc.region_proposal(batch_np['deltas'][0], batch_np['anchors'], batch_np['scores'][0], w['image_hw'],
+                                      w['post_nms'], w['iou_thr'], pre_nms_top_k=w['pre_nms'])
+        orc.roi_pool_c4(batch_np['feat'][:1], rois, w['stride'], w['pool'], False)
+        out['numpy_restatement'] = dict(value=round(1.0 / (time.perf_counter() - t0), 2), unit=UNIT, cores=1,
+                                        sample='one image of the workload through oracle/boxpath_oracle.py')
+    except Exception as e:                                   # the oracle is test infrastructure: never fatal here
+        out['numpy_restatement'] = dict(error=str(e)[:80])
+    return out
 
 
 def run_reference_arm(args):
