@@ -124,7 +124,6 @@ def run_ours(args, w):
     import torch
     import torch.distributed as dist
     from tf_eager_object_detection_b200 import _lib, ops
-    from tf_eager_object_detection_b200._tensor import stream_ptr
 
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))

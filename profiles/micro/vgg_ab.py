@@ -1,5 +1,5 @@
 """VGG16-shape pooled extractor (14x14 crop + 2x2 max, C=512): roi_pool2 (default) vs band kernel (BX_ROI_BAND_POOLED=1)."""
-import os, sys, time
+import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from tf_eager_object_detection_b200 import _lib, ops, synthetic as syn
