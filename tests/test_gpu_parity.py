@@ -892,3 +892,11 @@ def test_nms_long_suppression_chains_and_cluster_sweep(bx):
         n = int(cnt[0])
         assert n == ref.shape[0] and n < post                      # the list runs dry: every candidate was visited
         assert np.array_equal(idx[0, :n].cpu().numpy(), ref) and (idx[0, n:] == -1).all()
+    # a cluster launch with nothing to do: 30 000 equal scores overflow the top-set budget (empty compacted list), the
+    # helpers must be released at once and the full-length redo decides by index order
+    big = np.concatenate([boxes, boxes[:10000] + 1.0])
+    same = np.full(30000, 0.5, np.float32)
+    idx, cnt = bx.nms(cu(big)[None], cu(same)[None], 600, 0.7)
+    ref = orc.nms_tf(big, same, 600, 0.7)
+    n = int(cnt[0])
+    assert n == ref.shape[0] and np.array_equal(idx[0, :n].cpu().numpy(), ref)
