@@ -154,6 +154,8 @@ struct ATArgs {
   int* row_arg;           // [batch,n]
   int* col_max;           // [batch,max_gt] (fp32 bits, iou >= 0 so int order == float order)
   int* warp_max;          // [batch, ceil(n/256)*8, max_gt] per-warp maxima of pass A (fp32 bits)
+  int* inside_idx;        // [n] anchors inside the image (any order), shared by the batch
+  int* n_inside;          // [1]
   int* label;             // [batch,n] pre-sampling then final label (-1/0/1), -2 = outside image
   int* counts;            // [batch,4] = #fg, #bg before sampling; after sampling: fg_final, bg_final
   // outputs
@@ -166,6 +168,21 @@ struct ATArgs {
 
 __device__ __forceinline__ bool anchor_inside(const float4 a, float max_x, float max_y) {
   return (a.x >= 0.0f) && (a.y >= 0.0f) && (a.z <= max_x) && (a.w <= max_y);  // utils/bbox_tf.py:95-100
+}
+
+// pass 0: labels <- -2 ("outside the image", anchor_target.py:48-49 keeps only the inside anchors) and the list of inside
+// anchors, which is all passes A and B ever touch (8151 of 21 546 at cfg2/cfg4)
+__global__ void __launch_bounds__(256) at_prepare_kernel(const ATArgs a) {
+  const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int i = blockIdx.x * 256 + tid;
+  if (i < a.n) a.label[static_cast<size_t>(img) * a.n + i] = -2;
+  if (img != 0) return;
+  const bool inside = (i < a.n) && anchor_inside(a.anchors[i], static_cast<float>(a.p.image_w - 1), static_cast<float>(a.p.image_h - 1));
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, inside);
+  int base = 0;
+  if (lane == 0 && m) base = atomicAdd(a.n_inside, __popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  if (inside) a.inside_idx[base + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
 // IoU of one (anchor, gt) pair exactly as bx_iou_plus1, with the division skipped for disjoint pairs (most of them)
@@ -192,11 +209,14 @@ __global__ void __launch_bounds__(256) at_rowstats_kernel(const ATArgs a) {
     s_gt[j] = g;
     s_area[j] = bx_area_plus1(g);
   }
+  const int ni = *a.n_inside;
+  if (static_cast<int>(blockIdx.x) * 256 >= ni) return;          // the grid covers n; only the inside anchors do work
   __syncthreads();
-  const int i = blockIdx.x * 256 + tid;
-  const bool live = i < a.n;
+  const int ci = blockIdx.x * 256 + tid;
+  const bool live = ci < ni;
+  const int i = live ? a.inside_idx[ci] : 0;
   const float4 anc = live ? a.anchors[i] : make_float4(0, 0, 0, 0);
-  const bool inside = live && anchor_inside(anc, static_cast<float>(a.p.image_w - 1), static_cast<float>(a.p.image_h - 1));
+  const bool inside = live;
   const float area = bx_area_plus1(anc);
   float best = -1.0f;
   int arg = 0;
@@ -235,10 +255,13 @@ __global__ void __launch_bounds__(256) at_rowstats_kernel(const ATArgs a) {
 __global__ void __launch_bounds__(256) at_label_kernel(const ATArgs a) {
   const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = a.gt_counts ? a.gt_counts[img] : a.max_gt;
-  const int i = blockIdx.x * 256 + tid;
-  const bool live = i < a.n;
+  const int ni = *a.n_inside;
+  if (static_cast<int>(blockIdx.x) * 256 >= ni) return;
+  const int ci = blockIdx.x * 256 + tid;
+  const bool live = ci < ni;
+  const int i = live ? a.inside_idx[ci] : 0;
   const float4 anc = live ? a.anchors[i] : make_float4(0, 0, 0, 0);
-  const bool inside = live && anchor_inside(anc, static_cast<float>(a.p.image_w - 1), static_cast<float>(a.p.image_h - 1));
+  const bool inside = live;
   const float area = bx_area_plus1(anc);
   const int* g_w = a.warp_max + ((static_cast<size_t>(img) * gridDim.x + blockIdx.x) * 8 + warp) * a.max_gt;
   const int* colmax = a.col_max + static_cast<size_t>(img) * a.max_gt;
@@ -611,7 +634,7 @@ extern "C" int bx_anchor_target(bx_handle* h, const float* anchors, int n, const
   const int nblk = static_cast<int>(bx_div_up(n, 256));
   const size_t wm = static_cast<size_t>(batch) * nblk * 8 * (max_gt > 0 ? max_gt : 1);
   const size_t ws = bn * (sizeof(float) + 2 * sizeof(int)) + static_cast<size_t>(batch) * (max_gt + 4) * sizeof(int) +
-                    wm * sizeof(int);
+                    4 * sizeof(int) + wm * sizeof(int) + static_cast<size_t>(n) * sizeof(int);
   int rc = bx_ws_reserve(h, ws);
   if (rc) return rc;
   ATArgs a = {};
@@ -628,14 +651,18 @@ extern "C" int bx_anchor_target(bx_handle* h, const float* anchors, int n, const
   a.label = a.row_arg + bn;
   a.col_max = a.label + bn;
   a.counts = a.col_max + static_cast<size_t>(batch) * max_gt;
-  a.warp_max = a.counts + static_cast<size_t>(batch) * 4;
+  a.n_inside = a.counts + static_cast<size_t>(batch) * 4;
+  a.warp_max = a.n_inside + 4;
+  a.inside_idx = a.warp_max + wm;
   a.out_labels = out_labels;
   a.out_targets = reinterpret_cast<float4*>(out_targets);
   a.out_in_w = reinterpret_cast<float4*>(out_in_w);
   a.out_out_w = reinterpret_cast<float4*>(out_out_w);
   a.out_counts = out_counts;
-  BX_CUDA(cudaMemsetAsync(a.col_max, 0, static_cast<size_t>(batch) * (max_gt + 4) * sizeof(int), st));
+  BX_CUDA(cudaMemsetAsync(a.col_max, 0, (static_cast<size_t>(batch) * (max_gt + 4) + 4) * sizeof(int), st));
   const dim3 grid(nblk, batch);
+  at_prepare_kernel<<<grid, 256, 0, st>>>(a);
+  BX_LAUNCH_CHECK(h);
   const size_t smem_a = static_cast<size_t>(max_gt) * (sizeof(float4) + sizeof(float) + 8 * sizeof(int));
   if (smem_a > 48 * 1024)
     BX_CUDA(cudaFuncSetAttribute(at_rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
