@@ -74,9 +74,9 @@ class Borrow:
                 raise TypeError('tensor is on cuda:%d, handle is on cuda:%d' % (dv.index, self.device))
             if _TORCH_KIND.get(t.dtype) != kind:
                 raise TypeError('tensor dtype %s != expected (code %d, %d bits)' % (t.dtype, kind[0], kind[1]))
-            ts = t.shape
-            if len(ts) != len(shape) or any(e >= 0 and e != a for a, e in zip(ts, shape)):
-                raise TypeError('tensor shape %s, expected %s' % (tuple(ts), tuple(shape)))
+            ts = tuple(t.shape)
+            if ts != shape and (len(ts) != len(shape) or any(e >= 0 and e != a for a, e in zip(ts, shape))):
+                raise TypeError('tensor shape %s, expected %s' % (ts, tuple(shape)))
             p = t.data_ptr()
             if align > 1 and p % align and t.numel():
                 raise TypeError('tensor data is not %d-byte aligned' % align)
@@ -95,7 +95,13 @@ def device_index_of(t):
     return t.device.index if t.device.index is not None else torch.cuda.current_device()
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def stream_ptr(device_index):
+    """torch's current stream on the device as a cudaStream_t (raw accessor when torch has it: no Stream object)."""
+    if _raw_stream is not None:
+        return c_void_p(_raw_stream(device_index))
     return c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
 
 
