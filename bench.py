@@ -382,7 +382,9 @@ def run_ours(args):
         roi_bytes = B * b_roi                           # one launch pools the whole batch
         achieved = roi_bytes / (roi_avg_ms * 1e-3) / 1e9 if roi_avg_ms > 0 else 0.0
         step_bytes = B * (b_prop + b_roi)
-        cpu = run_cpu_baseline(w, host_batches[0])
+        # the CPU arm is timed on rank 0 at N=1 only (all host cores belong to the one process there)
+        cpu = run_cpu_baseline(w, host_batches[0]) if world == 1 else dict(
+            value=None, unit=UNIT, cores=0, kind='port', sample='not run at N > 1: measured on rank 0 at N = 1 only')
         line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps,
                     warmup=max(3, args.warmup), ms_per_step=round(ms_max / args.steps, 5), higher_is_better=True,
                     scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',

@@ -255,7 +255,10 @@ def run_ours(args, w):
         peak, which = hbm_peak()
         roi_avg = sum(roi_ms) / max(1, len(roi_ms))
         achieved = B * b_roi / (roi_avg * 1e-3) / 1e9 if roi_avg > 0 else 0.0
-        cpu_v, cores, sample = run_cpu(w, 8, 15.0)
+        if world == 1:
+            cpu_v, cores, sample = run_cpu(w, 8, 15.0)
+        else:
+            cpu_v, cores, sample = None, 0, 'not run at N > 1: measured on rank 0 at N = 1 only'
         line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=W,
                     ms_per_step=round(ms_max / args.steps, 5), higher_is_better=True, scaling=w['scaling'],
                     vs_baseline=None, dtype='f32', data='synthetic',
@@ -268,7 +271,7 @@ def run_ours(args, w):
                                   achieved=round(achieved, 1), peak=peak, peak_source=which, unit='GB/s',
                                   frac=round(achieved / peak, 4), traffic=None, launches_timed=len(roi_ms),
                                   avg_launch_ms=round(roi_avg, 5), algorithmic_bytes_per_launch=B * b_roi),
-                    cpu_baseline=dict(value=round(cpu_v, 2), unit=UNIT, cores=cores, kind='port', sample=sample),
+                    cpu_baseline=dict(value=None if cpu_v is None else round(cpu_v, 2), unit=UNIT, cores=cores, kind='port', sample=sample),
                     e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              steps=e2e_steps, images_per_step=Be,
                              api='ops.proposals + ops.fpn_roi_features, pinned host buffers, one stream'),
