@@ -203,6 +203,24 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(self.reasons), samples=len(self.samples))
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as local to its GPU, so that the pinned host buffers
+    of the e2e leg are allocated on the GPU's own NUMA node (first touch) and the copies do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -337,12 +355,17 @@ def run_ours(args):
     # ---- e2e: the public Python API with HOST (pinned) buffers; H2D inputs + D2H outputs inside the timed region
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
     hb = host_batches[0]
+    # pinned staging buffers are allocated (first touch) while the process is bound to the CPUs local to its GPU
+    old_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
     NE = 2   # two streams, two sets of pinned buffers: the D2H of step i overlaps the H2D + kernels of step i+1
     h_in = [dict(deltas=pin(b_['deltas']), scores=pin(b_['scores']), feat=pin(b_['feat'])) for b_ in host_batches[:NE]]
     h_outs = [(torch.empty((B, post, 4)).pin_memory(), torch.empty((B, post), dtype=torch.int32).pin_memory(),
                torch.empty((B,), dtype=torch.int32).pin_memory(), torch.empty((B * post, P, P, C)).pin_memory())
               for _ in range(NE)]
+    if numa is not None:
+        os.sched_setaffinity(0, old_affinity)
     h2d = sum(t_.numel() * t_.element_size() for t_ in h_in[0].values())
     d2h = sum(t_.numel() * t_.element_size() for t_ in h_outs[0])
     e_streams = [torch.cuda.Stream(dev) for _ in range(NE)]
@@ -406,7 +429,8 @@ def run_ours(args):
                     cpu_baseline=cpu,
                     e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              steps=e2e_steps, ms_per_step=round(e2e_ms / e2e_steps, 3), wall_ms_per_step=round(wall_ms / e2e_steps, 3),
-                             api='ops.c4_proposal_roi_host -> bx_c4_proposal_roi_host (pinned host buffers, 2 streams)'),
+                             api='ops.c4_proposal_roi_host -> bx_c4_proposal_roi_host (pinned host buffers, 2 streams)',
+                             numa_bound_cpus=numa),
                     gpu_launches=gpu_launches, clocks=sampler.summary())
         print(json.dumps(line), flush=True)
     if world > 1:
