@@ -9,6 +9,16 @@
 // prefix of the sorted order is ever needed.  Each round selects the next <= CHUNK best candidates (exact set, any
 // order), sorts just those, and sweeps them; with pre_nms_top_k = 0 (reference behaviour) rounds continue until the
 // quota is filled or every anchor was visited, so the result is identical to sorting all N.
+//
+// Two extensions keep that kernel fed at the larger configurations:
+//   * n > 24 576 (FPN, 150 k - 267 k anchors): a multi-CTA radix select + stable compaction over the whole device
+//     ("top set") hands the kernel the largest <= 24 576 keys, which it caches in shared memory; a per-image flag and an
+//     early-out relaunch cover the rare case that this list runs dry;
+//   * post_nms >= 512: the kernel runs as a thread-block cluster per image; helper CTAs hold a share of the kept list
+//     and test every tile against it (tile boxes pushed over DSMEM, mbarrier signalling, partial 64-bit masks).
+// The same file holds the inputs of the stage (anchors on the device, RPN score layouts, "next" row f2).
+#include <stdlib.h>
+
 #include "bx_common.cuh"
 
 namespace {
