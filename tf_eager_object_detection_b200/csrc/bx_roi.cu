@@ -3,9 +3,15 @@
 // (RoiPoolingCropAndResize), :93-176 (crop_and_resize(pad_border)/roi_align/RoiPoolingRoiAlign) and
 // model/fpn/base_fpn_model.py:152-161,303-324 (_get_roi_features, _assign_levels).
 //
-// Layout: features NHWC fp32, so the channel axis is the coalesced / float4 axis; one CTA produces one output row
-// (roi, py): P pixels x C channels, written once, contiguous.  Sample coordinates follow the TF r1.13 kernel's fp32
-// op order: in_y = y1*(h-1) + y*((y2-y1)*(h-1)/(Q-1)); a sample outside [0,h-1]x[0,w-1] is 0.
+// Layout: features NHWC fp32, so the channel axis is the coalesced / float4 axis.  Sample coordinates follow the TF r1.13
+// kernel's fp32 op order: in_y = y1*(h-1) + y*((y2-y1)*(h-1)/(Q-1)); a sample outside
+// [0,h-1]x[0,w-1] is 0.  Three forward kernels share that arithmetic bit for bit:
+//   * roi_band_kernel (bx_roi_band.cu)  plain crops: feature band stationary in shared memory (TMA), the headline kernel;
+//   * roi_pool2_kernel (here)           pooled crops (2x2 max / avg): one CTA per roi, shared taps of the 2x2 sample block
+//                                       loaded once, per-pixel records, packed fp32x2 lerps; FPN level routing reads
+//                                       `order` / `level` so the output lands in the reference's concatenated order;
+//   * roi_pool_kernel (here)            generic gather for every other shape (C % 4 != 0, wide maps, extrapolation != 0).
+// roi_pool_grad_kernel is the backward w.r.t. the feature map ("next" row f3).
 #include <stdlib.h>
 
 #include "bx_roi.cuh"
