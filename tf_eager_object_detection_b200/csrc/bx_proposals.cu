@@ -28,8 +28,10 @@ constexpr int kChunk = 2048;        // candidates sorted + swept per round
 constexpr int kBins = 2048;         // histogram bins per select level
 static_assert(kBins == 2 * kThreads, "the select scan gives every thread two bins");
 constexpr int kMaxPost = 2048;      // kept-box list capacity (post_nms limit)
-constexpr int kTile = 64;           // NMS tile: one 64-bit mask word
-constexpr int kPairs = kTile * (kTile - 1) / 2;   // unordered candidate pairs of a tile
+constexpr int kTile = 128;          // largest NMS tile: candidates resolved per round (two 64-bit mask words); the kernel
+                                    // is instantiated for 64 (small quotas: fewer pair tests) and 128 (cluster sweep:
+                                    // half the signalling rounds)
+constexpr int tile_pairs(int t) { return t * (t - 1) / 2; }   // unordered candidate pairs of a tile
 constexpr int kUnroll = 8;          // independent key loads in flight per thread in the streaming passes
 constexpr int kKeyCacheMax = 24576; // keys cached in smem when n <= this (C4 600x1000: 21 546)
 
@@ -109,21 +111,27 @@ __device__ __forceinline__ float4 normalise(const float4 b) {
   return make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
 }
 
-// what a helper needs to know about a tile (32 bytes, pushed with two 16-byte remote stores)
+// what a helper needs to know about a tile (48 bytes, pushed with three 16-byte remote stores)
 struct ClusterCmd {
   int cmd;                // 1 = tile, 2 = done
   int t0, tn;             // tile start / size in the leader's cand_box
   int kept;               // kept count before this tile
   int p_valid, p_kept;    // previous tile: valid flag, kept count before it
-  uint64_t p_keepmask;    // previous tile: keep mask
+  int pad0, pad1;
+  uint64_t p_keepmask[2]; // previous tile: keep mask (128 bits)
 };
+static_assert(sizeof(ClusterCmd) == 48, "ClusterCmd is pushed as three 16-byte remote stores");
+
+// bits [0, c) of a 128-bit mask held as two words
+__device__ __forceinline__ uint64_t below_w0(int c) { return c >= 64 ? ~0ull : ((1ull << c) - 1ull); }
+__device__ __forceinline__ uint64_t below_w1(int c) { return c <= 64 ? 0ull : (c >= 128 ? ~0ull : ((1ull << (c - 64)) - 1ull)); }
 
 struct Shared {
   uint64_t lo, hi;        // current select range (inclusive)
   uint64_t prev;          // exclusive upper bound: composites already consumed are >= prev
   uint64_t thresh;        // selected threshold of this round
-  uint64_t sup;           // tile: candidates suppressed by the kept list
-  uint64_t keepmask;      // tile: candidates kept
+  uint64_t sup[2];        // tile: candidates suppressed by the kept list
+  uint64_t keepmask[2];   // tile: candidates kept
   uint32_t kmin, kmax;    // key range of the image
   int n_valid;            // keys > 0
   int cand_count;
@@ -132,8 +140,8 @@ struct Shared {
   // thread-block-cluster sweep: the leader (cluster rank 0) pushes this block into every helper's copy of Shared
   alignas(16) ClusterCmd cc;
   int p_valid, p_kept;    // leader: result of the previous tile (copied into cc for the next one)
-  uint64_t p_keepmask;
-  uint64_t sup_part[8];   // partial suppression masks pushed by the helpers
+  uint64_t p_keepmask[2];
+  uint64_t sup_part[8][2];  // partial suppression masks pushed by the helpers
   uint64_t mb_tile;       // helpers: "tile pushed" (1 arrival per tile, from the leader)
   uint64_t mb_part;       // leader: "partial masks delivered" (cs - 1 arrivals per tile)
 };
@@ -201,52 +209,56 @@ __device__ __forceinline__ uint32_t load_key(const ProposalArgs& a, const uint32
 // announces, tests the tile's 64 candidates against them.  Two mbarrier signals per tile instead of whole-cluster
 // barriers: A = "tile pushed" (the leader has written the command block and the tile's boxes into this CTA's shared
 // memory and arrives on this CTA's mb_tile), B = "partial mask delivered" (this CTA arrives on the leader's mb_part).
-__device__ void nms_cluster_helper(const ProposalArgs& a, float4* tilebuf /* [2][kTile] */, float4* kept_box,
+template <int TILE>
+__device__ void nms_cluster_helper(const ProposalArgs& a, float4* tilebuf /* [2][TILE] */, float4* kept_box,
                                    Shared* sh, uint32_t rank, uint32_t cs) {
-  __shared__ uint64_t h_sup;
+  __shared__ uint64_t h_sup[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t lsup = dsmem_addr(&sh->sup_part[rank], 0);
+  const uint32_t lsup = dsmem_addr(&sh->sup_part[rank][0], 0);
   int cur = 0;
   for (;;) {
     cmbar_wait(&sh->mb_tile, static_cast<uint32_t>(cur));                  // A: the leader pushed a tile (or "done")
     const ClusterCmd cc = sh->cc;
-    if (tid == 0) h_sup = 0ull;
+    if (tid < 2) h_sup[tid] = 0ull;
     if (cc.cmd != 1) return;
     const int tn = cc.tn, kept = cc.kept;
-    if (cc.p_valid && tid < kTile && ((cc.p_keepmask >> tid) & 1ull)) {    // adopt this CTA's share of the last keeps
-      const uint32_t g = static_cast<uint32_t>(cc.p_kept) + __popcll(cc.p_keepmask & ((1ull << tid) - 1ull));
-      if (g % cs == rank) kept_box[g / cs] = normalise(tilebuf[(cur ^ 1) * kTile + tid]);
+    if (cc.p_valid && tid < TILE && ((cc.p_keepmask[tid >> 6] >> (tid & 63)) & 1ull)) {   // adopt this CTA's share of the last keeps
+      const uint32_t g = static_cast<uint32_t>(cc.p_kept) + __popcll(cc.p_keepmask[0] & below_w0(tid)) +
+                         __popcll(cc.p_keepmask[1] & below_w1(tid));
+      if (g % cs == rank) kept_box[g / cs] = normalise(tilebuf[(cur ^ 1) * TILE + tid]);
     }
     __syncthreads();
     const int kl = (kept > static_cast<int>(rank)) ? (kept - static_cast<int>(rank) + static_cast<int>(cs) - 1) / static_cast<int>(cs) : 0;
-    const int c = tid & 63;
+    const int c = tid & (TILE - 1);
     bool sflag = false;
     if (c < tn) {
-      const float4 cb = normalise(tilebuf[cur * kTile + c]);
+      const float4 cb = normalise(tilebuf[cur * TILE + c]);
       const float ca = (cb.z - cb.x) * (cb.w - cb.y);
-      for (int j = tid >> 6; j < kl && !sflag; j += 16) sflag = iou_gt(cb, ca, kept_box[j], a.thr);
+      for (int j = tid / TILE; j < kl && !sflag; j += kThreads / TILE) sflag = iou_gt(cb, ca, kept_box[j], a.thr);
     }
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, sflag);
-    if (lane == 0 && m) atomicOr(reinterpret_cast<unsigned long long*>(&h_sup),
+    if (lane == 0 && m) atomicOr(reinterpret_cast<unsigned long long*>(&h_sup[((warp * 32) & (TILE - 1)) >> 6]),
                                  static_cast<unsigned long long>(m) << ((warp & 1) * 32));
     __syncthreads();
     if (tid == 0) {
-      dsmem_st_u64(lsup, h_sup);
+      dsmem_st_u64(lsup, h_sup[0]);
+      dsmem_st_u64(lsup + 8u, h_sup[1]);
       cmbar_arrive_remote(&sh->mb_part, 0);                                // B: this helper's partial mask is in
     }
     cur ^= 1;
   }
 }
 
-template <bool kCache>
+template <bool kCache, int TILE>
 __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalArgs a) {
+  constexpr int kPairs = TILE * (TILE - 1) / 2;   // unordered candidate pairs of a tile
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // carve-up (all 16B aligned)
   float4* cand_box = reinterpret_cast<float4*>(smem_raw);                           // kChunk
   float4* kept_box = cand_box + kChunk;                                             // kMaxPost
   uint64_t* cand_key = reinterpret_cast<uint64_t*>(kept_box + kMaxPost);            // kChunk
-  uint64_t* rowmask = cand_key + kChunk;                                            // kTile
-  uint32_t* hist = reinterpret_cast<uint32_t*>(rowmask + kTile);                    // kBins
+  uint64_t* rowmask = cand_key + kChunk;                                            // kTile rows x 2 words
+  uint32_t* hist = reinterpret_cast<uint32_t*>(rowmask + 2 * kTile);                // kBins
   uint32_t* red = hist + kBins;                                                     // 64 (block reductions)
   Shared* sh = reinterpret_cast<Shared*>(red + 64);
   uint16_t* kept_ci = reinterpret_cast<uint16_t*>(sh + 1);                          // kMaxPost: chunk position of each keep
@@ -271,12 +283,12 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
     cluster_sync_all();                      // every CTA's barriers exist before anybody signals
   }
   if (crank != 0) {
-    nms_cluster_helper(a, cand_box, kept_box, sh, crank, cs);
+    nms_cluster_helper<TILE>(a, cand_box, kept_box, sh, crank, cs);
     return;
   }
-  if (tid < kTile - 1) {                      // row tid of the upper triangle: pairs (tid, tid+1 .. 63)
-    int o = tid * (2 * kTile - 1 - tid) / 2;
-    for (int j = tid + 1; j < kTile; ++j) pair_tab[o++] = static_cast<uint16_t>(tid | (j << 8));
+  if (tid < TILE - 1) {                          // row tid of the upper triangle: pairs (tid, tid+1 .. TILE-1)
+    int o = tid * (2 * TILE - 1 - tid) / 2;
+    for (int j = tid + 1; j < TILE; ++j) pair_tab[o++] = static_cast<uint16_t>(tid | (j << 8));
   }
   const int n = a.topset_info ? min(a.topset_info[img * 4 + 1], a.n) : a.n;
   const size_t full = a.src_idx ? static_cast<size_t>(a.src_stride) : static_cast<size_t>(a.n);
@@ -478,13 +490,14 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
     }
     __syncthreads();
 
-    // ---- greedy sweep in tiles of 64
+    // ---- greedy sweep in tiles of TILE candidates
     const int chunk_kept0 = sh->kept;
-    for (int t0 = 0; t0 < cnt && sh->kept < a.post_nms; t0 += kTile) {
-      const int tn = min(kTile, cnt - t0);
+    for (int t0 = 0; t0 < cnt && sh->kept < a.post_nms; t0 += TILE) {
+      const int tn = min(TILE, cnt - t0);
       const int kept = sh->kept;
       if (tid == 0) {
-        sh->sup = 0ull;
+        sh->sup[0] = 0ull;
+        sh->sup[1] = 0ull;
         if (cs > 1) {                        // the tile's command block (the previous tile's keeps ride along)
           sh->cc.cmd = 1;
           sh->cc.t0 = t0;
@@ -492,34 +505,36 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
           sh->cc.kept = kept;
           sh->cc.p_valid = sh->p_valid;
           sh->cc.p_kept = sh->p_kept;
-          sh->cc.p_keepmask = sh->p_keepmask;
+          sh->cc.p_keepmask[0] = sh->p_keepmask[0];
+          sh->cc.p_keepmask[1] = sh->p_keepmask[1];
         }
       }
-      if (cs > 1 && tid < 8) sh->sup_part[tid] = 0ull;
-      if (tid >= 64 && tid < 64 + kTile) {   // normalised corners + area of the tile's candidates, masks cleared
-        const int c = tid - 64;
+      if (cs > 1 && tid < 16) sh->sup_part[tid >> 1][tid & 1] = 0ull;
+      if (tid >= 128 && tid < 128 + TILE) { // normalised corners + area of the tile's candidates, masks cleared
+        const int c = tid - 128;
         const float4 nb = normalise(cand_box[t0 + min(c, tn - 1)]);
         tile_nb[c] = nb;
         tile_area[c] = (nb.z - nb.x) * (nb.w - nb.y);
-        rowmask[c] = 0ull;
+        rowmask[2 * c] = 0ull;
+        rowmask[2 * c + 1] = 0ull;
       }
       __syncthreads();
       if (cs > 1) {
-        // push the tile's boxes and the command block into every helper's shared memory, then barrier A
-        const int n_push = kTile * (static_cast<int>(cs) - 1);
+        // push the tile's boxes and the command block into every helper's shared memory, then signal A
+        const int n_push = TILE * (static_cast<int>(cs) - 1);                   // <= 896
         if (tid < n_push) {
-          const uint32_t helper = 1u + static_cast<uint32_t>(tid) / kTile;
-          const int c = tid % kTile;
+          const uint32_t helper = 1u + static_cast<uint32_t>(tid) / TILE;
+          const int c = tid % TILE;
           if (c < tn) {
             const float4 b = cand_box[t0 + c];
-            dsmem_st_v4(dsmem_addr(&cand_box[(tile_seq & 1) * kTile + c], helper),
+            dsmem_st_v4(dsmem_addr(&cand_box[(tile_seq & 1) * TILE + c], helper),
                         make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
           }
-        } else if (tid >= 512 && tid < 512 + 2 * (static_cast<int>(cs) - 1)) {
-          const int e = tid - 512;
-          const uint32_t helper = 1u + static_cast<uint32_t>(e >> 1);
-          const uint4* src = reinterpret_cast<const uint4*>(&sh->cc) + (e & 1);
-          dsmem_st_v4(dsmem_addr(reinterpret_cast<const uint4*>(&sh->cc) + (e & 1), helper), *src);
+        } else if (tid >= 960 && tid < 960 + 3 * (static_cast<int>(cs) - 1)) {
+          const int e = tid - 960, part = e % 3;
+          const uint32_t helper = 1u + static_cast<uint32_t>(e / 3);
+          const uint4* src = reinterpret_cast<const uint4*>(&sh->cc) + part;
+          dsmem_st_v4(dsmem_addr(src, helper), *src);
         }
         __syncthreads();                     // every push is issued before the signal
         if (tid < static_cast<int>(cs) - 1) cmbar_arrive_remote(&sh->mb_tile, 1u + static_cast<uint32_t>(tid));   // A
@@ -528,28 +543,24 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
       // kept boxes are dealt round-robin over the cluster: this CTA holds g = 0, cs, 2cs, ... at kept_box[g / cs]
       const int kl = (cs > 1) ? (kept + static_cast<int>(cs) - 1) / static_cast<int>(cs) : kept;
       {
-        // (1) tile candidates vs kept list: candidate c = tid & 63, kept subset j = tid>>6 (mod 16)
-        const int c = tid & 63;
+        // (1) tile candidates vs kept list: candidate c = tid mod TILE, kept subset j = tid / TILE (mod 1024 / TILE)
+        const int c = tid & (TILE - 1);
         bool s = false;
         if (c < tn) {
           const float4 cb = tile_nb[c];
           const float ca = tile_area[c];
-          for (int j = tid >> 6; j < kl && !s; j += 16) s = iou_gt(cb, ca, kept_box[j], a.thr);
+          for (int j = tid / TILE; j < kl && !s; j += kThreads / TILE) s = iou_gt(cb, ca, kept_box[j], a.thr);
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, s);
-        if (lane == 0 && m) atomicOr(reinterpret_cast<unsigned long long*>(&sh->sup),
+        if (lane == 0 && m) atomicOr(reinterpret_cast<unsigned long long*>(&sh->sup[((warp * 32) & (TILE - 1)) >> 6]),
                                      static_cast<unsigned long long>(m) << ((warp & 1) * 32));
         // (2) intra-tile masks: every unordered pair (i < j) once — the test is symmetric bit for bit, so a hit sets
         //     bit j of row i and bit i of row j (the bits below i are "the earlier candidates that suppress i")
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int p = tid + q * kThreads;
-          if (p < kPairs) {
-            const int e = pair_tab[p], i = e & 0xFF, j = e >> 8;
-            if (j < tn && iou_gt(tile_nb[i], tile_area[i], tile_nb[j], a.thr)) {
-              atomicOr(reinterpret_cast<unsigned long long*>(&rowmask[i]), 1ull << j);
-              atomicOr(reinterpret_cast<unsigned long long*>(&rowmask[j]), 1ull << i);
-            }
+        for (int p = tid; p < kPairs; p += kThreads) {
+          const int e = pair_tab[p], i = e & 0xFF, j = e >> 8;
+          if (j < tn && iou_gt(tile_nb[i], tile_area[i], tile_nb[j], a.thr)) {
+            atomicOr(reinterpret_cast<unsigned long long*>(&rowmask[2 * i + (j >> 6)]), 1ull << (j & 63));
+            atomicOr(reinterpret_cast<unsigned long long*>(&rowmask[2 * j + (i >> 6)]), 1ull << (i & 63));
           }
         }
       }
@@ -559,47 +570,68 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         // greedy resolve of the tile by warp 0 as a fixed point: candidate i is kept iff it is alive and no KEPT earlier
         // candidate suppresses it.  Iterating K <- {i alive : full[i] & below(i) & K == 0} from K = alive fixes
         // candidates in index order (after t rounds every i < t is final), the greedy set is its only fixed point,
-        // and suppression chains inside a tile are short: a few ballot rounds instead of a 64-step dependent chain.
-        const uint64_t f0 = rowmask[lane], f1 = rowmask[lane + 32];
-        uint64_t removed = sh->sup;
+        // and suppression chains inside a tile are short: a few ballot rounds instead of a 128-step dependent chain.
+        // Lane l owns candidates l, l+32, l+64, l+96.
+        uint64_t f[4][2], bl[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = lane + 32 * k;
+          f[k][0] = rowmask[2 * c];
+          f[k][1] = rowmask[2 * c + 1];
+          bl[k][0] = below_w0(c);
+          bl[k][1] = below_w1(c);
+        }
+        uint64_t rem0 = sh->sup[0], rem1 = sh->sup[1];
         if (cs > 1) {
 #pragma unroll
-          for (int r = 1; r < 8; ++r) removed |= sh->sup_part[r];
+          for (int r = 1; r < 8; ++r) { rem0 |= sh->sup_part[r][0]; rem1 |= sh->sup_part[r][1]; }
         }
-        if (tn < 64) removed |= ~((1ull << tn) - 1ull);
-        const uint64_t alive = ~removed;
-        const uint64_t below0 = (1ull << lane) - 1ull, below1 = (1ull << (lane + 32)) - 1ull;
-        const bool a0 = (alive >> lane) & 1ull, a1 = (alive >> (lane + 32)) & 1ull;
-        uint64_t K = alive;
+        rem0 |= ~below_w0(tn);
+        rem1 |= ~below_w1(tn);
+        const uint64_t al0 = ~rem0, al1 = ~rem1;
+        const bool a0 = (al0 >> lane) & 1ull, a1 = (al0 >> (lane + 32)) & 1ull;
+        const bool a2 = (al1 >> lane) & 1ull, a3 = (al1 >> (lane + 32)) & 1ull;
+        uint64_t K0 = al0, K1 = al1;
         for (;;) {
-          const bool k0 = a0 && ((f0 & below0 & K) == 0ull);
-          const bool k1 = a1 && ((f1 & below1 & K) == 0ull);
-          const uint64_t Kn = static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, k0)) |
+          const bool k0 = a0 && (((f[0][0] & bl[0][0] & K0) | (f[0][1] & bl[0][1] & K1)) == 0ull);
+          const bool k1 = a1 && (((f[1][0] & bl[1][0] & K0) | (f[1][1] & bl[1][1] & K1)) == 0ull);
+          const bool k2 = a2 && (((f[2][0] & bl[2][0] & K0) | (f[2][1] & bl[2][1] & K1)) == 0ull);
+          const bool k3 = a3 && (((f[3][0] & bl[3][0] & K0) | (f[3][1] & bl[3][1] & K1)) == 0ull);
+          const uint64_t n0 = static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, k0)) |
                               (static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, k1)) << 32);
-          if (Kn == K) break;
-          K = Kn;
+          const uint64_t n1 = static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, k2)) |
+                              (static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, k3)) << 32);
+          if (n0 == K0 && n1 == K1) break;
+          K0 = n0;
+          K1 = n1;
         }
         const int room = a.post_nms - kept;                      // quota: only the first `room` keeps count
-        if (__popcll(K) > room) {
-          const bool k0 = ((K >> lane) & 1ull) && __popcll(K & below0) < room;
-          const bool k1 = ((K >> (lane + 32)) & 1ull) && __popcll(K & below1) < room;
-          K = static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, k0)) | (static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, k1)) << 32);
+        if (__popcll(K0) + __popcll(K1) > room) {
+          bool kk[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = lane + 32 * k;
+            const bool set = (((k < 2 ? K0 : K1) >> (c & 63)) & 1ull) != 0ull;
+            kk[k] = set && (__popcll(K0 & bl[k][0]) + __popcll(K1 & bl[k][1]) < room);
+          }
+          K0 = static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, kk[0])) | (static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, kk[1])) << 32);
+          K1 = static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, kk[2])) | (static_cast<uint64_t>(__ballot_sync(0xFFFFFFFFu, kk[3])) << 32);
         }
-        const uint32_t keep_lo = static_cast<uint32_t>(K), keep_hi = static_cast<uint32_t>(K >> 32);
         if (lane == 0) {
-          const uint64_t keep = static_cast<uint64_t>(keep_lo) | (static_cast<uint64_t>(keep_hi) << 32);
-          sh->keepmask = keep;
-          sh->kept = kept + __popcll(keep);
+          sh->keepmask[0] = K0;
+          sh->keepmask[1] = K1;
+          sh->kept = kept + __popcll(K0) + __popcll(K1);
           sh->p_valid = 1;
           sh->p_kept = kept;
-          sh->p_keepmask = keep;
+          sh->p_keepmask[0] = K0;
+          sh->p_keepmask[1] = K1;
         }
       }
       __syncthreads();
       if (tid < tn) {
-        const uint64_t keep = sh->keepmask;
-        if ((keep >> tid) & 1ull) {
-          const int pos = kept + __popcll(keep & ((1ull << tid) - 1ull));
+        const uint64_t K0 = sh->keepmask[0], K1 = sh->keepmask[1];
+        if (((tid < 64 ? K0 : K1) >> (tid & 63)) & 1ull) {
+          const int pos = kept + __popcll(K0 & below_w0(tid)) + __popcll(K1 & below_w1(tid));
           const float4 b = cand_box[t0 + tid];
           if (cs == 1) kept_box[pos] = normalise(b);
           else if (pos % cs == 0) kept_box[pos / cs] = normalise(b);
@@ -625,10 +657,10 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   if (cs > 1) {                              // release the helpers; stay until they have read the command
     if (tid == 0) sh->cc.cmd = 2;
     __syncthreads();
-    if (tid >= 512 && tid < 512 + 2 * (static_cast<int>(cs) - 1)) {
-      const int e = tid - 512;
-      dsmem_st_v4(dsmem_addr(reinterpret_cast<const uint4*>(&sh->cc) + (e & 1), 1u + static_cast<uint32_t>(e >> 1)),
-                  *(reinterpret_cast<const uint4*>(&sh->cc) + (e & 1)));
+    if (tid >= 960 && tid < 960 + 3 * (static_cast<int>(cs) - 1)) {
+      const int e = tid - 960, part = e % 3;
+      const uint4* src = reinterpret_cast<const uint4*>(&sh->cc) + part;
+      dsmem_st_v4(dsmem_addr(src, 1u + static_cast<uint32_t>(e / 3)), *src);
     }
     __syncthreads();
     if (tid < static_cast<int>(cs) - 1) cmbar_arrive_remote(&sh->mb_tile, 1u + static_cast<uint32_t>(tid));
@@ -921,10 +953,10 @@ __global__ void __launch_bounds__(kTopThreads) topset_write_kernel(const TopsetA
   }
 }
 
-size_t proposals_smem_bytes(int n, bool cache) {
-  size_t b = sizeof(float4) * (kChunk + kMaxPost) + sizeof(uint64_t) * (kChunk + kTile) +
+size_t proposals_smem_bytes(int n, bool cache, int tile) {
+  size_t b = sizeof(float4) * (kChunk + kMaxPost) + sizeof(uint64_t) * (kChunk + 2 * kTile) +
              sizeof(uint32_t) * (kBins + 64) + sizeof(Shared) + sizeof(uint16_t) * kMaxPost +
-             sizeof(float4) * kTile + sizeof(float) * kTile + sizeof(uint16_t) * kPairs;
+             sizeof(float4) * kTile + sizeof(float) * kTile + sizeof(uint16_t) * tile_pairs(tile);
   if (cache) b += sizeof(uint32_t) * static_cast<size_t>(n);
   return (b + 15) & ~static_cast<size_t>(15);
 }
@@ -932,42 +964,49 @@ size_t proposals_smem_bytes(int n, bool cache) {
 static int launch_proposals_kernel(bx_handle* h, ProposalArgs& a, int batch, cudaStream_t st) {
   const bool cache = a.n <= kKeyCacheMax;
   a.cache_keys = cache ? 1 : 0;
-  const size_t smem = proposals_smem_bytes(a.n, cache);
-  BX_REQUIRE(smem <= h->smem_optin, BX_ERR_UNSUPPORTED, "proposals: %zu B shared memory > device limit %zu", smem,
+  const size_t smem64 = proposals_smem_bytes(a.n, cache, 64);
+  BX_REQUIRE(smem64 <= h->smem_optin, BX_ERR_UNSUPPORTED, "proposals: %zu B shared memory > device limit %zu", smem64,
              h->smem_optin);
-  if (cache) {
-    BX_CUDA(cudaFuncSetAttribute(proposals_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // large quotas: the sweep against the kept list dominates -> spread it over a thread-block cluster per image
-    static const int cs_env = getenv("BX_NMS_CLUSTER") ? atoi(getenv("BX_NMS_CLUSTER")) : 0;   // A/B switch
-    int cs = (a.post_nms >= 512) ? 8 : 1;
-    if (cs_env > 0) cs = cs_env > 8 ? 8 : cs_env;
-    for (; cs > 1; cs >>= 1) {             // largest cluster size whose clusters are all co-resident (one wave)
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(batch * cs);
-      cfg.blockDim = dim3(kThreads);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = cs;
-      at[0].val.clusterDim.y = 1;
-      at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      int max_clusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&max_clusters, proposals_kernel<true>, &cfg) != cudaSuccess) {
-        cudaGetLastError();
-        continue;
-      }
-      if (max_clusters < batch && cs_env <= 0) continue;
-      if (max_clusters < 1) continue;
-      BX_CUDA(cudaLaunchKernelEx(&cfg, proposals_kernel<true>, a));
-      break;
+  if (!cache) {
+    BX_CUDA(cudaFuncSetAttribute(proposals_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+    proposals_kernel<false, 64><<<batch, kThreads, smem64, st>>>(a);
+    BX_LAUNCH_CHECK(h);
+    return BX_OK;
+  }
+  // large quotas: the sweep against the kept list dominates -> spread it over a thread-block cluster per image, with
+  // 128-candidate tiles (half the leader <-> helper signalling rounds); small quotas keep 64-candidate tiles on one CTA
+  static const int cs_env = getenv("BX_NMS_CLUSTER") ? atoi(getenv("BX_NMS_CLUSTER")) : 0;   // A/B switch
+  const size_t smem128 = proposals_smem_bytes(a.n, cache, 128);
+  int cs = (a.post_nms >= 512 && smem128 <= h->smem_optin) ? 8 : 1;
+  if (cs_env > 0) cs = cs_env > 8 ? 8 : cs_env;
+  if (cs > 1 && smem128 > h->smem_optin) cs = 1;
+  if (cs > 1) BX_CUDA(cudaFuncSetAttribute(proposals_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128));
+  for (; cs > 1; cs >>= 1) {               // largest cluster size whose clusters are all co-resident (one wave)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(batch * cs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem128;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, proposals_kernel<true, 128>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
     }
-    if (cs == 1) proposals_kernel<true><<<batch, kThreads, smem, st>>>(a);
-  } else {
-    BX_CUDA(cudaFuncSetAttribute(proposals_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    proposals_kernel<false><<<batch, kThreads, smem, st>>>(a);
+    if (max_clusters < batch && cs_env <= 0) continue;
+    if (max_clusters < 1) continue;
+    BX_CUDA(cudaLaunchKernelEx(&cfg, proposals_kernel<true, 128>, a));
+    break;
+  }
+  if (cs == 1) {
+    BX_CUDA(cudaFuncSetAttribute(proposals_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+    proposals_kernel<true, 64><<<batch, kThreads, smem64, st>>>(a);
   }
   BX_LAUNCH_CHECK(h);
   return BX_OK;
