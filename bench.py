@@ -270,8 +270,7 @@ def run_ours(args):
     if world > 1:
         from tf_eager_object_detection_b200.distributed import nccl_comm_ptr
         comm = nccl_comm_ptr()
-        assert comm is not None, 'no ncclComm_t behind the default process group'
-        comm = ctypes.c_void_p(comm)
+        comm = ctypes.c_void_p(comm) if comm is not None else None   # None: torch build without _comm_ptr -> torch collectives
 
     def launch(step):
         s = step % NSTREAM
@@ -281,10 +280,14 @@ def run_ours(args):
                                           ctypes.byref(params), float(w['stride']), P, _lib.POOL_NONE, o[0].data_ptr(),
                                           o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(),
                                           ctypes.c_void_p(streams[s].cuda_stream)))
-        if world > 1:
+        if world > 1 and comm is not None:
             _lib.check(lib.bx_allgather_detections(handles[s], comm, o[0].data_ptr(), o[2].data_ptr(), B, post, 4, world,
                                                    gathered[s][0].data_ptr(), gathered[s][1].data_ptr(),
                                                    ctypes.c_void_p(streams[s].cuda_stream)))
+        elif world > 1:
+            with torch.cuda.stream(streams[s]):
+                dist.all_gather_into_tensor(gathered[s][0], o[0])
+                dist.all_gather_into_tensor(gathered[s][1], o[2])
 
     def barrier():
         if world > 1:
