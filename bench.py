@@ -240,7 +240,7 @@ def run_ours(args):
     lib = _lib.load()
 
     # ---- inputs: NBUF distinct batches resident in HBM, rotated so no step re-reads the previous step's inputs from L2
-    NBUF = 4
+    NBUF = max(4, args.streams)          # one distinct input batch per stream: concurrent steps never share inputs in L2
     host_batches = [make_batch(w, rank * 10000 + k * B) for k in range(NBUF)]
     n = host_batches[0]['anchors'].shape[0]
     fh, fw = host_batches[0]['feat_hw']
@@ -446,7 +446,7 @@ def main():
     ap.add_argument('--steps', type=int, default=1000)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--streams', type=int, default=4, help='steps are issued round-robin over this many CUDA streams')
+    ap.add_argument('--streams', type=int, default=8, help='steps are issued round-robin over this many CUDA streams')
     ap.add_argument('--e2e-steps', type=int, default=20)
     args = ap.parse_args()
     if args.impl == 'reference':
