@@ -248,12 +248,19 @@ def run_ours(args):
     d_in = [dict(deltas=torch.as_tensor(hb['deltas']).to(dev), scores=torch.as_tensor(hb['scores']).to(dev),
                  feat=torch.as_tensor(hb['feat']).to(dev)) for hb in host_batches]
     NSTREAM = max(1, args.streams)
-    # per-image detection records of a step = kept boxes [B,post,4] fp32 + counts [B] int32 (one allocation)
-    rec_bytes = B * post * 16 + ((B * 4 + 15) // 16) * 16
-    recs = [torch.empty((rec_bytes,), dtype=torch.uint8, device=dev) for _ in range(NSTREAM)]
-    outs = [(r[:B * post * 16].view(torch.float32).view(B, post, 4), torch.empty((B, post), dtype=torch.int32, device=dev),
-             r[B * post * 16:B * post * 16 + B * 4].view(torch.int32), torch.empty((B * post, P, P, C), device=dev))
-            for r in recs]
+    # per-image detection records of a step = kept boxes [B,post,4] fp32 + counts [B] int32.  N > 1: the records of G
+    # consecutive steps land in one bucket (a ring of NBK buckets) and are all-gathered together — same bytes, 1/G of the
+    # NCCL launches (the all-gathers of one communicator serialise, so their launch latency is what N > 1 adds per step)
+    G = max(1, args.gather_every) if world > 1 else 1
+    NBK = max(2, (2 * NSTREAM + G - 1) // G + 1)         # a bucket is reused only after >= 2 * NSTREAM later steps
+    bk_boxes = [torch.empty((G * B, post, 4), device=dev) for _ in range(NBK)]
+    bk_counts = [torch.empty((G * B,), dtype=torch.int32, device=dev) for _ in range(NBK)]
+    idx_bufs = [torch.empty((B, post), dtype=torch.int32, device=dev) for _ in range(NSTREAM)]
+    feat_bufs = [torch.empty((B * post, P, P, C), device=dev) for _ in range(NSTREAM)]
+
+    def outs_of(step):
+        b, slot, s = (step // G) % NBK, step % G, step % NSTREAM
+        return (bk_boxes[b][slot * B:(slot + 1) * B], idx_bufs[s], bk_counts[b][slot * B:(slot + 1) * B], feat_bufs[s])
     params = ops.proposal_params(w['image_hw'], post, w['iou_thr'], pre_nms_top_k=w['pre_nms'])
     streams = [torch.cuda.Stream(dev) for _ in range(NSTREAM)]
     handles = []
@@ -264,30 +271,52 @@ def run_ours(args):
 
     # N > 1: the only collective of the path — all-gather of the per-image detection records (kept boxes + counts)
     # bx_allgather_detections on torch's own ncclComm_t: boxes + counts in one fused NCCL group on the step's stream
-    gathered = [(torch.empty((world * B, post, 4), device=dev), torch.empty((world * B,), dtype=torch.int32, device=dev))
-                for _ in range(NSTREAM)] if world > 1 else None
+    gathered = [(torch.empty((world * G * B, post, 4), device=dev), torch.empty((world * G * B,), dtype=torch.int32, device=dev))
+                for _ in range(NBK)] if world > 1 else None
     comm = None
     if world > 1:
         from tf_eager_object_detection_b200.distributed import nccl_comm_ptr
         comm = nccl_comm_ptr()
         comm = ctypes.c_void_p(comm) if comm is not None else None   # None: torch build without _comm_ptr -> torch collectives
+    step_done = {}                                       # step -> event recorded behind its kernels (N > 1)
+    bucket_free = [None] * NBK                           # event behind the last all-gather that read the bucket
 
-    def launch(step):
+    def gather_bucket(last_step, n_in_bucket):
+        """All-gather the bucket whose last filled slot belongs to `last_step`, on that step's stream."""
+        b, s = (last_step // G) % NBK, last_step % NSTREAM
+        for k in range(last_step - n_in_bucket + 1, last_step):
+            ev_k = step_done.pop(k, None)
+            if ev_k is not None:
+                streams[s].wait_event(ev_k)
+        step_done.pop(last_step, None)
+        rows = n_in_bucket * B
+        if comm is not None:
+            _lib.check(lib.bx_allgather_detections(handles[s], comm, bk_boxes[b].data_ptr(), bk_counts[b].data_ptr(), rows,
+                                                   post, 4, world, gathered[b][0].data_ptr(), gathered[b][1].data_ptr(),
+                                                   ctypes.c_void_p(streams[s].cuda_stream)))
+        else:
+            with torch.cuda.stream(streams[s]):
+                dist.all_gather_into_tensor(gathered[b][0][:world * rows], bk_boxes[b][:rows])
+                dist.all_gather_into_tensor(gathered[b][1][:world * rows], bk_counts[b][:rows])
+        ev = torch.cuda.Event(); ev.record(streams[s]); bucket_free[b] = ev
+
+    def launch(step, last_of_run=False):
         s = step % NSTREAM
-        din, o = d_in[step % NBUF], outs[s]
+        din, o = d_in[step % NBUF], outs_of(step)
+        if world > 1 and step % G == 0 and bucket_free[(step // G) % NBK] is not None:
+            for s2 in range(NSTREAM):                    # nobody refills the bucket before its all-gather has read it
+                streams[s2].wait_event(bucket_free[(step // G) % NBK])
+            bucket_free[(step // G) % NBK] = None
         _lib.check(lib.bx_c4_proposal_roi(handles[s], anchors.data_ptr(), din['deltas'].data_ptr(),
                                           din['scores'].data_ptr(), din['feat'].data_ptr(), B, n, fh, fw, C,
                                           ctypes.byref(params), float(w['stride']), P, _lib.POOL_NONE, o[0].data_ptr(),
                                           o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(),
                                           ctypes.c_void_p(streams[s].cuda_stream)))
-        if world > 1 and comm is not None:
-            _lib.check(lib.bx_allgather_detections(handles[s], comm, o[0].data_ptr(), o[2].data_ptr(), B, post, 4, world,
-                                                   gathered[s][0].data_ptr(), gathered[s][1].data_ptr(),
-                                                   ctypes.c_void_p(streams[s].cuda_stream)))
-        elif world > 1:
-            with torch.cuda.stream(streams[s]):
-                dist.all_gather_into_tensor(gathered[s][0], o[0])
-                dist.all_gather_into_tensor(gathered[s][1], o[2])
+        if world > 1:
+            if step % G == G - 1 or last_of_run:
+                gather_bucket(step, step % G + 1)
+            else:
+                ev = torch.cuda.Event(); ev.record(streams[s]); step_done[step] = ev
 
     def barrier():
         if world > 1:
@@ -305,7 +334,7 @@ def run_ours(args):
         for s in streams:
             s.wait_event(e0)
         for k in range(nsteps):
-            launch(first + k)
+            launch(first + k, last_of_run=(k == nsteps - 1))
         for s in streams:
             ev = torch.cuda.Event(); ev.record(s); main.wait_event(ev)
         e1.record(main)
@@ -320,7 +349,7 @@ def run_ours(args):
         e0.record(main)
         streams[0].wait_event(e0)
         for k in range(nsteps):
-            launch((first + k) * saved)          # step index = multiple of NSTREAM -> always stream 0 / handle 0
+            launch((first + k) * saved * G, last_of_run=True)   # multiple of NSTREAM * G -> stream 0, slot 0, own gather
         ev = torch.cuda.Event(); ev.record(streams[0]); main.wait_event(ev)
         e1.record(main)
         barrier()
@@ -348,12 +377,14 @@ def run_ours(args):
     value = world * args.steps * B / (ms_max * 1e-3)
 
     # ---- sanity inside the bench: every image filled its quota (otherwise the work measured is not the workload)
-    for o in outs:
-        assert bool((o[2] == post).all()), 'a step kept fewer than post_nms proposals'
-    if world > 1:                                       # the gathered buffer holds this rank's records at its slot
-        for s_ in range(NSTREAM):
-            assert torch.equal(gathered[s_][0][rank * B:(rank + 1) * B], outs[s_][0]), 'all-gather mismatch (boxes)'
-            assert torch.equal(gathered[s_][1][rank * B:(rank + 1) * B], outs[s_][2]), 'all-gather mismatch (counts)'
+    for c_ in bk_counts if world > 1 else [outs_of(k_)[2] for k_ in range(NSTREAM)]:
+        assert bool((c_ == post).all()), 'a step kept fewer than post_nms proposals'
+    if world > 1:                                       # a gathered bucket holds this rank's records at its slot
+        torch.cuda.synchronize()
+        gather_bucket(G - 1, G)                         # bucket 0, all G slots
+        torch.cuda.synchronize()
+        assert torch.equal(gathered[0][0][rank * G * B:(rank + 1) * G * B], bk_boxes[0]), 'all-gather mismatch (boxes)'
+        assert torch.equal(gathered[0][1][rank * G * B:(rank + 1) * G * B], bk_counts[0]), 'all-gather mismatch (counts)'
 
     # ---- e2e: the public Python API with HOST (pinned) buffers; H2D inputs + D2H outputs inside the timed region
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
@@ -416,7 +447,8 @@ def run_ours(args):
                     scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                     config=dict(workload=w['name'], images_per_step_per_gpu=B, streams=NSTREAM,
                                 parallelism='images sharded over GPUs, no data-path collective; NCCL all-gather of the '
-                                            'per-image detection records each step (bx_allgather_detections on the process group\'s ncclComm_t)' if world > 1 else 'single GPU',
+                                            'per-image detection records, %d steps per bucket (bx_allgather_detections on the process group\'s '
+                                            'ncclComm_t)' % G if world > 1 else 'single GPU',
                                 l2='working set %.0f MB/step (inputs rotate over %d batches, outputs %.0f MB) > 126 MB L2'
                                    % (step_bytes / 1e6, NBUF, B * post * P * P * C * 4 / 1e6),
                                 algorithmic_bytes_per_image=b_prop + b_roi,
@@ -448,6 +480,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--streams', type=int, default=8, help='steps are issued round-robin over this many CUDA streams')
     ap.add_argument('--e2e-steps', type=int, default=20)
+    ap.add_argument('--gather-every', type=int, default=4,
+                    help='N > 1: detection records of this many consecutive steps are all-gathered together')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)
