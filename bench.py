@@ -355,6 +355,7 @@ def run_ours(args):
         barrier()
         return e0.elapsed_time(e1)
 
+    timed(NSTREAM, 0)                                   # priming, not a warm-up step: every stream's handle allocates its workspace
     timed(max(3, args.warmup), 0)                       # warm-up (>= 3 steps)
     launches_w = [int(lib.bx_launch_count(hh)) for hh in handles]
     sampler = ClockSampler(local); sampler.start()
