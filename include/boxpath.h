@@ -12,13 +12,19 @@
  *  - every call returns 0 on success or a negative bx_status; bx_last_error() gives the message of the
  *    last failure on the calling thread.
  *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream);
- *    the library never calls cudaDeviceSynchronize and never frees caller memory.
+ *    the library never calls cudaDeviceSynchronize and never frees caller memory.  Only bx_destroy and
+ *    bx_profile_read wait (on the handle's own stream / events).
+ *  - every call runs on the HANDLE's device whatever the caller's current device is, and leaves the caller's current
+ *    device unchanged (bx_create does not change it either).  A handle is used from one host thread and one stream at a
+ *    time (its workspace is shared by consecutive calls and ordered by that stream); use one handle per stream for
+ *    concurrent streams.
  *  - boxes are (x1, y1, x2, y2) in image pixels, as everywhere on the reference's path.
  *  - no CPU fallback: without a CUDA device bx_create fails and nothing else can be called.
  */
 #ifndef BOXPATH_H_
 #define BOXPATH_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -272,6 +278,19 @@ int bx_allgather_detections(bx_handle* h, void* nccl_comm, const float* records,
 
 /* number of kernels launched by this handle since creation (bench.py "gpu_launches") */
 long long bx_launch_count(const bx_handle* h);
+
+/* Counters and sizes of the handle: out[0] = kernels launched, out[1] = RoI launches served by the TMA band kernel,
+ * out[2] = plain-crop RoI launches that FELL BACK to a gather kernel (shape outside the band kernel's limits: C % 32 != 0,
+ * map too wide for a 3-row band, no cuTensorMapEncodeTiled; about 0.75x the speed — never silent: it is counted here),
+ * out[3..5] = bytes held by the workspace / RoI plan area / host-entry staging area.  Writes min(n, 6) values. */
+int bx_stats(const bx_handle* h, long long* out, int n);
+
+/* Grow the handle's three device areas to at least the given sizes now (stream-ordered on `stream`).  Every entry point
+ * grows them on demand — stream-ordered (cudaMallocAsync / cudaFreeAsync), without synchronising the device — the first
+ * time a call needs more than any earlier call did; bx_reserve() (or one warm-up call of each op at its largest shape)
+ * moves that growth out of the steady state, and is required before a CUDA-graph capture, during which growth is refused
+ * with BX_ERR_UNSUPPORTED.  Read the sizes a workload reached with bx_stats(). */
+int bx_reserve(bx_handle* h, size_t workspace_bytes, size_t plan_bytes, size_t stage_bytes, void* stream);
 
 /* Measurement support (bench.py roofline leg): when enabled, every RoI-pooling launch of this handle is bracketed by a
  * cudaEvent pair recorded on the launch stream (up to `capacity` launches, then recording stops).

@@ -465,15 +465,57 @@ def roi_pool_c4_grad(feat, rois, stride, grad_out, pool_size=7, max_pooling_flag
         return crop_and_resize_grad_image(feat.shape, nb, bi, g)
     q = 2 * pool_size
     crops = crop_and_resize_tf(feat, nb, bi, q, q)
+    return crop_and_resize_grad_image(feat.shape, nb, bi, _max_pool_grad_2x2(crops, g, pool_size))
+
+
+def _max_pool_grad_2x2(crops, g, pool_size):
+    """TF MaxPoolGrad for the 2x2 / stride 2 window: all of it to the first maximal element (row-major)."""
     gc = np.zeros_like(crops)
     n, _, _, c = crops.shape
     for i in range(pool_size):
         for j in range(pool_size):
             win = crops[:, 2 * i:2 * i + 2, 2 * j:2 * j + 2].reshape(n, 4, c)
-            arg = np.argmax(win, axis=1)                       # first maximum
+            arg = np.argmax(win, axis=1)
             for s in range(4):
                 gc[:, 2 * i + s // 2, 2 * j + s % 2] = np.where(arg == s, g[:, i, j], F(0))
-    return crop_and_resize_grad_image(feat.shape, nb, bi, gc)
+    return gc
+
+
+def roi_pool_fpn_grad(feat, rois, image_shape, grad_out, pool_size=7, box_ind=None):
+    """Gradient of roi_pool_fpn (model/roi_pooling.py:15-42: image-normalised boxes, 14x14 crop, 2x2 max pool) w.r.t.
+    feat — what scripts/train.py:99-103 back-propagates through the FPN extractor."""
+    feat = np.asarray(feat, F); g = np.asarray(grad_out, F)
+    r = np.asarray(rois, F)
+    H, W = F(image_shape[0]), F(image_shape[1])
+    bi = np.zeros(r.shape[0], np.int32) if box_ind is None else box_ind
+    nb = np.stack([r[:, 1] / H, r[:, 0] / W, r[:, 3] / H, r[:, 2] / W], axis=1)
+    q = 2 * pool_size
+    crops = crop_and_resize_tf(feat, nb, bi, q, q)
+    return crop_and_resize_grad_image(feat.shape, nb, bi, _max_pool_grad_2x2(crops, g, pool_size))
+
+
+def roi_align_pad_grad(feat, rois, stride, grad_out, pool_size=7, box_ind=None):
+    """Gradient of roi_align_pad (model/roi_pooling.py:93-176) w.r.t. feat: avg_pool gradient (a quarter to each sample),
+    CropAndResizeGradImage on the padded map, then the gradient of tf.pad(SYMMETRIC, 1): each border ring element adds
+    to the element it mirrors (rows first, then columns, the reverse of the padding order)."""
+    feat = np.asarray(feat, F); g = np.asarray(grad_out, F)
+    b = np.asarray(rois, F) / F(stride)
+    b = b + F(1)
+    q = 2 * pool_size
+    x0, y0, x1, y1 = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    sw = (x1 - x0) / F(q); sh = (y1 - y0) / F(q)
+    ph, pw = feat.shape[1] + 2, feat.shape[2] + 2
+    ih, iw = F(ph - 1), F(pw - 1)
+    nx0 = (x0 + sw / F(2) - F(0.5)) / iw; ny0 = (y0 + sh / F(2) - F(0.5)) / ih
+    nb = np.stack([ny0, nx0, ny0 + sh * F(q - 1) / ih, nx0 + sw * F(q - 1) / iw], axis=1).astype(F)
+    bi = np.zeros(b.shape[0], np.int32) if box_ind is None else box_ind
+    gq = (g / F(4))
+    gc = np.repeat(np.repeat(gq, 2, axis=1), 2, axis=2)
+    gp = crop_and_resize_grad_image((feat.shape[0], ph, pw, feat.shape[3]), nb, bi, gc)
+    gp[:, :, 1] += gp[:, :, 0]; gp[:, :, -2] += gp[:, :, -1]
+    gp = gp[:, :, 1:-1]
+    gp[:, 1] += gp[:, 0]; gp[:, -2] += gp[:, -1]
+    return np.ascontiguousarray(gp[:, 1:-1])
 
 
 # --------------------------------------------------------------------------- f3 losses (model/losses.py)

@@ -37,6 +37,14 @@ def _worker(rank, world, port, num_images, kmax, out):
         loc_rec, loc_cnt = bxd.shard_images([rec, counts], rank, world)
         all_rec, all_cnt = bxd.allgather_detections(loc_rec.contiguous(), loc_cnt.contiguous())
         ok = torch.equal(all_rec, rec) and torch.equal(all_cnt, counts)
+        sizes = [hi - lo for lo, hi in (bxd.shard_bounds(num_images, r, world) for r in range(world))]
+        rec2, cnt2 = bxd.allgather_detections(loc_rec.contiguous(), loc_cnt.contiguous(), sizes=sizes)   # static sizes
+        ok = ok and torch.equal(rec2, rec) and torch.equal(cnt2, counts)
+        try:
+            bxd.allgather_detections(loc_rec.contiguous(), loc_cnt.contiguous(), sizes=[1] * world if num_images != world else [2] * world)
+            ok = False                                           # wrong sizes must be rejected
+        except ValueError:
+            pass
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

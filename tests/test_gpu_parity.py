@@ -900,3 +900,205 @@ def test_nms_long_suppression_chains_and_cluster_sweep(bx):
     ref = orc.nms_tf(big, same, 600, 0.7)
     n = int(cnt[0])
     assert n == ref.shape[0] and np.array_equal(idx[0, :n].cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ round-2 parity holes
+def test_nms_iou_threshold_guard_band(bx):
+    """iou_gt() screens `inter / union > thr` without the division when the pair is >= 2e-6 (relative) away from the
+    threshold and falls back to TF's exact fp32 division otherwise.  Pairs whose quotient is exactly the threshold, one
+    ulp above and one ulp below (integer geometry, scaled down to denormal areas) must be decided like the oracle on
+    every code path: the intra-tile pair test (2 boxes), the kept-list test of the single-CTA kernel (64-candidate
+    tiles) and of the cluster kernel (128-candidate tiles, helpers over DSMEM)."""
+    from _nms_cases import near_threshold_cases
+    cases = near_threshold_cases()
+    # 200 disjoint unit fillers score between the two boxes, so box B meets box A through the KEPT list, two tiles later
+    k = np.arange(200, dtype=np.float32)
+    filler = np.stack([1e6 + 3.0 * k, np.full_like(k, 1e6), 1e6 + 1.0 + 3.0 * k, np.full_like(k, 1e6 + 1.0)], axis=1)   # far from every pair
+    fs = (0.8 - k / 1000.0).astype(np.float32)
+    groups = {}
+    for bxs, thr, sup in cases:
+        groups.setdefault(float(thr), []).append((bxs, sup))
+    n_checked = 0
+    for thr, items in groups.items():
+        pair = np.stack([b for b, _ in items]).astype(np.float32)                       # [g,2,4]
+        sc = np.tile(np.float32([0.9, 0.1]), (len(items), 1))
+        idx, cnt = bx.nms(cu(pair), cu(sc), 2, thr)
+        want = np.array([1 if s else 2 for _, s in items])
+        assert np.array_equal(cnt.cpu().numpy(), want), ('intra-tile', thr)
+        big = np.stack([np.concatenate([b[:1], filler, b[1:]]) for b, _ in items]).astype(np.float32)   # [g,202,4]
+        bsc = np.tile(np.concatenate([np.float32([0.9]), fs, np.float32([0.1])]), (len(items), 1))
+        for post in (202, 600):                                                         # single CTA / cluster sweep
+            idx, cnt = bx.nms(cu(big), cu(bsc), post, thr)
+            assert np.array_equal(cnt.cpu().numpy(), want + 200), ('kept list', post, thr)
+            last = idx.cpu().numpy()[np.arange(len(items)), want + 200 - 1]
+            assert np.array_equal(last, np.where(want == 2, 201, 200))
+        for (b, s) in items[:3]:                                                        # and the oracle agrees with `want`
+            assert orc.nms_tf(b, np.float32([0.9, 0.1]), 2, np.float32(thr)).size == (1 if s else 2)
+        n_checked += len(items)
+    assert n_checked == len(cases) > 800
+
+
+def test_cfg5_roi_features_one_image_all_rois(bx):
+    """BASELINE cfg 5 geometry at full channel count: 800x1333, P2 = 200x334 ... P5 = 25x42, C = 256, all 1000 proposals of
+    one image through bx_fpn_roi_features against the oracle's per-level crop + max pool (bit-exact given the rois)."""
+    img = syn.fpn_image(5, 0, (800, 1333), channels=256)
+    ob, oi, oc = bx.proposals(cu(img['anchors']), cu(img['deltas'])[None], cu(img['scores'])[None], (800, 1333), 1000)
+    assert int(oc[0]) == 1000
+    _, idx = orc.region_proposal(img['deltas'], img['anchors'], img['scores'], (800, 1333), 1000)
+    assert np.array_equal(oi[0].cpu().numpy(), idx)
+    feats = [cu(f)[None] for f in img['feats']]
+    assert [tuple(f.shape[1:3]) for f in feats] == [(200, 334), (100, 167), (50, 84), (25, 42)]
+    out, lv, order, counts = bx.fpn_roi_features(feats, ob[0], (800, 1333))
+    rois = ob[0].cpu().numpy()
+    olv, _, oorder = orc.assign_levels(rois)
+    assert np.array_equal(order.cpu().numpy(), oorder) and np.array_equal(lv.cpu().numpy(), olv)
+    got = out.cpu().numpy()
+    pos = 0
+    for l in range(4):
+        k = oorder[olv[oorder] == l + 2]
+        assert int(counts[l]) == k.size
+        if k.size:
+            ref = orc.roi_pool_fpn(img['feats'][l][None], rois[k], (800, 1333), 7)
+            assert np.array_equal(got[pos:pos + k.size], ref), 'level P%d' % (l + 2)
+        pos += k.size
+    assert pos == 1000 and (counts > 0).sum() >= 3
+
+
+def test_cfg2_one_image_all_300_rois_at_c1024(bx):
+    """BASELINE cfg 2 at full channel count: every one of the 300 RoI feature blocks [7,7,1024] of one image, through the
+    composite entry point (TMA band kernel), bit-exact against the oracle."""
+    from tf_eager_object_detection_b200 import _lib
+    img = syn.c4_image(2, 3)
+    s0 = _lib.total_stats()
+    before, fb0 = s0.get('band_launches', 0), s0.get('band_fallbacks', 0)
+    ob, oi, oc, of = bx.c4_proposal_roi(cu(img['anchors']), cu(img['deltas'])[None], cu(img['scores'])[None],
+                                        cu(img['feat'])[None], (600, 1000), 300, pre_nms_top_k=6000)
+    assert int(oc[0]) == 300
+    st = _lib.total_stats()
+    assert st['band_launches'] == before + 1 and st['band_fallbacks'] == fb0        # served by the band kernel, no fallback
+    ref = orc.roi_pool_c4(img['feat'][None], ob[0].cpu().numpy(), 16, 7, False)
+    assert ref.shape == (300, 7, 7, 1024)
+    assert np.array_equal(of.cpu().numpy(), ref)
+
+
+def test_band_fallback_is_counted(bx):
+    """A plain crop outside the band kernel's limits (C % 32 != 0) runs on the gather kernel and is reported by bx_stats."""
+    from tf_eager_object_detection_b200 import _lib
+    rng = np.random.default_rng(9)
+    feat = rng.standard_normal((1, 20, 30, 20), dtype=np.float32)
+    rois = syn.random_rois(rng, 50, (320, 480))
+    s0 = _lib.total_stats()
+    out = bx.roi_pool(_lib.ROI_STRIDE_NORM, _lib.POOL_NONE, 7, cu(feat), cu(rois))
+    s1 = _lib.total_stats()
+    assert s1['band_fallbacks'] == s0.get('band_fallbacks', 0) + 1 and s1['band_launches'] == s0.get('band_launches', 0)
+    assert np.array_equal(out.cpu().numpy(), orc.roi_pool_c4(feat, rois, 16, 7, False))
+
+
+@pytest.mark.parametrize('which', ['image_max', 'align_avg'])
+def test_roi_pool_backward_fpn_and_roialign(bx, which):
+    """bx_roi_pool_grad for the two other extractors: IMAGE_NORM + 2x2 max (the FPN training path,
+    model/roi_pooling.py:15-42) and ALIGN_PAD + 2x2 mean (dormant RoIAlign, :93-176), functional op and autograd hook."""
+    from tf_eager_object_detection_b200 import _lib
+    from tf_eager_object_detection_b200.roi_pooling import RoiPoolingCropAndResize2, RoiPoolingRoiAlign
+    rng = np.random.default_rng(41 + len(which))
+    feat = rng.standard_normal((2, 25, 38, 32), dtype=np.float32)
+    H, W = 400, 608
+    rois = syn.random_rois(rng, 60, (H, W))
+    bi = rng.integers(0, 2, 60).astype(np.int32)
+    g = rng.standard_normal((60, 7, 7, 32), dtype=np.float32)
+    if which == 'image_max':
+        got = bx.roi_pool_grad(_lib.ROI_IMAGE_NORM, _lib.POOL_MAX2, 7, cu(feat), cu(rois), cu(g), image_shape=(H, W), box_ind=cu(bi))
+        ref = orc.roi_pool_fpn_grad(feat, rois, (H, W), g, 7, box_ind=bi)
+        ft = cu(feat[:1]).requires_grad_(True)
+        out = RoiPoolingCropAndResize2(7)((ft, cu(rois), (H, W)))
+        fwd, ref1 = orc.roi_pool_fpn(feat[:1], rois, (H, W), 7), orc.roi_pool_fpn_grad(feat[:1], rois, (H, W), g, 7)
+    else:
+        got = bx.roi_pool_grad(_lib.ROI_ALIGN_PAD, _lib.POOL_AVG2, 7, cu(feat), cu(rois), cu(g), stride=16.0, box_ind=cu(bi))
+        ref = orc.roi_align_pad_grad(feat, rois, 16, g, 7, box_ind=bi)
+        ft = cu(feat[:1]).requires_grad_(True)
+        out = RoiPoolingRoiAlign(7)((ft, cu(rois), 16))
+        fwd, ref1 = orc.roi_align_pad(feat[:1], rois, 16, 7), orc.roi_align_pad_grad(feat[:1], rois, 16, g, 7)
+    close(got.cpu().numpy(), ref, scale=np.abs(ref).max())          # fp32 accumulation order differs from the oracle's
+    close(out.detach().cpu().numpy(), fwd, scale=np.abs(fwd).max())
+    out.backward(cu(g))
+    close(ft.grad.cpu().numpy(), ref1, scale=np.abs(ref1).max())
+
+
+def test_targets_without_ground_truth(bx):
+    """An image with no ground-truth boxes: max_gt == 0 (NULL gt pointer) must behave like gt_counts == 0 — all inside
+    anchors background (label 0), 256 of them sampled, zero targets / inside weights; ProposalTarget pads with background."""
+    from tf_eager_object_detection_b200.anchor_target import AnchorTarget
+    img = syn.c4_image(4, 0, with_features=False)
+    n = img['anchors'].shape[0]
+    perm = np.random.default_rng(3).permutation(n).astype(np.int32)[None]
+    at = AnchorTarget()
+    empty = torch.zeros((1, 0, 4), device='cuda')
+    lab0, tg0, iw0, ow0, c0 = at.call_batched((empty, [600, 1000], cu(img['anchors'])), perm=perm)
+    dummy = torch.zeros((1, 5, 4), device='cuda')
+    lab1, tg1, iw1, ow1, c1 = at.call_batched((dummy, [600, 1000], cu(img['anchors'])), perm=perm,
+                                              gt_counts=torch.zeros(1, dtype=torch.int32, device='cuda'))
+    for x, y in ((lab0, lab1), (tg0, tg1), (iw0, iw1), (ow0, ow1), (c0, c1)):
+        assert torch.equal(x, y)
+    lab = lab0[0].cpu().numpy()
+    assert set(np.unique(lab).tolist()) == {-1.0, 0.0} and int((lab == 0).sum()) == 256
+    assert c0[0].tolist() == [0, 256] and float(tg0.abs().max()) == 0.0 and float(iw0.abs().max()) == 0.0
+    rois = cu(syn.random_rois(np.random.default_rng(4), 300, (600, 1000)))[None]
+    permr = np.random.default_rng(5).permutation(300).astype(np.int32)[None]
+    o = bx.proposal_target(rois, torch.zeros((1, 0, 4), device='cuda'), torch.zeros((1, 0), dtype=torch.int32, device='cuda'),
+                           permr, neg_iou_threshold=0.0)
+    assert int(o[6][0, 0]) == 0 and int(o[6][0, 1]) == 0 and (o[1] == 0).all() and float(o[3].abs().max()) == 0.0
+
+
+def test_cls_loss_rejects_out_of_range_labels(bx):
+    """tf.losses.sparse_softmax_cross_entropy raises (CPU) / yields NaN (GPU) for a label >= num_classes; the library
+    yields NaN — never a silently clamped class."""
+    logits = torch.randn((16, 5), device='cuda')
+    labels = torch.tensor([0, 1, 2, 3, 4, 5, -1, 0] * 2, device='cuda', dtype=torch.float32)
+    loss, grad = bx.cls_loss(logits, labels, with_grad=True)
+    assert torch.isnan(loss) and torch.isnan(grad[5]).all() and not torch.isnan(grad[4]).any()
+    ok = labels.clone(); ok[ok == 5] = 4
+    assert torch.isfinite(bx.cls_loss(logits, ok))
+    from tf_eager_object_detection_b200.prediction import post_ops_prediction
+    with pytest.raises(ValueError):
+        post_ops_prediction(torch.rand((4, 21), device='cuda'), torch.zeros((4, 21, 4), device='cuda'),
+                            torch.zeros((4, 4), device='cuda'), [600, 1000], None, None, num_classes=20)
+
+
+def test_no_hidden_conversions_on_the_device_path(bx, monkeypatch):
+    """Tensor hand-off rules (_tensor.py): well-formed CUDA tensors are borrowed zero-copy — the conversion counters stay
+    at zero — and BX_STRICT=1 turns every upload / cast / compaction into a TypeError."""
+    from tf_eager_object_detection_b200 import _tensor
+    img = syn.c4_image(2, 0, channels=32)
+    a, d, s, f = cu(img['anchors']), cu(img['deltas'])[None], cu(img['scores'])[None], cu(img['feat'])[None]
+    before = dict(_tensor.CONVERSIONS)
+    bx.c4_proposal_roi(a, d, s, f, (600, 1000), 300, pre_nms_top_k=6000)
+    assert _tensor.CONVERSIONS == before
+    bx.nms(img['anchors'], img['scores'], 10, 0.7)                    # numpy inputs: uploaded, and counted
+    assert _tensor.CONVERSIONS['uploads'] == before['uploads'] + 2
+    monkeypatch.setenv('BX_STRICT', '1')
+    with pytest.raises(TypeError):
+        bx.nms(img['anchors'], img['scores'], 10, 0.7)
+    with pytest.raises(TypeError):
+        bx.nms(a.double(), s[0], 10, 0.7)
+    with pytest.raises(TypeError):
+        bx.roi_pool(0, 0, 7, f.permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2), a[:8].clone())
+    bx.c4_proposal_roi(a, d, s, f, (600, 1000), 300, pre_nms_top_k=6000)   # the well-formed call still passes
+
+
+def test_calls_run_on_the_handles_device_not_the_current_one():
+    """A handle created for cuda:1 launches on cuda:1 (and allocates its workspace there) while cuda:0 is current, and
+    neither bx_create nor the calls change the caller's current device.  Needs 2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import tf_eager_object_detection_b200.ops as ops
+    torch.cuda.set_device(0)
+    img = syn.fpn_image(3, 1, with_features=False)
+    dev1 = torch.device('cuda', 1)
+    a = torch.as_tensor(img['anchors']).to(dev1); d = torch.as_tensor(img['deltas']).to(dev1)[None]
+    s = torch.as_tensor(img['scores']).to(dev1)[None]
+    ob, oi, oc = ops.proposals(a, d, s, (600, 1000), 1000)            # top-set path: workspace allocation + memsets + 8 launches
+    assert torch.cuda.current_device() == 0 and ob.device == dev1
+    _, idx = orc.region_proposal(img['deltas'], img['anchors'], img['scores'], (600, 1000), 1000)
+    assert np.array_equal(oi[0].cpu().numpy(), idx)
+    x = torch.empty(4, device='cuda')
+    assert x.device.index == 0

@@ -212,3 +212,59 @@ def test_anchor_generator_mirror_host_tables(golden):
     off = ag._offsets(32, (1.0,), (0.5, 1.0, 2.0))
     lvl = syn.fpn_level_anchors(32, 1, 1, 4)                    # one cell at the origin = the offsets themselves
     assert np.array_equal(off, lvl)
+
+
+def _dense_crop(ft, ys, xs, h, w):
+    """Differentiable crop_and_resize of one box by dense bilinear weight matrices (float64): ft [h,w,c] torch tensor,
+    ys / xs = sample coordinates in pixels; samples outside [0,h-1] x [0,w-1] contribute 0."""
+    import torch
+    wy = torch.zeros(len(ys), h, dtype=torch.float64); wx = torch.zeros(len(xs), w, dtype=torch.float64)
+    for i, y in enumerate(ys):
+        if 0 <= y <= h - 1:
+            t = int(np.floor(y)); wy[i, t] += 1 - (y - t); wy[i, int(np.ceil(y))] += y - t
+    for i, x in enumerate(xs):
+        if 0 <= x <= w - 1:
+            t = int(np.floor(x)); wx[i, t] += 1 - (x - t); wx[i, int(np.ceil(x))] += x - t
+    return torch.einsum('yh,xw,hwc->yxc', wy, wx, ft)
+
+
+def test_fpn_and_roialign_gradients_against_torch_autograd():
+    """The two other extractor gradients (FPN: image-normalised boxes + 2x2 max; dormant RoIAlign: symmetric pad + 2x2
+    mean) against torch autograd through a dense restatement — the oracle functions the GPU backward tests compare with."""
+    import torch
+    import torch.nn.functional as tnf
+    rng = np.random.default_rng(6)
+    fh, fw, c, P = 10, 13, 3, 3
+    feat = rng.standard_normal((1, fh, fw, c), dtype=np.float32)
+    H, W = 160, 208
+    rois = syn.random_rois(rng, 7, (H, W))
+    go = rng.standard_normal((7, P, P, c), dtype=np.float32)
+    q = 2 * P
+    # FPN extractor
+    ft = torch.tensor(feat, dtype=torch.float64, requires_grad=True)
+    crops = []
+    for k in range(7):
+        r = rois[k].astype(np.float32)
+        y1, y2 = np.float64(r[1] / np.float32(H)), np.float64(r[3] / np.float32(H))
+        x1, x2 = np.float64(r[0] / np.float32(W)), np.float64(r[2] / np.float32(W))
+        ys = y1 * (fh - 1) + np.arange(q) * ((y2 - y1) * (fh - 1) / (q - 1))
+        xs = x1 * (fw - 1) + np.arange(q) * ((x2 - x1) * (fw - 1) / (q - 1))
+        crops.append(_dense_crop(ft[0], ys, xs, fh, fw))
+    out = tnf.max_pool2d(torch.stack(crops).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    np.testing.assert_allclose(orc.roi_pool_fpn(feat, rois, (H, W), P), out.detach().numpy(), rtol=1e-4, atol=1e-5)
+    out.backward(torch.tensor(go, dtype=torch.float64))
+    np.testing.assert_allclose(orc.roi_pool_fpn_grad(feat, rois, (H, W), go, P), ft.grad.numpy(), rtol=1e-4, atol=1e-5)
+    # RoIAlign variant: pad (replicate == SYMMETRIC for a 1-pixel border), tensorpack sample centres, mean pool
+    ft = torch.tensor(feat, dtype=torch.float64, requires_grad=True)
+    padded = tnf.pad(ft[0].permute(2, 0, 1)[None], (1, 1, 1, 1), mode='replicate')[0].permute(1, 2, 0)
+    crops = []
+    for k in range(7):
+        b = rois[k].astype(np.float64) / 16.0 + 1.0
+        sw, sh = (b[2] - b[0]) / q, (b[3] - b[1]) / q
+        xs = b[0] + sw / 2 - 0.5 + np.arange(q) * sw
+        ys = b[1] + sh / 2 - 0.5 + np.arange(q) * sh
+        crops.append(_dense_crop(padded, ys, xs, fh + 2, fw + 2))
+    out = tnf.avg_pool2d(torch.stack(crops).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    np.testing.assert_allclose(orc.roi_align_pad(feat, rois, 16, P), out.detach().numpy(), rtol=1e-4, atol=1e-5)
+    out.backward(torch.tensor(go, dtype=torch.float64))
+    np.testing.assert_allclose(orc.roi_align_pad_grad(feat, rois, 16, go, P), ft.grad.numpy(), rtol=1e-4, atol=1e-5)

@@ -46,6 +46,8 @@ SIGNATURES = {
     'bx_create': (c_int, [c_int, POINTER(c_void_p)]),
     'bx_destroy': (c_int, [c_void_p]),
     'bx_launch_count': (c_longlong, [c_void_p]),
+    'bx_stats': (c_int, [c_void_p, POINTER(c_longlong), c_int]),
+    'bx_reserve': (c_int, [c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, c_void_p]),
     'bx_profile_roi': (c_int, [c_void_p, c_int, c_int]),
     'bx_profile_read': (c_int, [c_void_p, POINTER(c_float), c_int, POINTER(c_int)]),
     'bx_dlpack_data': (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_int64), c_int, POINTER(c_void_p)]),
@@ -129,21 +131,83 @@ def check(rc):
     raise BoxpathError(msg)
 
 
+class _ThreadHandles:
+    """The bx_handle* objects of one host thread; destroyed (workspaces freed) when the thread ends or at exit."""
+
+    def __init__(self):
+        self.by_key = {}
+
+    def close(self):
+        lib = _lib
+        for key, h in list(self.by_key.items()):
+            _handles.pop(key, None)
+            if lib is not None:
+                try:
+                    lib.bx_destroy(h)
+                except Exception:
+                    pass
+        self.by_key.clear()
+
+    def __del__(self):
+        self.close()
+
+
+_tls = threading.local()
+_all_sets = []
+
+
 def handle(device_index, stream=0):
     """bx_handle* for (device, calling thread, stream) — SURVEY §8b: one handle per (device, host thread); keyed by the
-    stream as well so that calls issued on different streams never share a workspace."""
+    stream as well so that calls issued on different streams never share a workspace.  Handles are destroyed with their
+    thread (thread-local owner) and at interpreter exit."""
     key = (int(device_index), threading.get_ident(), int(stream or 0))
     h = _handles.get(key)
     if h is None:
         lib = load()
         out = c_void_p()
         check(lib.bx_create(int(device_index), ctypes.byref(out)))
-        h = _handles[key] = out
+        owner = getattr(_tls, 'owner', None)
+        if owner is None:
+            owner = _tls.owner = _ThreadHandles()
+            import weakref
+            _all_sets.append(weakref.ref(owner))
+        h = _handles[key] = owner.by_key[key] = out
     return h
+
+
+def destroy_handles():
+    """Destroy every cached handle (all threads).  Registered with atexit; callable from tests."""
+    for ref in list(_all_sets):
+        owner = ref()
+        if owner is not None:
+            owner.close()
+    del _all_sets[:]
+    _handles.clear()
+
+
+import atexit  # noqa: E402
+atexit.register(destroy_handles)
 
 
 def launch_count(device_index):
     return int(load().bx_launch_count(handle(device_index)))
+
+
+def stats(h):
+    """bx_stats of a handle as a dict (launches, band_launches, band_fallbacks, workspace / plan / stage bytes)."""
+    buf = (c_longlong * 6)()
+    check(load().bx_stats(h, buf, 6))
+    return dict(zip(('launches', 'band_launches', 'band_fallbacks', 'ws_bytes', 'plan_bytes', 'stage_bytes'),
+                    [int(v) for v in buf]))
+
+
+def total_stats():
+    """Sum of stats() over every live handle of the process."""
+    tot = {}
+    for h in list(_handles.values()):
+        for k, v in stats(h).items():
+            tot[k] = tot.get(k, 0) + v
+    return tot
 
 
 def f4(values):

@@ -1,5 +1,15 @@
-"""Zero-copy tensor hand-off: any object exposing `__dlpack__` (torch CUDA tensors here; a TF>=2.2 EagerTensor through
-tf.experimental.dlpack in the reference's world) -> DLTensor* -> validated device pointer (bx_dlpack_data).
+"""Tensor hand-off between the host framework and the C ABI.
+
+Rules (DESIGN.md §1 "Boundary"):
+  * a CUDA tensor of the expected dtype, C-contiguous and suitably aligned is BORROWED zero-copy — torch tensors by their
+    storage pointer after the same checks bx_dlpack_data makes, any other `__dlpack__` producer (a TF >= 2.2 EagerTensor
+    through tf.experimental.dlpack in the reference's world), or every tensor under BX_FORCE_DLPACK=1, through a DLPack
+    capsule validated by bx_dlpack_data;
+  * everything else is normalised HERE, in the Python layer, before the C ABI sees it, and counted in `CONVERSIONS`:
+    host data (numpy / lists / CPU tensors) is uploaded ("uploads" — feeding a numpy array to a TF op), other dtypes are
+    cast ("casts" — the reference's own tf.to_float / tf.to_int32), non-contiguous views are compacted ("compactions");
+    BX_STRICT=1 turns each of them into a TypeError instead, for callers that want to prove their path makes none;
+  * the C ABI itself never copies or converts: bx_dlpack_data rejects wrong device / dtype / strides / alignment.
 
 torch is used for device memory (output allocation), streams and nothing else."""
 import ctypes
@@ -25,17 +35,33 @@ def require_cuda():
                                 '(hand-written sm_100a kernels; no CPU fallback)')
 
 
+CONVERSIONS = {'uploads': 0, 'casts': 0, 'compactions': 0}
+
+
+def strict():
+    return os.environ.get('BX_STRICT', '') not in ('', '0')
+
+
+def _converted(kind, what):
+    if strict():
+        raise TypeError('BX_STRICT: %s (%s) would need a copy before the C ABI' % (what, kind))
+    CONVERSIONS[kind] += 1
+
+
 def to_device(x, dtype, device=None):
-    """Inputs may arrive as torch tensors (kept as they are, zero-copy) or as numpy / lists (copied host->device,
-    as feeding a numpy array to a TF op would)."""
+    """Normalise one input for the C ABI: torch CUDA tensors of the right dtype pass through untouched (zero-copy);
+    host data is uploaded and other dtypes are cast — explicitly, and counted in CONVERSIONS (module docstring)."""
     if isinstance(x, torch.Tensor):
         if not x.is_cuda:
             require_cuda()
+            _converted('uploads', 'CPU tensor')
             x = x.cuda(device)
         if x.dtype != dtype:
+            _converted('casts', 'dtype %s -> %s' % (x.dtype, dtype))
             x = x.to(dtype)
         return x.detach() if x.requires_grad else x
     require_cuda()
+    _converted('uploads', type(x).__name__)
     np_dtype = {torch.float32: np.float32, torch.int32: np.int32}[dtype]
     return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np_dtype)), device=device or 'cuda')
 
@@ -63,6 +89,7 @@ class Borrow:
         if t is None:
             return None
         if isinstance(t, torch.Tensor) and not t.is_contiguous():
+            _converted('compactions', 'non-contiguous view %s' % (tuple(t.stride()),))
             t = t.contiguous()
             self._caps.append(t)
         if isinstance(t, torch.Tensor) and not self._dlpack:

@@ -14,25 +14,53 @@ void bx_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int reserve(void** p, size_t* cur, size_t bytes) {
+// Workspace growth is stream-ordered (cudaMallocAsync / cudaFreeAsync on the caller's stream): no device-wide
+// synchronisation, other streams and other handles keep running.  It happens only when a call needs more than any
+// earlier call of the handle did (bx_reserve() sizes everything up front, e.g. before a CUDA-graph capture, during which
+// growth is refused).  If the handle was last used on a different stream, the free is ordered behind that stream too.
+static int reserve(bx_handle* h, void** p, size_t* cur, size_t bytes, cudaStream_t st) {
   if (*cur >= bytes) return BX_OK;
-  // growth only: happens on the first call of a given problem size, never in steady state
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cudaGetLastError();
+  BX_REQUIRE(cap == cudaStreamCaptureStatusNone, BX_ERR_UNSUPPORTED,
+             "workspace growth (%zu -> %zu bytes) during CUDA-graph capture: run the call once, or bx_reserve(), before capturing",
+             *cur, bytes);
   size_t want = bytes + (bytes >> 2);
   want = (want + 0xFFFFF) & ~static_cast<size_t>(0xFFFFF);
   if (*p) {
-    BX_CUDA(cudaDeviceSynchronize());  // the old block may still be in use by enqueued kernels
-    BX_CUDA(cudaFree(*p));
+    if (h->last_stream_valid && h->last_stream != st) {          // the old block may still be in use over there
+      cudaEvent_t ev;
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+        if (cudaEventRecord(ev, h->last_stream) == cudaSuccess) cudaStreamWaitEvent(st, ev, 0);
+        cudaEventDestroy(ev);
+      }
+      cudaGetLastError();                                        // a destroyed stream has nothing pending
+    }
+    BX_CUDA(cudaFreeAsync(*p, st));
     *p = nullptr;
     *cur = 0;
   }
-  BX_CUDA(cudaMalloc(p, want));
+  BX_CUDA(cudaMallocAsync(p, want, st));
   *cur = want;
   return BX_OK;
 }
 
-int bx_ws_reserve(bx_handle* h, size_t bytes) { return reserve(&h->ws, &h->ws_bytes, bytes); }
-int bx_stage_reserve(bx_handle* h, size_t bytes) { return reserve(&h->stage, &h->stage_bytes, bytes); }
-int bx_plan_reserve(bx_handle* h, size_t bytes) { return reserve(&h->plan, &h->plan_bytes, bytes); }
+int bx_ws_reserve(bx_handle* h, size_t bytes, cudaStream_t st) { return reserve(h, &h->ws, &h->ws_bytes, bytes, st); }
+int bx_stage_reserve(bx_handle* h, size_t bytes, cudaStream_t st) { return reserve(h, &h->stage, &h->stage_bytes, bytes, st); }
+int bx_plan_reserve(bx_handle* h, size_t bytes, cudaStream_t st) { return reserve(h, &h->plan, &h->plan_bytes, bytes, st); }
+
+BxEnter::BxEnter(bx_handle* h, void* stream) : prev_(-1) {
+  if (!h) return;
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur != h->device) {
+    if (cudaSetDevice(h->device) == cudaSuccess) prev_ = cur;
+  }
+  h->last_stream = static_cast<cudaStream_t>(stream);
+  h->last_stream_valid = 1;
+}
+BxEnter::~BxEnter() {
+  if (prev_ >= 0) cudaSetDevice(prev_);
+}
 
 extern "C" int bx_version(void) { return BX_VERSION; }
 extern "C" const char* bx_last_error(void) { return g_err; }
@@ -48,8 +76,7 @@ extern "C" int bx_create(int device, bx_handle** out) {
     return BX_ERR_CUDA;
   }
   BX_REQUIRE(device >= 0 && device < count, BX_ERR_INVALID, "bx_create: device %d not in [0, %d)", device, count);
-  BX_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
+  cudaDeviceProp prop;                               // no cudaSetDevice: the caller's current device stays what it was
   BX_CUDA(cudaGetDeviceProperties(&prop, device));
   BX_REQUIRE(prop.major >= 10, BX_ERR_UNSUPPORTED, "bx_create: device %d is sm_%d%d; libboxpath is built for sm_100a only",
              device, prop.major, prop.minor);
@@ -65,12 +92,35 @@ extern "C" int bx_create(int device, bx_handle** out) {
 
 extern "C" int bx_destroy(bx_handle* h) {
   if (!h) return BX_OK;
-  cudaSetDevice(h->device);
-  if (h->ws) cudaFree(h->ws);
-  if (h->stage) cudaFree(h->stage);
-  if (h->plan) cudaFree(h->plan);
-  bx_profile_roi(h, 0, 0);
+  {
+    BxEnter guard(h, h->last_stream_valid ? h->last_stream : nullptr);
+    // stream-ordered frees behind the handle's last stream, then wait for them: after bx_destroy nothing of the handle
+    // is in flight
+    cudaStream_t st = h->last_stream_valid ? h->last_stream : nullptr;
+    if (h->ws) cudaFreeAsync(h->ws, st);
+    if (h->stage) cudaFreeAsync(h->stage, st);
+    if (h->plan) cudaFreeAsync(h->plan, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) cudaGetLastError();
+    bx_profile_roi(h, 0, 0);
+  }
   delete h;
+  return BX_OK;
+}
+
+extern "C" int bx_reserve(bx_handle* h, size_t workspace_bytes, size_t plan_bytes, size_t stage_bytes, void* stream) {
+  BX_REQUIRE(h, BX_ERR_INVALID, "bx_reserve: NULL handle");
+  BxEnter guard(h, stream);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = bx_ws_reserve(h, workspace_bytes, st)) return rc;
+  if (int rc = bx_plan_reserve(h, plan_bytes, st)) return rc;
+  return bx_stage_reserve(h, stage_bytes, st);
+}
+
+extern "C" int bx_stats(const bx_handle* h, long long* out, int n) {
+  BX_REQUIRE(h && out && n >= 0, BX_ERR_INVALID, "bx_stats: NULL argument");
+  const long long v[6] = {h->launches, h->band_launches, h->band_fallbacks, static_cast<long long>(h->ws_bytes),
+                          static_cast<long long>(h->plan_bytes), static_cast<long long>(h->stage_bytes)};
+  for (int i = 0; i < n && i < 6; ++i) out[i] = v[i];
   return BX_OK;
 }
 
@@ -146,6 +196,7 @@ extern "C" int bx_c4_proposal_roi(bx_handle* h, const float* anchors, const floa
                                   const float* feat, int batch, int n, int fh, int fw, int c,
                                   const bx_proposal_params* p, float stride, int pool_size, int pool, float* out_rois,
                                   int* out_idx, int* out_count, float* out_feat, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(p, BX_ERR_INVALID, "bx_c4_proposal_roi: NULL params");
   int rc = bx_proposals(h, anchors, deltas, scores, batch, n, p, out_rois, out_idx, out_count, stream);
   if (rc) return rc;
@@ -158,6 +209,7 @@ extern "C" int bx_c4_proposal_roi_host(bx_handle* h, const float* anchors_dev, c
                                        int fw, int c, const bx_proposal_params* p, float stride, int pool_size,
                                        int pool, float* out_rois_host, int* out_idx_host, int* out_count_host,
                                        float* out_feat_host, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && p && deltas_host && scores_host && feat_host && out_rois_host && out_idx_host && out_count_host &&
                  out_feat_host, BX_ERR_INVALID, "bx_c4_proposal_roi_host: NULL argument");
   BX_REQUIRE(batch > 0 && n > 0 && fh > 0 && fw > 0 && c > 0 && pool_size > 0, BX_ERR_INVALID,
@@ -169,7 +221,7 @@ extern "C" int bx_c4_proposal_roi_host(bx_handle* h, const float* anchors_dev, c
   const size_t k = static_cast<size_t>(batch) * p->post_nms;
   const size_t b_rois = up(sizeof(float) * 4 * k), b_idx = up(sizeof(int) * k), b_cnt = up(sizeof(int) * batch);
   const size_t b_out = up(sizeof(float) * k * pool_size * pool_size * c);
-  int rc = bx_stage_reserve(h, b_deltas + b_scores + b_feat + b_rois + b_idx + b_cnt + b_out);
+  int rc = bx_stage_reserve(h, b_deltas + b_scores + b_feat + b_rois + b_idx + b_cnt + b_out, st);
   if (rc) return rc;
   char* base = static_cast<char*>(h->stage);
   float* d_deltas = reinterpret_cast<float*>(base); base += b_deltas;
@@ -224,6 +276,7 @@ bool nccl_resolve() {
 extern "C" int bx_allgather_detections(bx_handle* h, void* nccl_comm, const float* records, const int* counts,
                                        int b_local, int kmax, int fields, int world, float* out_records,
                                        int* out_counts, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && nccl_comm && out_records && out_counts, BX_ERR_INVALID, "bx_allgather_detections: NULL argument");
   BX_REQUIRE(b_local >= 0 && kmax >= 0 && fields > 0 && world >= 1, BX_ERR_INVALID, "bx_allgather_detections: bad size");
   BX_REQUIRE(b_local == 0 || (records && counts), BX_ERR_INVALID, "bx_allgather_detections: NULL input");

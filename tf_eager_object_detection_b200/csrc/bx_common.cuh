@@ -24,6 +24,10 @@ struct bx_handle {
   long long dbg_count;
   int dbg_info[4];
   long long launches;
+  long long band_launches;       // RoI launches served by the TMA band kernel ...
+  long long band_fallbacks;      // ... and plain-crop launches that fell back to a gather kernel (bx_stats)
+  cudaStream_t last_stream;      // stream of the handle's latest call (orders workspace frees, bx_destroy)
+  int last_stream_valid;
   // optional event bracketing of the RoI-pooling kernel (bx_profile_roi)
   cudaEvent_t* prof_ev;   // 2 * prof_cap events
   int prof_cap;
@@ -32,9 +36,21 @@ struct bx_handle {
 };
 
 void bx_set_error(const char* fmt, ...);
-int bx_ws_reserve(bx_handle* h, size_t bytes);       // ensure h->ws has >= bytes (may cudaMalloc; not in steady state)
-int bx_stage_reserve(bx_handle* h, size_t bytes);
-int bx_plan_reserve(bx_handle* h, size_t bytes);
+// ensure the handle's workspace / staging area / plan area has >= bytes (stream-ordered growth, never a device sync)
+int bx_ws_reserve(bx_handle* h, size_t bytes, cudaStream_t st);
+int bx_stage_reserve(bx_handle* h, size_t bytes, cudaStream_t st);
+int bx_plan_reserve(bx_handle* h, size_t bytes, cudaStream_t st);
+
+// First statement of every entry point that takes a handle: makes the handle's device current for the duration of the
+// call (kernels, memsets and allocations land on h->device whatever the caller's current device is) and restores the
+// caller's device on return; remembers the stream for stream-ordered workspace retirement.  NULL handle: no-op.
+struct BxEnter {
+  BxEnter(bx_handle* h, void* stream);
+  ~BxEnter();
+  BxEnter(const BxEnter&) = delete;
+  BxEnter& operator=(const BxEnter&) = delete;
+  int prev_;
+};
 int bx_internal_nms_keys(bx_handle* h, const float* boxes, const uint32_t* keys, int batch, int n, int max_out,
                          float iou_threshold, float* out_boxes, int* out_idx, int* out_count, cudaStream_t st);
 

@@ -97,8 +97,10 @@ __global__ void __launch_bounds__(kThreads) cls_loss_kernel(const ClsArgs a) {
     for (int k = 1; k < a.c; ++k) m = fmaxf(m, x[k]);
     float se = 0.0f;
     for (int k = 0; k < a.c; ++k) se += expf(x[k] - m);
-    const int li = min(static_cast<int>(lab), a.c - 1);                   // tf.to_int32 truncates
-    acc += static_cast<double>((logf(se) - (x[li] - m)) * a.weight);
+    const int li = static_cast<int>(lab);                                 // tf.to_int32 truncates
+    // a label >= c is invalid: tf.losses.sparse_softmax_cross_entropy raises on the CPU and yields NaN on the GPU; the
+    // loss (and that row's gradient) is NaN here, never a silently clamped class
+    acc += (li < a.c) ? static_cast<double>((logf(se) - (x[li] - m)) * a.weight) : static_cast<double>(nanf(""));
     ++cnt;
   }
   cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -134,14 +136,18 @@ __global__ void __launch_bounds__(kThreads) cls_grad_kernel(const ClsArgs a) {
     for (int k = 1; k < a.c; ++k) m = fmaxf(m, x[k]);
     float se = 0.0f;
     for (int k = 0; k < a.c; ++k) se += expf(x[k] - m);
-    const int li = min(static_cast<int>(lab), a.c - 1);
+    const int li = static_cast<int>(lab);
+    if (li >= a.c) {
+      for (int k = 0; k < a.c; ++k) g[k] = nanf("");
+      continue;
+    }
     for (int k = 0; k < a.c; ++k) g[k] = (expf(x[k] - m) / se - (k == li ? 1.0f : 0.0f)) * scale;
   }
 }
 
 int reduce_ws(bx_handle* h, int grid, ReduceWs* ws, int** d_count, cudaStream_t st) {
   const size_t bytes = static_cast<size_t>(grid) * (sizeof(double) + sizeof(int)) + 64;
-  if (int rc = bx_ws_reserve(h, bytes)) return rc;
+  if (int rc = bx_ws_reserve(h, bytes, st)) return rc;
   char* p = static_cast<char*>(h->ws);
   ws->partial = reinterpret_cast<double*>(p);
   ws->ticket = reinterpret_cast<unsigned int*>(p + static_cast<size_t>(grid) * sizeof(double));
@@ -156,6 +162,7 @@ int reduce_ws(bx_handle* h, int grid, ReduceWs* ws, int** d_count, cudaStream_t 
 extern "C" int bx_smooth_l1_loss(bx_handle* h, const float* pred, const float* target, const float* in_w,
                                  const float* out_w, long long n, int d, float sigma, int reduce_all, float* out_loss,
                                  float* out_grad, void* stream) {
+  BxEnter guard(h, stream);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BX_REQUIRE(h && out_loss, BX_ERR_INVALID, "bx_smooth_l1_loss: null handle / output");
   BX_REQUIRE(n >= 0 && d >= 1 && sigma > 0.0f, BX_ERR_INVALID, "bx_smooth_l1_loss: n >= 0, d >= 1, sigma > 0 required");
@@ -174,6 +181,7 @@ extern "C" int bx_smooth_l1_loss(bx_handle* h, const float* pred, const float* t
 
 extern "C" int bx_cls_loss(bx_handle* h, const float* logits, const float* labels, int n, int c, float weight,
                            float* out_loss, int* out_count, float* out_grad, void* stream) {
+  BxEnter guard(h, stream);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BX_REQUIRE(h && out_loss, BX_ERR_INVALID, "bx_cls_loss: null handle / output");
   BX_REQUIRE(n >= 0 && c >= 1, BX_ERR_INVALID, "bx_cls_loss: n >= 0, c >= 1 required");

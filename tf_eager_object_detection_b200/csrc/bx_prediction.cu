@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(1024) prediction_topk_kernel(const TopkArgs a)
 extern "C" int bx_post_ops_prediction(bx_handle* h, const float* scores, const float* deltas, const float* rois,
                                       const int* roi_counts, int batch, int r, const bx_prediction_params* p,
                                       float* out_det, int* out_count, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && scores && deltas && rois && p && out_det && out_count, BX_ERR_INVALID,
              "bx_post_ops_prediction: NULL argument");
   BX_REQUIRE(batch >= 0 && r >= 0 && p->num_classes >= 2, BX_ERR_INVALID, "bx_post_ops_prediction: bad size");
@@ -123,7 +124,7 @@ extern "C" int bx_post_ops_prediction(bx_handle* h, const float* scores, const f
   const size_t b_boxes = up(pairs * rr * sizeof(float4)), b_keys = up(pairs * rr * sizeof(uint32_t));
   const size_t b_kbox = up(pairs * p->max_per_class * sizeof(float4)), b_kidx = up(pairs * p->max_per_class * sizeof(int));
   const size_t b_kcnt = up(pairs * sizeof(int));
-  int rc = bx_ws_reserve(h, b_boxes + b_keys + b_kbox + b_kidx + b_kcnt);
+  int rc = bx_ws_reserve(h, b_boxes + b_keys + b_kbox + b_kidx + b_kcnt, st);
   if (rc) return rc;
   char* base = static_cast<char*>(h->ws);
   float4* ws_boxes = reinterpret_cast<float4*>(base); base += b_boxes;

@@ -35,6 +35,18 @@ constexpr int tile_pairs(int t) { return t * (t - 1) / 2; }   // unordered candi
 constexpr int kUnroll = 8;          // independent key loads in flight per thread in the streaming passes
 constexpr int kKeyCacheMax = 24576; // keys cached in smem when n <= this (C4 600x1000: 21 546)
 
+// IoU threshold with the two screening constants of iou_gt() below
+struct IouThr {
+  float thr, hi, lo;
+};
+__host__ inline IouThr make_iou_thr(float thr) {
+  IouThr t;
+  t.thr = thr;
+  const bool screen = thr >= 1e-6f;
+  t.hi = screen ? thr * 1.000002f : 0.0f;
+  t.lo = screen ? thr * 0.999998f : 0.0f;
+  return t;
+}
 struct ProposalArgs {
   const float4* anchors;  // [n] (shared) — decode mode
   const float4* deltas;   // [batch,n] — decode mode
@@ -45,7 +57,7 @@ struct ProposalArgs {
   BoxCodec codec;
   int pre_nms_top_k;
   int post_nms;
-  float thr;
+  IouThr thr;
   float4* out_boxes;      // [batch,post_nms] or null
   int* out_idx;           // [batch,post_nms]
   int* out_count;         // [batch]
@@ -88,10 +100,19 @@ __device__ __forceinline__ uint64_t composite(uint32_t key, uint32_t idx) {
   return (static_cast<uint64_t>(key) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
 }
 
-// TF NonMaxSuppressionV3 IoU test on min/max-normalised corners (x=lo0,y=lo1,z=hi0,w=hi1); every shortcut is
-// decision-equivalent to TF's fp32 test.  (Measured: extra early-out branches — per-axis disjointness, area ratio — make
+// TF NonMaxSuppressionV3 IoU test on min/max-normalised corners (x=lo0,y=lo1,z=hi0,w=hi1).  TF decides
+// `inter / (area_a + area_b - inter) > thr` with one correctly rounded fp32 division; that exact test is the fallback
+// below.  In front of it sits a division-free screen that is decision-EQUIVALENT (not an approximation):
+//   thr_hi = fl(thr * 1.000002f), thr_lo = fl(thr * 0.999998f)  (host; both 0 when thr < 1e-6, which disables the screen)
+//   p_hi = fl(thr_hi * uni) >= thr * uni * (1 + 2e-6)(1 - 2^-24)^2 > thr * uni * (1 + 1.8e-6)
+//   inter > p_hi  =>  inter / uni > thr (1 + 1.8e-6)  =>  fl(inter / uni) >= thr (1 + 1.8e-6)(1 - 2^-24) > thr
+//   inter < p_lo  =>  inter / uni < thr (1 - 1.8e-6)  =>  fl(inter / uni) <= thr (1 - 1.8e-6)(1 + 2^-24) < thr
+// The bounds need normal-range products (relative rounding error 2^-24); `p_lo >= 1e-30f` guarantees that for p_lo and
+// p_hi, so tiny / denormal unions and thr ~ 0 always take the exact division.  Pairs within 2e-6 (relative) of the
+// threshold take it too.  tests/test_gpu_parity.py::test_nms_iou_threshold_guard_band pins the decisions at, one ulp
+// above and one ulp below the quotient.  (Measured: extra early-out branches — per-axis disjointness, area ratio — make
 // the sweep slower, the straight-line form below is the fastest.)
-__device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const float4 b, const float thr) {
+__device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const float4 b, const IouThr t) {
   const float area_b = (b.z - b.x) * (b.w - b.y);
   if (area_a <= 0.0f || area_b <= 0.0f) return false;
   const float i0 = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.0f);
@@ -99,12 +120,12 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const
   const float inter = i0 * i1;
   if (inter <= 0.0f) return false;  // iou == 0, never > thr for thr in [0,1]
   const float uni = area_a + area_b - inter;
-  // decide `inter / uni > thr` without the division when the quotient is at least 2e-6 (relative) away from thr: the
-  // correctly rounded quotient lies within 2^-24 of inter/uni, and thr*uni, *(1 +- 2e-6) round within 2^-23 each
-  const float p = thr * uni;
-  if (inter > p * 1.000002f) return true;
-  if (inter < p * 0.999998f) return false;
-  return inter / uni > thr;         // TF's exact test (fp32 division, strict >)
+  const float p_lo = t.lo * uni;
+  if (p_lo >= 1e-30f) {
+    if (inter > t.hi * uni) return true;
+    if (inter < p_lo) return false;
+  }
+  return inter / uni > t.thr;       // TF's exact test (fp32 division, strict >)
 }
 
 __device__ __forceinline__ float4 normalise(const float4 b) {
@@ -1172,6 +1193,7 @@ BoxCodec make_codec(const float means[4], const float stds[4], int image_h, int 
 extern "C" int bx_decode_clip(bx_handle* h, const float* anchors, int anchors_batched, const float* deltas,
                               int batch, int n, const float means[4], const float stds[4], int image_h, int image_w,
                               float* out_boxes, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && anchors && deltas && out_boxes && means && stds, BX_ERR_INVALID, "bx_decode_clip: NULL argument");
   BX_REQUIRE(batch >= 0 && n >= 0, BX_ERR_INVALID, "bx_decode_clip: negative size");
   BX_REQUIRE(bx_aligned(anchors, 16) && bx_aligned(deltas, 16) && bx_aligned(out_boxes, 16), BX_ERR_INVALID,
@@ -1188,6 +1210,7 @@ extern "C" int bx_decode_clip(bx_handle* h, const float* anchors, int anchors_ba
 
 extern "C" int bx_encode(bx_handle* h, const float* src, const float* dst, int n, const float means[4],
                          const float stds[4], float* out, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && src && dst && out && means && stds, BX_ERR_INVALID, "bx_encode: NULL argument");
   BX_REQUIRE(bx_aligned(src, 16) && bx_aligned(dst, 16) && bx_aligned(out, 16), BX_ERR_INVALID,
              "bx_encode: box tensors must be 16-byte aligned");
@@ -1201,6 +1224,7 @@ extern "C" int bx_encode(bx_handle* h, const float* src, const float* dst, int n
 
 extern "C" int bx_clip_filter(bx_handle* h, const float* boxes, int n, float min_value, int image_h, int image_w,
                               float min_edge, float* out_boxes, int* out_idx, int* out_count, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && boxes && out_boxes && out_idx && out_count, BX_ERR_INVALID, "bx_clip_filter: NULL argument");
   BX_REQUIRE(n >= 0, BX_ERR_INVALID, "bx_clip_filter: negative size");
   BX_REQUIRE(bx_aligned(boxes, 16) && bx_aligned(out_boxes, 16), BX_ERR_INVALID, "bx_clip_filter: alignment");
@@ -1213,6 +1237,7 @@ extern "C" int bx_clip_filter(bx_handle* h, const float* boxes, int n, float min
 
 extern "C" int bx_range_filter(bx_handle* h, const float* anchors, int n, int image_h, int image_w, int* out_idx,
                                int* out_count, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && anchors && out_idx && out_count, BX_ERR_INVALID, "bx_range_filter: NULL argument");
   BX_REQUIRE(n >= 0 && bx_aligned(anchors, 16), BX_ERR_INVALID, "bx_range_filter: bad size/alignment");
   filter_compact_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -1232,7 +1257,7 @@ int bx_internal_nms_keys(bx_handle* h, const float* boxes, const uint32_t* keys,
   a.keys = keys;
   a.n = n;
   a.post_nms = max_out;
-  a.thr = iou_threshold;
+  a.thr = make_iou_thr(iou_threshold);
   a.out_boxes = reinterpret_cast<float4*>(out_boxes);
   a.out_idx = out_idx;
   a.out_count = out_count;
@@ -1241,6 +1266,7 @@ int bx_internal_nms_keys(bx_handle* h, const float* boxes, const uint32_t* keys,
 
 extern "C" int bx_nms(bx_handle* h, const float* boxes, const float* scores, int batch, int n, int max_out,
                       float iou_threshold, int* out_idx, int* out_count, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && boxes && scores && out_idx && out_count, BX_ERR_INVALID, "bx_nms: NULL argument");
   BX_REQUIRE(batch >= 0 && n >= 0 && max_out >= 0, BX_ERR_INVALID, "bx_nms: negative size");
   BX_REQUIRE(iou_threshold >= 0.0f && iou_threshold <= 1.0f, BX_ERR_INVALID,
@@ -1254,12 +1280,12 @@ extern "C" int bx_nms(bx_handle* h, const float* boxes, const float* scores, int
   a.scores = scores;
   a.n = n;
   a.post_nms = max_out;
-  a.thr = iou_threshold;
+  a.thr = make_iou_thr(iou_threshold);
   a.out_idx = out_idx;
   a.out_count = out_count;
   void* top_ws = nullptr;
   if (n > kKeyCacheMax) {
-    if (int rc = bx_ws_reserve(h, topset_ws_bytes(batch, kKeyCacheMax))) return rc;
+    if (int rc = bx_ws_reserve(h, topset_ws_bytes(batch, kKeyCacheMax), static_cast<cudaStream_t>(stream))) return rc;
     top_ws = h->ws;
   }
   return launch_proposals(h, a, batch, static_cast<cudaStream_t>(stream), top_ws);
@@ -1326,6 +1352,7 @@ __global__ void __launch_bounds__(256) generate_anchors_kernel(const __grid_cons
 
 extern "C" int bx_generate_anchors(bx_handle* h, int n_levels, const int* fh, const int* fw, const float* stride,
                                    int anchors_per_cell, const float* offsets, float* out_anchors, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && fh && fw && stride && offsets, BX_ERR_INVALID, "bx_generate_anchors: NULL argument");
   BX_REQUIRE(n_levels >= 1 && n_levels <= kMaxAnchorLevels, BX_ERR_UNSUPPORTED,
              "bx_generate_anchors: n_levels %d not in [1, %d]", n_levels, kMaxAnchorLevels);
@@ -1368,6 +1395,7 @@ static int check_rpn(const char* who, const float* logits, int layout, int A, in
 
 extern "C" int bx_rpn_scores(bx_handle* h, const float* logits, int layout, int anchors_per_cell, int batch, int n,
                              float* out_scores, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && out_scores, BX_ERR_INVALID, "bx_rpn_scores: NULL argument");
   BX_REQUIRE(batch >= 0 && n >= 0, BX_ERR_INVALID, "bx_rpn_scores: negative size");
   if (int rc = check_rpn("bx_rpn_scores", logits, layout, anchors_per_cell, n)) return rc;
@@ -1381,6 +1409,7 @@ static int proposals_impl(bx_handle* h, const float* anchors, const float* delta
 extern "C" int bx_proposals(bx_handle* h, const float* anchors, const float* deltas, const float* scores, int batch,
                             int n, const bx_proposal_params* p, float* out_boxes, int* out_idx, int* out_count,
                             void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(scores, BX_ERR_INVALID, "bx_proposals: NULL argument");
   return proposals_impl(h, anchors, deltas, scores, nullptr, 0, 0, nullptr, batch, n, p, out_boxes, out_idx, out_count,
                         stream);
@@ -1389,6 +1418,7 @@ extern "C" int bx_proposals(bx_handle* h, const float* anchors, const float* del
 extern "C" int bx_proposals_rpn(bx_handle* h, const float* anchors, const float* deltas, const float* logits,
                                 int layout, int anchors_per_cell, int batch, int n, const bx_proposal_params* p,
                                 float* out_boxes, int* out_idx, int* out_count, float* out_scores, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(batch >= 0 && n >= 0, BX_ERR_INVALID, "bx_proposals_rpn: negative size");
   if (int rc = check_rpn("bx_proposals_rpn", logits, layout, anchors_per_cell, n)) return rc;
   return proposals_impl(h, anchors, deltas, nullptr, logits, layout, anchors_per_cell, out_scores, batch, n, p, out_boxes,
@@ -1419,7 +1449,7 @@ static int proposals_impl(bx_handle* h, const float* anchors, const float* delta
   a.codec = make_codec(p->means, p->stds, p->image_h, p->image_w);
   a.pre_nms_top_k = p->pre_nms_top_k;
   a.post_nms = p->post_nms;
-  a.thr = p->iou_threshold;
+  a.thr = make_iou_thr(p->iou_threshold);
   a.out_boxes = reinterpret_cast<float4*>(out_boxes);
   a.out_idx = out_idx;
   a.out_count = out_count;
@@ -1428,7 +1458,7 @@ static int proposals_impl(bx_handle* h, const float* anchors, const float* delta
   const size_t ws_scores = ((logits && !fuse && !out_scores) ? total * sizeof(float) + 15 : 0) & ~size_t(15);
   const size_t ws_min = ((p->min_size > 0.0f) ? total * (sizeof(float4) + sizeof(uint32_t)) + 15 : 0) & ~size_t(15);
   const size_t ws_top = (n > kKeyCacheMax) ? topset_ws_bytes(batch, kKeyCacheMax) : 0;
-  if (int rc = bx_ws_reserve(h, ws_scores + ws_min + ws_top)) return rc;
+  if (int rc = bx_ws_reserve(h, ws_scores + ws_min + ws_top, st)) return rc;
   if (fuse) {
     a.logits = logits;
     a.logit_layout = layout;

@@ -459,6 +459,9 @@ int launch_roi(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
   if (pool == BX_POOL_NONE || band_pooled || !roi_pool2_ok(a, pool)) {
     rc = roi_band_launch(h, a, pool, st, &used);     // TMA band-stationary kernel when the shape allows it
     if (rc) return rc;
+    // a plain crop the band kernel could not take (C % 32, map too wide, no TMA entry point ...) runs on a gather kernel
+    // at roughly 0.75x the speed: not an error, but visible — bx_stats() reports the count next to bx_launch_count()
+    if (!used && pool == BX_POOL_NONE && !band_pooled) h->band_fallbacks++;
   }
   if (!used && roi_pool2_ok(a, pool)) {
     if (pool == BX_POOL_MAX2) roi_pool2_kernel<BX_POOL_MAX2><<<a.r, 256, 0, st>>>(a, -0.0f);
@@ -558,6 +561,7 @@ int check_roi_common(const char* fn, bx_handle* h, int pool_size, int c, int r, 
 extern "C" int bx_crop_and_resize(bx_handle* h, const float* image, int b, int ih, int iw, int c, const float* boxes,
                                   const int* box_ind, int r, int crop_h, int crop_w, float extrapolation_value,
                                   float* out, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && image && out && (boxes || r == 0), BX_ERR_INVALID, "bx_crop_and_resize: NULL argument");
   BX_REQUIRE(crop_h > 0 && crop_w > 0, BX_ERR_INVALID, "bx_crop_and_resize: crop_size must be 2 positive ints");
   BX_REQUIRE(crop_h == crop_w && crop_h <= kMaxQ, BX_ERR_UNSUPPORTED,
@@ -580,6 +584,7 @@ extern "C" int bx_crop_and_resize(bx_handle* h, const float* image, int b, int i
 extern "C" int bx_roi_pool(bx_handle* h, int mode, int pool, int pool_size, const float* feat, int b, int fh, int fw,
                            int c, const float* rois, const int* box_ind, const int* roi_counts, int r, float stride,
                            int image_h, int image_w, float* out, void* stream) {
+  BxEnter guard(h, stream);
   int rc = check_roi_common("bx_roi_pool", h, pool_size, c, r, rois, out);
   if (rc) return rc;
   BX_REQUIRE(feat && b > 0 && fh > 1 && fw > 1, BX_ERR_INVALID, "bx_roi_pool: bad feature map");
@@ -610,6 +615,7 @@ extern "C" int bx_roi_pool_grad(bx_handle* h, int mode, int pool, int pool_size,
                                 int fw, int c, const float* rois, const int* box_ind, const int* roi_counts, int r,
                                 float stride, int image_h, int image_w, const float* grad_out, float* grad_feat,
                                 void* stream) {
+  BxEnter guard(h, stream);
   int rc = check_roi_common("bx_roi_pool_grad", h, pool_size, c, r, rois, grad_feat);
   if (rc) return rc;
   BX_REQUIRE(grad_out || r == 0, BX_ERR_INVALID, "bx_roi_pool_grad: NULL grad_out");
@@ -651,6 +657,7 @@ extern "C" int bx_roi_pool_grad(bx_handle* h, int mode, int pool, int pool_size,
 
 extern "C" int bx_fpn_assign_levels(bx_handle* h, const float* rois, int r, int min_level, int max_level,
                                     int* out_level, int* out_order, int* out_counts, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && out_order && (rois || r == 0), BX_ERR_INVALID, "bx_fpn_assign_levels: NULL argument");
   BX_REQUIRE(r >= 0 && max_level >= min_level && max_level - min_level < kMaxLevels, BX_ERR_INVALID,
              "bx_fpn_assign_levels: bad level range");
@@ -666,6 +673,7 @@ extern "C" int bx_fpn_roi_features(bx_handle* h, const float* const* feats, cons
                                    int n_levels, int min_level, int b, int c, const float* rois, const int* box_ind,
                                    int r, int image_h, int image_w, int pool_size, float* out, int* out_level,
                                    int* out_order, int* out_counts, void* stream) {
+  BxEnter guard(h, stream);
   int rc = check_roi_common("bx_fpn_roi_features", h, pool_size, c, r, rois, out);
   if (rc) return rc;
   BX_REQUIRE(feats && fh && fw && out_level && out_order, BX_ERR_INVALID, "bx_fpn_roi_features: NULL argument");

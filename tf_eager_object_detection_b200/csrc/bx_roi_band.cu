@@ -698,7 +698,7 @@ int roi_band_launch(bx_handle* h, const RoiArgs& ra, int pool, cudaStream_t st, 
   BX_REQUIRE(cr == CUDA_SUCCESS, BX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
   const size_t plan_bytes = static_cast<size_t>(ra.b) * cfg.n_bands * cfg.n_blocks_max * plan_layout(cfg.cap, ra.Q).bytes;
-  int rc = bx_plan_reserve(h, plan_bytes);
+  int rc = bx_plan_reserve(h, plan_bytes, st);
   if (rc) return rc;
 
   BandArgs a;
@@ -717,7 +717,7 @@ int roi_band_launch(bx_handle* h, const RoiArgs& ra, int pool, cudaStream_t st, 
   a.dbg = nullptr;
   if (getenv("BX_BAND_DEBUG")) {   // measurement aid: per-CTA timestamps appended to the plan buffer, dumped by the caller
     const size_t grid = static_cast<size_t>(ra.b) * a.n_slices * a.n_bands;
-    rc = bx_plan_reserve(h, plan_bytes + 256 + grid * 32);
+    rc = bx_plan_reserve(h, plan_bytes + 256 + grid * 32, st);
     if (rc) return rc;
     a.plan = static_cast<unsigned char*>(h->plan);
     a.dbg = reinterpret_cast<unsigned long long*>(a.plan + ((plan_bytes + 255) & ~static_cast<size_t>(255)));
@@ -728,7 +728,10 @@ int roi_band_launch(bx_handle* h, const RoiArgs& ra, int pool, cudaStream_t st, 
   if (pool == BX_POOL_NONE) rc = launch_band<BX_POOL_NONE>(h, a, tmap, cfg.smem, threads, st);
   else if (pool == BX_POOL_MAX2) rc = launch_band<BX_POOL_MAX2>(h, a, tmap, cfg.smem, threads, st);
   else rc = launch_band<BX_POOL_AVG2>(h, a, tmap, cfg.smem, threads, st);
-  if (rc == BX_OK) *used = 1;
+  if (rc == BX_OK) {
+    *used = 1;
+    h->band_launches++;
+  }
   return rc;
 }
 

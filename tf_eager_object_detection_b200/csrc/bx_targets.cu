@@ -604,6 +604,7 @@ BoxCodec codec_of(const float means[4], const float stds[4]) {
 }  // namespace
 
 extern "C" int bx_pairwise_iou(bx_handle* h, const float* a, int n, const float* b, int m, float* out, void* stream) {
+  BxEnter guard(h, stream);
   BX_REQUIRE(h && out && (a || n == 0) && (b || m == 0), BX_ERR_INVALID, "bx_pairwise_iou: NULL argument");
   BX_REQUIRE(n >= 0 && m >= 0, BX_ERR_INVALID, "bx_pairwise_iou: negative size");
   BX_REQUIRE(bx_aligned(a, 16) && bx_aligned(b, 16), BX_ERR_INVALID, "bx_pairwise_iou: boxes must be 16-byte aligned");
@@ -620,8 +621,9 @@ extern "C" int bx_anchor_target(bx_handle* h, const float* anchors, int n, const
                                 int batch, int max_gt, const int* perm, const bx_anchor_target_params* p,
                                 float* out_labels, float* out_targets, float* out_in_w, float* out_out_w,
                                 int* out_counts, void* stream) {
-  BX_REQUIRE(h && anchors && gt && perm && p && out_labels && out_targets && out_in_w && out_out_w, BX_ERR_INVALID,
-             "bx_anchor_target: NULL argument");
+  BxEnter guard(h, stream);
+  BX_REQUIRE(h && anchors && (gt || max_gt == 0) && perm && p && out_labels && out_targets && out_in_w && out_out_w,
+             BX_ERR_INVALID, "bx_anchor_target: NULL argument");   // an image set without ground truth (max_gt == 0) is valid
   BX_REQUIRE(n > 0 && batch >= 0 && max_gt >= 0, BX_ERR_INVALID, "bx_anchor_target: bad size");
   BX_REQUIRE(max_gt <= kMaxGt, BX_ERR_UNSUPPORTED, "bx_anchor_target: max_gt %d > %d", max_gt, kMaxGt);
   BX_REQUIRE(p->max_pos_samples >= 0 && p->total_num_samples >= p->max_pos_samples, BX_ERR_INVALID,
@@ -635,7 +637,7 @@ extern "C" int bx_anchor_target(bx_handle* h, const float* anchors, int n, const
   const size_t wm = static_cast<size_t>(batch) * nblk * 8 * (max_gt > 0 ? max_gt : 1);
   const size_t ws = bn * (sizeof(float) + 2 * sizeof(int)) + static_cast<size_t>(batch) * (max_gt + 4) * sizeof(int) +
                     4 * sizeof(int) + wm * sizeof(int) + static_cast<size_t>(n) * sizeof(int);
-  int rc = bx_ws_reserve(h, ws);
+  int rc = bx_ws_reserve(h, ws, st);
   if (rc) return rc;
   ATArgs a = {};
   a.anchors = reinterpret_cast<const float4*>(anchors);
@@ -688,8 +690,10 @@ extern "C" int bx_proposal_target(bx_handle* h, const float* rois, const int* ro
                                   const bx_proposal_target_params* p, float* out_rois, int* out_labels,
                                   float* out_targets, float* out_in_w, float* out_out_w, int* out_keep,
                                   int* out_counts, void* stream) {
-  BX_REQUIRE(h && rois && gt && gt_labels && perm && p && out_rois && out_labels && out_targets && out_in_w &&
-                 out_out_w && out_keep && out_counts, BX_ERR_INVALID, "bx_proposal_target: NULL argument");
+  BxEnter guard(h, stream);
+  BX_REQUIRE(h && (rois || k == 0) && (gt || max_gt == 0) && (gt_labels || max_gt == 0) && (perm || k == 0) && p &&
+                 out_rois && out_labels && out_targets && out_in_w && out_out_w && out_keep && out_counts,
+             BX_ERR_INVALID, "bx_proposal_target: NULL argument");
   BX_REQUIRE(k >= 0 && batch >= 0 && max_gt >= 0, BX_ERR_INVALID, "bx_proposal_target: negative size");
   BX_REQUIRE(k <= kMaxRois, BX_ERR_UNSUPPORTED, "bx_proposal_target: %d rois per image > %d", k, kMaxRois);
   BX_REQUIRE(max_gt <= kMaxGt, BX_ERR_UNSUPPORTED, "bx_proposal_target: max_gt %d > %d", max_gt, kMaxGt);
@@ -698,6 +702,7 @@ extern "C" int bx_proposal_target(bx_handle* h, const float* rois, const int* ro
   BX_REQUIRE(bx_aligned(rois, 16) && bx_aligned(gt, 16) && bx_aligned(out_rois, 16), BX_ERR_INVALID,
              "bx_proposal_target: box tensors must be 16-byte aligned");
   if (batch == 0) return BX_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   PTArgs a = {};
   a.rois = reinterpret_cast<const float4*>(rois);
   a.roi_counts = roi_counts;
@@ -718,7 +723,7 @@ extern "C" int bx_proposal_target(bx_handle* h, const float* rois, const int* ro
   a.out_counts = out_counts;
   const size_t smem = sizeof(float4) * kMaxGt + 2 * sizeof(uint64_t) * kMaxRois + sizeof(float) * kMaxGt +
                       sizeof(unsigned short) * kMaxRois;
-  if (int rc = bx_ws_reserve(h, static_cast<size_t>(batch) * (k > 0 ? k : 1) * (sizeof(float) + sizeof(int)))) return rc;
+  if (int rc = bx_ws_reserve(h, static_cast<size_t>(batch) * (k > 0 ? k : 1) * (sizeof(float) + sizeof(int)), st)) return rc;
   a.ws_best = reinterpret_cast<float*>(h->ws);
   a.ws_arg = reinterpret_cast<int*>(a.ws_best + static_cast<size_t>(batch) * k);
   if (k > 0) {

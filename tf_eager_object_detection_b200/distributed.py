@@ -7,7 +7,8 @@ torch.distributed is plumbing only (NCCL over NVLink on the GPUs; gloo in the CP
 import torch
 import torch.distributed as dist
 
-__all__ = ['shard_bounds', 'shard_images', 'pack_detections', 'allgather_detections']
+__all__ = ['shard_bounds', 'shard_images', 'pack_detections', 'allgather_detections', 'allgather_native',
+           'new_detection_group', 'nccl_comm_ptr']
 
 
 def shard_bounds(num_images, rank, world_size):
@@ -31,64 +32,95 @@ def pack_detections(boxes, scores, labels):
 
 
 def nccl_comm_ptr(group=None):
-    """Raw ncclComm_t of the group's NCCL backend on the current CUDA device, or None (gloo / no NCCL / not initialised)."""
-    try:
-        pg = group if group is not None else dist.distributed_c10d._get_default_group()
-        backend = pg._get_backend(torch.device('cuda', torch.cuda.current_device()))
-        ptr = backend._comm_ptr()
-        return int(ptr) if ptr else None
-    except Exception:
+    """Raw ncclComm_t of the group's NCCL backend on the current CUDA device, or None (gloo / no NCCL / not initialised /
+    a torch build without ProcessGroupNCCL._comm_ptr)."""
+    if not (dist.is_available() and dist.is_initialized()):
         return None
+    pg = group if group is not None else dist.distributed_c10d._get_default_group()
+    try:
+        backend = pg._get_backend(torch.device('cuda', torch.cuda.current_device()))
+    except (RuntimeError, ValueError):           # no CUDA backend registered for this group (gloo)
+        return None
+    get = getattr(backend, '_comm_ptr', None)
+    if get is None:
+        return None
+    ptr = get()
+    return int(ptr) if ptr else None
 
 
-def _allgather_native(records, counts, rec_all, cnt_all, world, group):
-    """bx_allgather_detections on the framework's own communicator: both tensors in one fused NCCL group on the current
-    stream.  Returns False when the group is not NCCL-backed (the gloo CPU tests), so the caller uses torch.distributed."""
-    if not (records.is_cuda and records.dtype == torch.float32 and counts.dtype == torch.int32 and records.dim() == 3):
-        return False
-    comm = nccl_comm_ptr(group)
-    if comm is None:
-        return False
+def new_detection_group():
+    """A process group (and hence an ncclComm_t) used by NOTHING but bx_allgather_detections.  NCCL requires the
+    operations of one communicator to be issued in one order on every rank; the native all-gather enqueues on the raw
+    communicator behind ProcessGroupNCCL's back, so it must never share a communicator with torch collectives that may be
+    in flight (async_op=True, or issued from other streams).  A dedicated group makes that structural."""
+    return dist.new_group(ranks=list(range(dist.get_world_size())), backend='nccl')
+
+
+def allgather_native(records, counts, rec_all, cnt_all, group, stream=None):
+    """bx_allgather_detections (C ABI) on `group`'s ncclComm_t: records + counts in ONE fused NCCL group, enqueued on
+    `stream` (default: torch's current stream).  `group` should come from new_detection_group().  Raises when the group is
+    not NCCL-backed; never falls back."""
     import ctypes
     from . import _lib
     from ._tensor import stream_ptr
+    if not (records.is_cuda and records.dtype == torch.float32 and counts.dtype == torch.int32 and records.dim() == 3
+            and records.is_contiguous() and counts.is_contiguous()):
+        raise TypeError('allgather_native: records must be contiguous CUDA fp32 [b,k,f], counts contiguous int32 [b]')
+    comm = nccl_comm_ptr(group)
+    if comm is None:
+        raise RuntimeError('allgather_native: the process group has no NCCL communicator on this device')
+    world = dist.get_world_size(group)
     dev = records.device.index
-    st = stream_ptr(dev)
+    st = ctypes.c_void_p(stream.cuda_stream) if stream is not None else stream_ptr(dev)
     h = _lib.handle(dev, st.value)
     b, k, f = records.shape
     _lib.check(_lib.load().bx_allgather_detections(h, ctypes.c_void_p(comm), records.data_ptr(), counts.data_ptr(), b, k, f,
                                                    world, rec_all.data_ptr(), cnt_all.data_ptr(), st))
-    return True
+    return rec_all, cnt_all
 
 
-def allgather_detections(records, counts, group=None, max_images_per_rank=None):
+def allgather_detections(records, counts, group=None, sizes=None, native_group=None):
     """records [b_local, kmax, f] fp32 (zero padded), counts [b_local] int32 ->
     (records_all [b_total, kmax, f], counts_all [b_total]) in rank order, identical on every rank.
 
-    Ranks may own different numbers of images (uneven shards): blocks are padded to `max_images_per_rank`
-    (default: all-reduced max) for a single fixed-size all-gather, then the padding is dropped."""
+    `sizes`: the number of images every rank owns (a list of world_size ints, e.g. from shard_bounds) — static shard
+    sizes make the call free of host synchronisation.  Without it the sizes are exchanged first (one small all-gather and
+    one device->host read per call).  Uneven shards are padded to the largest for a single fixed-size all-gather and the
+    padding is dropped afterwards.
+
+    Transport: ONE torch.distributed all_gather_into_tensor of a packed [b, kmax*f + 1] buffer (the int32 counts travel
+    bit-cast in the last column) on `group`, ordered by ProcessGroupNCCL like every other torch collective.  Pass
+    `native_group=new_detection_group()` to use the C-ABI entry point bx_allgather_detections on that dedicated
+    communicator instead (no packing copy; see new_detection_group for why it must be dedicated)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return records, counts
     world = dist.get_world_size(group)
     b_local = records.shape[0]
-    nloc = torch.tensor([b_local], dtype=torch.int32, device=records.device)
-    sizes = torch.empty((world,), dtype=torch.int32, device=records.device)
-    dist.all_gather_into_tensor(sizes, nloc, group=group)
-    if max_images_per_rank is None:
-        max_images_per_rank = int(sizes.max().item())
-    pad = max_images_per_rank - b_local
+    if sizes is None:
+        nloc = torch.tensor([b_local], dtype=torch.int32, device=records.device)
+        szt = torch.empty((world,), dtype=torch.int32, device=records.device)
+        dist.all_gather_into_tensor(szt, nloc, group=group)
+        sizes = szt.tolist()                                   # the one host sync of the dynamic-size form
+    sizes = [int(v) for v in sizes]
+    if len(sizes) != world or sizes[dist.get_rank(group)] != b_local:
+        raise ValueError('allgather_detections: sizes %s do not match world size %d / local block %d' % (sizes, world, b_local))
+    bmax = max(sizes)
+    pad = bmax - b_local
     if pad:
         records = torch.cat([records, records.new_zeros((pad,) + tuple(records.shape[1:]))])
         counts = torch.cat([counts, counts.new_zeros((pad,))])
-    rec_all = torch.empty((world * max_images_per_rank,) + tuple(records.shape[1:]), dtype=records.dtype,
-                          device=records.device)
-    cnt_all = torch.empty((world * max_images_per_rank,), dtype=counts.dtype, device=counts.device)
-    if not _allgather_native(records.contiguous(), counts.contiguous(), rec_all, cnt_all, world, group):
-        dist.all_gather_into_tensor(rec_all, records.contiguous(), group=group)
-        dist.all_gather_into_tensor(cnt_all, counts.contiguous(), group=group)
-    sizes = sizes.tolist()
-    if all(s == max_images_per_rank for s in sizes):
+    k, f = records.shape[1], records.shape[2]
+    if native_group is not None:
+        rec_all = torch.empty((world * bmax, k, f), dtype=records.dtype, device=records.device)
+        cnt_all = torch.empty((world * bmax,), dtype=counts.dtype, device=counts.device)
+        allgather_native(records.contiguous(), counts.contiguous(), rec_all, cnt_all, native_group)
+    else:
+        packed = torch.cat([records.reshape(bmax, k * f), counts.to(torch.int32).view(torch.float32).reshape(bmax, 1)], dim=1)
+        out = torch.empty((world * bmax, k * f + 1), dtype=torch.float32, device=records.device)
+        dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
+        rec_all = out[:, :k * f].reshape(world * bmax, k, f)
+        cnt_all = out[:, k * f].contiguous().view(torch.int32)
+    if all(s_ == bmax for s_ in sizes):
         return rec_all, cnt_all
-    keep = torch.cat([torch.arange(r * max_images_per_rank, r * max_images_per_rank + s, device=records.device)
-                      for r, s in enumerate(sizes)])
+    keep = torch.cat([torch.arange(r * bmax, r * bmax + s_, device=records.device) for r, s_ in enumerate(sizes)])
     return rec_all.index_select(0, keep), cnt_all.index_select(0, keep)

@@ -24,6 +24,8 @@ def post_ops_prediction(roi_scores_softmax, roi_txtytwth, rois, image_shape, tar
     (None, None, None) when nothing survives.  Order: descending score (the reference's `top_k(sorted=False)` leaves
     it unspecified).  One host sync reads n."""
     scores = ops.to_device(roi_scores_softmax, torch.float32)
+    if num_classes is not None and int(num_classes) != scores.shape[1]:
+        raise ValueError('post_ops_prediction: num_classes=%d but the score tensor has %d columns' % (num_classes, scores.shape[1]))
     deltas = ops.to_device(roi_txtytwth, torch.float32, scores.device)
     rois = ops.to_device(rois, torch.float32, scores.device)
     det, cnt = post_ops_prediction_batched(scores.unsqueeze(0), deltas.reshape(1, scores.shape[0], -1, 4), rois.unsqueeze(0),
