@@ -1,12 +1,20 @@
 #!/usr/bin/env python
 """bench.py — proposal + NMS + RoI pooling throughput (BASELINE.json metric) on N B200s, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workloads all|none|cfg3,cfg5,cfg4]
 
-A "step" = one pass of the hot path over one batch of synthetic images (workload cfg2 of BASELINE.json: ResNet-50 C4,
-600x1000, 21 546 anchors, pre-NMS 6000 -> post-NMS 300, crop 7x7x1024, batch 8 per GPU).  Prints ONE JSON line (rank 0).
-Device-resident `value`, host-buffer `e2e`, `roofline` of the dominant kernel (RoI pooling), `cpu_baseline` (oracle C
-twin on the host cores), clocks.  `--impl reference` times the CPU restatement of the reference path instead.
+A "step" = one pass of the hot path over one batch of synthetic images.  Headline workload: cfg2 of BASELINE.json
+(ResNet-50 C4, 600x1000, 21 546 anchors, pre-NMS 6000 -> post-NMS 300, crop 7x7x1024, batch 8 per GPU).  Prints ONE JSON
+line (rank 0): device-resident `value`, host-buffer `e2e`, `roofline` of the dominant kernel (RoI pooling) measured in
+the same regime as `value`, `regimes` (pipelined / single stream, structured), `cpu_baseline` (oracle C twin on the host
+cores), clocks, and `workloads` — the FPN configurations cfg3 / cfg5 and the training-target configuration cfg4 measured
+in the same run.  `--impl reference` times the CPU restatement of the reference path instead.
+
+How the timed region is issued: the K steps are captured ONCE into a CUDA graph (steps dealt round-robin over S streams,
+fork/join inside the graph; at N > 1 the all-gather of the per-image detection records runs on its own branch of the
+same graph, on a dedicated communicator, and no compute stream ever waits for it) and the timed region is one replay of
+that graph between two CUDA events — no host code between the first and the last kernel.  `--no-graph` issues the same
+launches eagerly.
 """
 import argparse
 import ctypes
@@ -31,6 +39,12 @@ METRIC = 'proposal+NMS+RoIAlign images/s'
 UNIT = 'images/s'
 FALLBACK_HBM_GBS = 6650.0
 NCU_TRAFFIC_BYTES_PER_LAUNCH = 516283136   # profiles/r1_ncu_full_raw.csv: 92.8 MB read + 423.5 MB written by roi_band_kernel
+
+
+def headline_config(w):
+    """The `config` object — identical in the GPU arm and in `--impl reference` (the driver compares them)."""
+    return dict(workload=w['name'], images_per_step_per_gpu=w['batch'],
+                l2='inputs larger than L2: working set 566 MB/step (82 MB inputs rotating over distinct batches, 482 MB outputs) > 126 MB')
 
 
 def algorithmic_bytes(w, n, fh, fw):
@@ -153,9 +167,9 @@ def run_reference_arm(args):
     sample = '%d steps x %d images of the workload batch per step' % (args.steps, n_img)
     line = dict(metric=METRIC, value=round(val, 2), unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=round(1e3 * el / args.steps, 3), higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload=w['name'], images_per_step=n_img,
-                            note='CPU restatement of the reference TF ops (oracle C twin); TensorFlow itself is not installable here'),
+                dtype='f32', data='synthetic', impl='reference', config=headline_config(w),
+                details=dict(images_per_step=n_img,
+                             note='CPU restatement of the reference TF ops (oracle C twin); TensorFlow itself is not installable here'),
                 cpu_baseline=dict(value=round(val, 2), unit=UNIT, cores=cores, kind='port', sample=sample),
                 e2e=dict(value=round(val, 2), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -203,203 +217,326 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(self.reasons), samples=len(self.samples))
 
 
-def bind_to_gpu_numa_node(index):
-    """Multi-rank runs: pin this process to the CPUs NVML reports as local to its GPU, so that the pinned host buffers
-    of the e2e leg are allocated on the GPU's own NUMA node (first touch) and the copies do not cross sockets."""
+def gpu_numa_cpus(index):
+    """CPUs local to GPU `index`: NVML's affinity mask when it is a proper subset of the visible CPUs, else the cpulist
+    of the GPU's PCI device NUMA node from sysfs, else None (single node / not exposed in this container)."""
+    allowed = os.sched_getaffinity(0)
     try:
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
         ncpu = os.cpu_count() or 1
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
-        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
-        allowed = os.sched_getaffinity(0)
-        cpus = (cpus & allowed) or allowed
-        os.sched_setaffinity(0, cpus)
-        return len(cpus)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1} & allowed
+        if cpus and cpus != allowed:
+            return cpus, 'nvml'
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(':')[0]) == 8:
+            bus = bus[4:]
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read())
+        if node >= 0:
+            cpus = set()
+            for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus |= set(range(int(lo), int(hi or lo) + 1))
+            cpus &= allowed
+            if cpus and cpus != allowed:
+                return cpus, 'sysfs node %d' % node
     except Exception:
-        return None
+        pass
+    return None, 'one NUMA domain visible (affinity covers every CPU of the container)'
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from tf_eager_object_detection_b200 import _lib, ops
+class Ctx:
+    """Process-wide state of the GPU arm: rank / device / library / process groups."""
 
-    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback)')
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from tf_eager_object_detection_b200 import _lib
+        self.torch, self.dist, self._lib = torch, dist, _lib
+        self.rank = int(os.environ.get('RANK', '0')); self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback)')
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        self.comm = None
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
+            # the C-ABI all-gather runs on a communicator nothing else uses (distributed.new_detection_group)
+            from tf_eager_object_detection_b200 import distributed as bxd
+            self.det_group = bxd.new_detection_group()
+            dist.all_reduce(torch.zeros(1, device=self.dev), group=self.det_group)   # forces the communicator to exist
+            torch.cuda.synchronize()
+            ptr = bxd.nccl_comm_ptr(self.det_group)
+            if ptr is None:
+                raise SystemExit('bench.py: the process group exposes no ncclComm_t (torch without ProcessGroupNCCL._comm_ptr)')
+            self.comm = ctypes.c_void_p(ptr)
+        self.lib = _lib.load()
+        self.main = torch.cuda.current_stream(self.dev)
+        self.use_graph = not args.no_graph
+        self.graph_error = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def new_handle(self):
+        hh = ctypes.c_void_p()
+        self._lib.check(self.lib.bx_create(self.local, ctypes.byref(hh)))
+        return hh
+
+    def max_over_ranks(self, ms):
+        """(max over ranks, per-rank list) of a device-timed duration."""
+        torch = self.torch
+        if self.world == 1:
+            return ms, [round(ms, 5)]
+        mine = torch.tensor([ms], device=self.dev)
+        allv = torch.empty((self.world,), device=self.dev)
+        self.dist.all_gather_into_tensor(allv, mine)
+        v = [round(float(x), 5) for x in allv.tolist()]
+        return max(v), v
+
+
+class Pipeline:
+    """A region of steps dealt round-robin over S CUDA streams (one library handle per stream), with the all-gather of
+    the region's detection records on a separate communication stream at N > 1.
+
+    launch(step, pos, stream_index) enqueues the kernels of one step on stream `stream_index`; `pos` is the step's
+    position in the region and selects its slot in the record accumulators.  region() forks the streams from `root`,
+    issues the steps and joins everything back — the same code eagerly (root = main stream) or under CUDA-graph capture
+    (root = capturing stream; events recorded / waited inside the capture become graph edges)."""
+
+    def __init__(self, ctx, n_streams, launch, records=None, gather_every=0):
+        torch = ctx.torch
+        self.ctx, self.launch = ctx, launch
+        self.streams = [torch.cuda.Stream(ctx.dev) for _ in range(n_streams)]
+        self.handles = [ctx.new_handle() for _ in range(n_streams)]
+        self.records = records          # dict(boxes [cap*B,k,4], counts [cap*B], B, k, out_boxes, out_counts) or None
+        self.gather_every = gather_every
+        self.comm_stream = torch.cuda.Stream(ctx.dev) if (records is not None and ctx.world > 1) else None
+        self.comm_handle = ctx.new_handle() if self.comm_stream is not None else None
+        self.graphs = {}
+
+    def _gather(self, first_pos, n_pos, done_events):
+        """All-gather of the records of positions [first_pos, first_pos + n_pos) on the communication stream."""
+        ctx, r = self.ctx, self.records
+        for ev in done_events:
+            self.comm_stream.wait_event(ev)
+        rows = n_pos * r['B']
+        lo = first_pos * r['B']
+        # gathered layout per chunk: [world, rows, k, 4] at row offset world * lo
+        ctx._lib.check(ctx.lib.bx_allgather_detections(
+            self.comm_handle, ctx.comm, r['boxes'][lo:lo + rows].data_ptr(), r['counts'][lo:lo + rows].data_ptr(), rows,
+            r['k'], 4, ctx.world, r['out_boxes'][ctx.world * lo:].data_ptr(), r['out_counts'][ctx.world * lo:].data_ptr(),
+            ctypes.c_void_p(self.comm_stream.cuda_stream)))
+
+    def region(self, nsteps, first, root, only_stream=None):
+        torch = self.ctx.torch
+        streams = self.streams if only_stream is None else [self.streams[only_stream]]
+        ev0 = torch.cuda.Event(); ev0.record(root)
+        for s in streams:
+            s.wait_event(ev0)
+        if self.comm_stream is not None:
+            self.comm_stream.wait_event(ev0)
+        G = self.gather_every if self.gather_every > 0 else nsteps
+        pending = []
+        for k in range(nsteps):
+            si = (first + k) % len(self.streams) if only_stream is None else only_stream
+            self.launch(first + k, k, si)
+            if self.comm_stream is not None:
+                ev = torch.cuda.Event(); ev.record(self.streams[si]); pending.append(ev)
+                if len(pending) == G or k == nsteps - 1:
+                    self._gather(k + 1 - len(pending), len(pending), pending)
+                    pending = []
+        for s in streams + ([self.comm_stream] if self.comm_stream is not None else []):
+            ev = torch.cuda.Event(); ev.record(s); root.wait_event(ev)
+
+    def graph(self, nsteps, first, key):
+        """The region as one CUDA graph (captured once per key); None when capture is disabled or failed."""
+        ctx, torch = self.ctx, self.ctx.torch
+        if not ctx.use_graph:
+            return None
+        if key in self.graphs:
+            return self.graphs[key]
+        g = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(ctx.dev)
+        try:
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=cap, capture_error_mode='thread_local'):
+                self.region(nsteps, first, cap)
+        except Exception as e:                                   # report and fall back to eager issue for the whole run
+            ctx.graph_error = '%s: %s' % (type(e).__name__, str(e)[:200])
+            ctx.use_graph = False
+            torch.cuda.synchronize()
+            return None
+        self.graphs[key] = g
+        return g
+
+    def timed(self, nsteps, first, key=None, only_stream=None, prime_graph=True):
+        """Device time (ms) of the region: CUDA events on the main stream around one graph replay (or the eager issue)."""
+        ctx, torch = self.ctx, self.ctx.torch
+        g = self.graph(nsteps, first, key) if (key is not None and only_stream is None) else None
+        if g is not None and prime_graph and not getattr(g, '_bx_primed', False):
+            g.replay()                                           # untimed: instantiation upload of the executable graph
+            g._bx_primed = True
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.barrier()
+        e0.record(ctx.main)
+        if g is not None:
+            g.replay()
+        else:
+            self.region(nsteps, first, ctx.main, only_stream)
+        e1.record(ctx.main)
+        ctx.barrier()
+        return e0.elapsed_time(e1)
+
+    def launches(self):
+        return sum(int(self.ctx.lib.bx_launch_count(h)) for h in self.handles + ([self.comm_handle] if self.comm_handle else []))
+
+    def close(self):
+        self.graphs.clear()
+        for h in self.handles + ([self.comm_handle] if self.comm_handle else []):
+            self.ctx.lib.bx_destroy(h)
+        self.handles = []
+
+
+def make_records(ctx, cap_steps, B, k):
+    """Accumulators of the per-image detection records of a region (kept boxes [B,k,4] + counts [B] per step) and, at
+    N > 1, their all-gathered copies — what the reference accumulates in one process over an evaluation run
+    (evaluation/pascal_eval_files_utils.py:73-107)."""
+    torch = ctx.torch
+    r = dict(B=B, k=k, cap=cap_steps,
+             boxes=torch.zeros((cap_steps * B, k, 4), device=ctx.dev),
+             counts=torch.zeros((cap_steps * B,), dtype=torch.int32, device=ctx.dev))
+    if ctx.world > 1:
+        r['out_boxes'] = torch.zeros((ctx.world * cap_steps * B, k, 4), device=ctx.dev)
+        r['out_counts'] = torch.zeros((ctx.world * cap_steps * B,), dtype=torch.int32, device=ctx.dev)
+    return r
+
+
+def verify_gather(ctx, r, nsteps, G):
+    """Every rank checks the gathered records of EVERY rank: an exact integer checksum (bit patterns summed in int64) of
+    each rank's own accumulator is exchanged with torch.distributed and compared with the checksum of that rank's slots
+    in the gathered buffer."""
+    torch, dist = ctx.torch, ctx.dist
+    B, world = r['B'], ctx.world
+    rows_total = nsteps * B
+    own = torch.stack([r['boxes'][:rows_total].reshape(-1).view(torch.int32).to(torch.int64).sum(),
+                       r['counts'][:rows_total].to(torch.int64).sum()])
+    allsum = torch.empty((world, 2), dtype=torch.int64, device=ctx.dev)
+    dist.all_gather_into_tensor(allsum, own)
+    got = torch.zeros((world, 2), dtype=torch.int64, device=ctx.dev)
+    G = G if G > 0 else nsteps
+    for first in range(0, nsteps, G):
+        n_pos = min(G, nsteps - first)
+        rows, lo = n_pos * B, first * B
+        blk_b = r['out_boxes'][world * lo: world * lo + world * rows].reshape(world, -1).view(torch.int32).to(torch.int64).sum(dim=1)
+        blk_c = r['out_counts'][world * lo: world * lo + world * rows].reshape(world, rows).to(torch.int64).sum(dim=1)
+        got[:, 0] += blk_b
+        got[:, 1] += blk_c
+    assert torch.equal(got, allsum), 'all-gather mismatch: gathered records differ from their owners (rank %d sees %s vs %s)' % (
+        ctx.rank, got.tolist(), allsum.tolist())
+    return True
+
+
+def bench_c4(ctx, args):
+    """Headline workload (cfg2)."""
+    torch, lib, _lib = ctx.torch, ctx.lib, ctx._lib
+    from tf_eager_object_detection_b200 import ops
     w = WORKLOAD
     B, post, P, C = w['batch'], w['post_nms'], w['pool'], w['channels']
-    lib = _lib.load()
-
-    # ---- inputs: NBUF distinct batches resident in HBM, rotated so no step re-reads the previous step's inputs from L2
-    NBUF = max(4, args.streams)          # one distinct input batch per stream: concurrent steps never share inputs in L2
-    host_batches = [make_batch(w, rank * 10000 + k * B) for k in range(NBUF)]
+    K, W = args.steps, max(3, args.warmup)
+    NSTREAM = max(1, args.streams)
+    NBUF = max(4, NSTREAM)               # one distinct input batch per stream: concurrent steps never share inputs in L2
+    host_batches = [make_batch(w, ctx.rank * 10000 + k * B) for k in range(NBUF)]
     n = host_batches[0]['anchors'].shape[0]
     fh, fw = host_batches[0]['feat_hw']
+    dev = ctx.dev
     anchors = torch.as_tensor(host_batches[0]['anchors']).to(dev)
     d_in = [dict(deltas=torch.as_tensor(hb['deltas']).to(dev), scores=torch.as_tensor(hb['scores']).to(dev),
                  feat=torch.as_tensor(hb['feat']).to(dev)) for hb in host_batches]
-    NSTREAM = max(1, args.streams)
-    # per-image detection records of a step = kept boxes [B,post,4] fp32 + counts [B] int32.  N > 1: the records of G
-    # consecutive steps land in one bucket (a ring of NBK buckets) and are all-gathered together — same bytes, 1/G of the
-    # NCCL launches (the all-gathers of one communicator serialise, so their launch latency is what N > 1 adds per step)
-    G = max(1, args.gather_every) if world > 1 else 1
-    NBK = max(2, (2 * NSTREAM + G - 1) // G + 1)         # a bucket is reused only after >= 2 * NSTREAM later steps
-    bk_boxes = [torch.empty((G * B, post, 4), device=dev) for _ in range(NBK)]
-    bk_counts = [torch.empty((G * B,), dtype=torch.int32, device=dev) for _ in range(NBK)]
+    rec = make_records(ctx, max(K, W, NSTREAM), B, post)
     idx_bufs = [torch.empty((B, post), dtype=torch.int32, device=dev) for _ in range(NSTREAM)]
     feat_bufs = [torch.empty((B * post, P, P, C), device=dev) for _ in range(NSTREAM)]
-
-    def outs_of(step):
-        b, slot, s = (step // G) % NBK, step % G, step % NSTREAM
-        return (bk_boxes[b][slot * B:(slot + 1) * B], idx_bufs[s], bk_counts[b][slot * B:(slot + 1) * B], feat_bufs[s])
     params = ops.proposal_params(w['image_hw'], post, w['iou_thr'], pre_nms_top_k=w['pre_nms'])
-    streams = [torch.cuda.Stream(dev) for _ in range(NSTREAM)]
-    handles = []
-    for _ in range(NSTREAM):
-        hh = ctypes.c_void_p()
-        _lib.check(lib.bx_create(local, ctypes.byref(hh)))
-        handles.append(hh)
+    G = args.gather_every if args.gather_every > 0 else max(1, (K + 3) // 4)
 
-    # N > 1: the only collective of the path — all-gather of the per-image detection records (kept boxes + counts)
-    # bx_allgather_detections on torch's own ncclComm_t: boxes + counts in one fused NCCL group on the step's stream
-    gathered = [(torch.empty((world * G * B, post, 4), device=dev), torch.empty((world * G * B,), dtype=torch.int32, device=dev))
-                for _ in range(NBK)] if world > 1 else None
-    comm = None
-    if world > 1:
-        from tf_eager_object_detection_b200.distributed import nccl_comm_ptr
-        comm = nccl_comm_ptr()
-        comm = ctypes.c_void_p(comm) if comm is not None else None   # None: torch build without _comm_ptr -> torch collectives
-    step_done = {}                                       # step -> event recorded behind its kernels (N > 1)
-    bucket_free = [None] * NBK                           # event behind the last all-gather that read the bucket
+    pipe = None
 
-    def gather_bucket(last_step, n_in_bucket):
-        """All-gather the bucket whose last filled slot belongs to `last_step`, on that step's stream."""
-        b, s = (last_step // G) % NBK, last_step % NSTREAM
-        for k in range(last_step - n_in_bucket + 1, last_step):
-            ev_k = step_done.pop(k, None)
-            if ev_k is not None:
-                streams[s].wait_event(ev_k)
-        step_done.pop(last_step, None)
-        rows = n_in_bucket * B
-        if comm is not None:
-            _lib.check(lib.bx_allgather_detections(handles[s], comm, bk_boxes[b].data_ptr(), bk_counts[b].data_ptr(), rows,
-                                                   post, 4, world, gathered[b][0].data_ptr(), gathered[b][1].data_ptr(),
-                                                   ctypes.c_void_p(streams[s].cuda_stream)))
-        else:
-            with torch.cuda.stream(streams[s]):
-                dist.all_gather_into_tensor(gathered[b][0][:world * rows], bk_boxes[b][:rows])
-                dist.all_gather_into_tensor(gathered[b][1][:world * rows], bk_counts[b][:rows])
-        ev = torch.cuda.Event(); ev.record(streams[s]); bucket_free[b] = ev
-
-    def launch(step, last_of_run=False):
-        s = step % NSTREAM
-        din, o = d_in[step % NBUF], outs_of(step)
-        if world > 1 and step % G == 0 and bucket_free[(step // G) % NBK] is not None:
-            for s2 in range(NSTREAM):                    # nobody refills the bucket before its all-gather has read it
-                streams[s2].wait_event(bucket_free[(step // G) % NBK])
-            bucket_free[(step // G) % NBK] = None
-        _lib.check(lib.bx_c4_proposal_roi(handles[s], anchors.data_ptr(), din['deltas'].data_ptr(),
+    def launch(step, pos, si):
+        din = d_in[step % NBUF]
+        lo = pos * B
+        _lib.check(lib.bx_c4_proposal_roi(pipe.handles[si], anchors.data_ptr(), din['deltas'].data_ptr(),
                                           din['scores'].data_ptr(), din['feat'].data_ptr(), B, n, fh, fw, C,
-                                          ctypes.byref(params), float(w['stride']), P, _lib.POOL_NONE, o[0].data_ptr(),
-                                          o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(),
-                                          ctypes.c_void_p(streams[s].cuda_stream)))
-        if world > 1:
-            if step % G == G - 1 or last_of_run:
-                gather_bucket(step, step % G + 1)
-            else:
-                ev = torch.cuda.Event(); ev.record(streams[s]); step_done[step] = ev
+                                          ctypes.byref(params), float(w['stride']), P, _lib.POOL_NONE,
+                                          rec['boxes'][lo:lo + B].data_ptr(), idx_bufs[si].data_ptr(),
+                                          rec['counts'][lo:lo + B].data_ptr(), feat_bufs[si].data_ptr(),
+                                          ctypes.c_void_p(pipe.streams[si].cuda_stream)))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def launch_roi_only(step, pos, si):
+        """The RoI-pooling launch pair of a step (plan + band kernel) on the rois the full steps produced."""
+        din = d_in[step % NBUF]
+        lo = pos * B
+        _lib.check(lib.bx_roi_pool(pipe_roi.handles[si], _lib.ROI_STRIDE_NORM, _lib.POOL_NONE, P, din['feat'].data_ptr(), B, fh,
+                                   fw, C, rec['boxes'][lo:lo + B].data_ptr(), None, rec['counts'][lo:lo + B].data_ptr(),
+                                   B * post, float(w['stride']), w['image_hw'][0], w['image_hw'][1],
+                                   feat_bufs[si].data_ptr(), ctypes.c_void_p(pipe_roi.streams[si].cuda_stream)))
+
+    pipe = Pipeline(ctx, NSTREAM, launch, rec, G)
+    pipe_roi = Pipeline(ctx, NSTREAM, launch_roi_only)
+    pipe.timed(NSTREAM, 0)                                   # priming (eager): every handle allocates its workspace
+    pipe_roi.timed(NSTREAM, 0)
+    pipe.timed(W, 0, key=('warm', W))                        # warm-up: W steps (>= 3)
+    launches0 = pipe.launches()
+    g_timed = pipe.graph(K, W, ('timed', K))                 # capture (untimed) + one untimed priming replay
+    if g_timed is not None:
+        g_timed.replay(); g_timed._bx_primed = True
         torch.cuda.synchronize()
+        launches0 = pipe.launches()
+    sampler = ClockSampler(ctx.local); sampler.start()
+    ms = pipe.timed(K, W, key=('timed', K))                  # ---- the timed region: K steps
+    gpu_launches = (pipe.launches() - launches0) if g_timed is None else None
+    ms_max, ms_ranks = ctx.max_over_ranks(ms)
+    value = ctx.world * K * B / (ms_max * 1e-3)
+    assert bool((rec['counts'][:K * B] == post).all()), 'a step kept fewer than post_nms proposals'
+    gather_ok = verify_gather(ctx, rec, K, G) if ctx.world > 1 else None
+    launches_per_step = 3                                    # proposals_kernel, roi_plan_kernel, roi_band_kernel
+    if gpu_launches is None:                                 # graph replay: kernel nodes of the captured region
+        gpu_launches = K * launches_per_step + (((K + G - 1) // G) if ctx.world > 1 else 0)
 
-    main = torch.cuda.current_stream(dev)
-
-    def timed(nsteps, first):
-        """K steps round-robin over the streams; device time from a start event (main stream, all streams wait on it)
-        to an end event recorded after every stream has been joined back into the main stream."""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record(main)
-        for s in streams:
-            s.wait_event(e0)
-        for k in range(nsteps):
-            launch(first + k, last_of_run=(k == nsteps - 1))
-        for s in streams:
-            ev = torch.cuda.Event(); ev.record(s); main.wait_event(ev)
-        e1.record(main)
-        barrier()
-        return e0.elapsed_time(e1)
-
-    def timed_single_stream(nsteps, first):
-        """The same steps on ONE stream: per-launch CUDA-event durations of the RoI kernels without co-running launches."""
-        saved = NSTREAM
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record(main)
-        streams[0].wait_event(e0)
-        for k in range(nsteps):
-            launch((first + k) * saved * G, last_of_run=True)   # multiple of NSTREAM * G -> stream 0, slot 0, own gather
-        ev = torch.cuda.Event(); ev.record(streams[0]); main.wait_event(ev)
-        e1.record(main)
-        barrier()
-        return e0.elapsed_time(e1)
-
-    timed(NSTREAM, 0)                                   # priming, not a warm-up step: every stream's handle allocates its workspace
-    timed(max(3, args.warmup), 0)                       # warm-up (>= 3 steps)
-    launches_w = [int(lib.bx_launch_count(hh)) for hh in handles]
-    sampler = ClockSampler(local); sampler.start()
-    ms = timed(args.steps, max(3, args.warmup))         # ---- the timed region: K steps pipelined over the streams
-    launches_t = [int(lib.bx_launch_count(hh)) for hh in handles]
-    gpu_launches = sum(launches_t) - sum(launches_w)
-    # ---- roofline leg: the dominant kernel pair (plan + band) bracketed by CUDA events on its launch stream, K steps
-    #      issued on one stream so that every launch is timed alone (compared with the burst HBM peak)
-    _lib.check(lib.bx_profile_roi(handles[0], 1, args.steps + 2))
-    ms_single = timed_single_stream(args.steps, 1)
+    # ---- roofline leg, same regime as `value`: the dominant kernel pair (plan + band) of the same K steps, pipelined
+    #      over the same streams, one graph replay; average launch duration = region time / K
+    ms_roi = pipe_roi.timed(K, W, key=('roi', K))
+    ms_roi_max, _ = ctx.max_over_ranks(ms_roi)
+    # ---- single-stream regime: the same K steps on ONE stream, every RoI launch bracketed by CUDA events (timed alone)
+    _lib.check(lib.bx_profile_roi(pipe.handles[0], 1, K + 2))
+    ms_single = pipe.timed(K, W, only_stream=0)
+    buf = (ctypes.c_float * (K + 4))(); cnt = ctypes.c_int()
+    _lib.check(lib.bx_profile_read(pipe.handles[0], buf, K + 4, ctypes.byref(cnt)))
+    roi_ms_alone = list(buf[:cnt.value])
+    _lib.check(lib.bx_profile_roi(pipe.handles[0], 0, 0))
+    ms_single_max, _ = ctx.max_over_ranks(ms_single)
     sampler.stop_flag = True; sampler.join()
-    buf = (ctypes.c_float * (args.steps + 4))(); cnt = ctypes.c_int()
-    _lib.check(lib.bx_profile_read(handles[0], buf, args.steps + 4, ctypes.byref(cnt)))
-    roi_ms = list(buf[:cnt.value])
-    _lib.check(lib.bx_profile_roi(handles[0], 0, 0))
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * args.steps * B / (ms_max * 1e-3)
-
-    # ---- sanity inside the bench: every image filled its quota (otherwise the work measured is not the workload)
-    for c_ in bk_counts if world > 1 else [outs_of(k_)[2] for k_ in range(NSTREAM)]:
-        assert bool((c_ == post).all()), 'a step kept fewer than post_nms proposals'
-    if world > 1:                                       # a gathered bucket holds this rank's records at its slot
-        torch.cuda.synchronize()
-        gather_bucket(G - 1, G)                         # bucket 0, all G slots
-        torch.cuda.synchronize()
-        assert torch.equal(gathered[0][0][rank * G * B:(rank + 1) * G * B], bk_boxes[0]), 'all-gather mismatch (boxes)'
-        assert torch.equal(gathered[0][1][rank * G * B:(rank + 1) * G * B], bk_counts[0]), 'all-gather mismatch (counts)'
+    stats = _lib.stats(pipe.handles[0])
 
     # ---- e2e: the public Python API with HOST (pinned) buffers; H2D inputs + D2H outputs inside the timed region
-    e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    hb = host_batches[0]
-    # pinned staging buffers are allocated (first touch) while the process is bound to the CPUs local to its GPU
+    e2e_steps = max(3, min(K, args.e2e_steps))
+    cpus, numa_how = gpu_numa_cpus(ctx.local) if ctx.world > 1 else (None, 'single process')
     old_affinity = os.sched_getaffinity(0)
-    numa = bind_to_gpu_numa_node(local) if world > 1 else None
+    if cpus:
+        os.sched_setaffinity(0, cpus)                         # first touch of the pinned buffers on the GPU's own node
     pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
     NE = 2   # two streams, two sets of pinned buffers: the D2H of step i overlaps the H2D + kernels of step i+1
     h_in = [dict(deltas=pin(b_['deltas']), scores=pin(b_['scores']), feat=pin(b_['feat'])) for b_ in host_batches[:NE]]
     h_outs = [(torch.empty((B, post, 4)).pin_memory(), torch.empty((B, post), dtype=torch.int32).pin_memory(),
                torch.empty((B,), dtype=torch.int32).pin_memory(), torch.empty((B * post, P, P, C)).pin_memory())
               for _ in range(NE)]
-    if numa is not None:
+    if cpus:
         os.sched_setaffinity(0, old_affinity)
     h2d = sum(t_.numel() * t_.element_size() for t_ in h_in[0].values())
     d2h = sum(t_.numel() * t_.element_size() for t_ in h_outs[0])
@@ -413,76 +550,295 @@ def run_ours(args):
                                      iou_threshold=w['iou_thr'])
     for k in range(NE):
         e2e_step(k)
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(main)
+    e0.record(ctx.main)
     for s_ in e_streams:
         s_.wait_event(e0)
     for k in range(e2e_steps):
         e2e_step(k)
     for s_ in e_streams:
-        ev = torch.cuda.Event(); ev.record(s_); main.wait_event(ev)
-    e1.record(main)
-    barrier()
+        ev = torch.cuda.Event(); ev.record(s_); ctx.main.wait_event(ev)
+    e1.record(ctx.main)
+    ctx.barrier()
     e2e_ms = e0.elapsed_time(e1)
     wall_ms = (time.perf_counter() - t0) * 1e3
     assert all(int(o[2].min()) == post for o in h_outs)
-    t = torch.tensor([max(e2e_ms, 0.0)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * B / (float(t.item()) * 1e-3)
+    e2e_ms_max, e2e_ranks = ctx.max_over_ranks(max(e2e_ms, 0.0))
+    e2e_value = ctx.world * e2e_steps * B / (e2e_ms_max * 1e-3)
 
-    if rank == 0:
+    out = None
+    if ctx.rank == 0:
         b_prop, b_roi = algorithmic_bytes(w, n, fh, fw)
         peak, which = hbm_peak()
-        roi_avg_ms = sum(roi_ms) / max(1, len(roi_ms))
-        roi_bytes = B * b_roi                           # one launch pools the whole batch
-        achieved = roi_bytes / (roi_avg_ms * 1e-3) / 1e9 if roi_avg_ms > 0 else 0.0
+        roi_bytes = B * b_roi                                 # one launch pair pools the whole batch
         step_bytes = B * (b_prop + b_roi)
-        # the CPU arm is timed on rank 0 at N=1 only (all host cores belong to the one process there)
-        cpu = run_cpu_baseline(w, host_batches[0]) if world == 1 else dict(
+        roi_avg_ms = ms_roi_max / K
+        achieved = roi_bytes / (roi_avg_ms * 1e-3) / 1e9
+        alone_ms = sum(roi_ms_alone) / max(1, len(roi_ms_alone))
+        frac = lambda bytes_, ms_: round(bytes_ / (ms_ * 1e-3) / 1e9 / peak, 4)  # noqa: E731
+        cpu = run_cpu_baseline(w, host_batches[0]) if ctx.world == 1 else dict(
             value=None, unit=UNIT, cores=0, kind='port', sample='not run at N > 1: measured on rank 0 at N = 1 only')
-        line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps,
-                    warmup=max(3, args.warmup), ms_per_step=round(ms_max / args.steps, 5), higher_is_better=True,
-                    scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                    config=dict(workload=w['name'], images_per_step_per_gpu=B, streams=NSTREAM,
-                                parallelism='images sharded over GPUs, no data-path collective; NCCL all-gather of the '
-                                            'per-image detection records, %d steps per bucket (bx_allgather_detections on the process group\'s '
-                                            'ncclComm_t)' % G if world > 1 else 'single GPU',
-                                l2='working set %.0f MB/step (inputs rotate over %d batches, outputs %.0f MB) > 126 MB L2'
-                                   % (step_bytes / 1e6, NBUF, B * post * P * P * C * 4 / 1e6),
-                                algorithmic_bytes_per_image=b_prop + b_roi,
-                                composite_hbm_frac=round(step_bytes * args.steps / (ms_max * 1e-3) / 1e9 / peak, 4)),
-                    roofline=dict(bound='hbm', kernel='roi_plan_kernel + roi_band_kernel (RoI pooling of one batch)',
-                                  achieved=round(achieved, 1), peak=peak, peak_source=which, unit='GB/s',
-                                  frac=round(achieved / peak, 4), traffic=NCU_TRAFFIC_BYTES_PER_LAUNCH,
-                                  traffic_source='profiles/ (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum)',
-                                  launches_timed=len(roi_ms), avg_launch_ms=round(roi_avg_ms, 5),
-                                  algorithmic_bytes_per_launch=roi_bytes,
-                                  timed='CUDA events around every launch, same K steps issued on one stream '
-                                        '(kernel timed alone); single-stream step %.5f ms' % (ms_single / args.steps)),
-                    cpu_baseline=cpu,
-                    e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             steps=e2e_steps, ms_per_step=round(e2e_ms / e2e_steps, 3), wall_ms_per_step=round(wall_ms / e2e_steps, 3),
-                             api='ops.c4_proposal_roi_host -> bx_c4_proposal_roi_host (pinned host buffers, 2 streams)',
-                             numa_bound_cpus=numa),
-                    gpu_launches=gpu_launches, clocks=sampler.summary())
+        out = dict(
+            metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=ctx.world, steps=K, warmup=W,
+            ms_per_step=round(ms_max / K, 5), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+            data='synthetic', config=headline_config(w),
+            details=dict(streams=NSTREAM, issue='one CUDA-graph replay of the K steps' if g_timed is not None else 'eager launches',
+                         graph_error=ctx.graph_error,
+                         priming='one eager step per stream (workspace allocation) and one untimed replay of the step graph '
+                                 '(executable-graph upload) precede the W warm-up steps / the timed replay',
+                         parallelism=('images sharded over GPUs, no data-path collective; detection records (kept boxes + counts) of every '
+                                      '%d steps all-gathered by bx_allgather_detections on a dedicated ncclComm_t, on a communication '
+                                      'branch of the step graph no compute stream waits for; every rank verifies every rank\'s '
+                                      'gathered records' % G) if ctx.world > 1 else 'single GPU',
+                         gather_verified=gather_ok, ms_per_rank=ms_ranks,
+                         rank_skew=round((max(ms_ranks) - min(ms_ranks)) / max(ms_ranks), 4),
+                         algorithmic_bytes_per_image=b_prop + b_roi, band_launches=stats['band_launches'],
+                         band_fallbacks=stats['band_fallbacks']),
+            regimes=dict(
+                pipelined=dict(ms_per_step=round(ms_max / K, 5), images_per_s=round(value, 1),
+                               composite_hbm_frac=frac(step_bytes * K, ms_max), streams=NSTREAM,
+                               roi_launch_ms=round(roi_avg_ms, 5), roi_hbm_frac=round(achieved / peak, 4)),
+                single_stream=dict(ms_per_step=round(ms_single_max / K, 5),
+                                   images_per_s=round(ctx.world * K * B / (ms_single_max * 1e-3), 1),
+                                   composite_hbm_frac=frac(step_bytes * K, ms_single_max), streams=1,
+                                   roi_launch_ms=round(alone_ms, 5), roi_hbm_frac=frac(roi_bytes, alone_ms),
+                                   launches_timed=len(roi_ms_alone))),
+            roofline=dict(bound='hbm', kernel='roi_plan_kernel + roi_band_kernel (RoI pooling of one batch)',
+                          achieved=round(achieved, 1), peak=peak, peak_source=which, unit='GB/s',
+                          frac=round(achieved / peak, 4), traffic=NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                          traffic_source='profiles/ (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum)',
+                          launches_timed=K, avg_launch_ms=round(roi_avg_ms, 5), algorithmic_bytes_per_launch=roi_bytes,
+                          regime='pipelined (the regime of `value`): the K RoI launch pairs of the timed steps, same streams, '
+                                 'one graph replay between CUDA events; avg_launch_ms = region time / K <= ms_per_step',
+                          alone_launch_ms=round(alone_ms, 5), alone_frac=frac(roi_bytes, alone_ms)),
+            cpu_baseline=cpu,
+            e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                     steps=e2e_steps, ms_per_step=round(e2e_ms_max / e2e_steps, 3), wall_ms_per_step=round(wall_ms / e2e_steps, 3),
+                     h2d_gbs_per_gpu=round(h2d * e2e_steps / (e2e_ms_max * 1e-3) / 1e9, 2),
+                     d2h_gbs_per_gpu=round(d2h * e2e_steps / (e2e_ms_max * 1e-3) / 1e9, 2),
+                     host_link_gbs_all_gpus=round(ctx.world * (h2d + d2h) * e2e_steps / (e2e_ms_max * 1e-3) / 1e9, 1),
+                     bound='PCIe: the step moves 82 MB in and 482 MB out per 8 images; the kernels take 0.19 ms of it',
+                     ms_per_rank=e2e_ranks,
+                     api='ops.c4_proposal_roi_host -> bx_c4_proposal_roi_host (pinned host buffers, 2 streams)',
+                     numa=(('bound to %d CPUs (%s)' % (len(cpus), numa_how)) if cpus else numa_how)),
+            gpu_launches=gpu_launches, clocks=sampler.summary())
+    pipe.close(); pipe_roi.close()
+    del d_in, feat_bufs, h_outs, h_in, rec
+    torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------- other workloads
+FPN = dict(
+    cfg3=dict(name='cfg3: ResNet-101 FPN 600x1000, 150111 anchors P2-P6, one global NMS -> 1000 rois/image (reference behaviour), '
+                   'level assignment + RoI extractor 14x14 crop + 2x2 max -> 7x7x256 over P2-P5, batch 16/GPU',
+              cfg=3, image_hw=(600, 1000), batch=16, scaling='weak'),
+    cfg5=dict(name='cfg5: COCO-shape FPN 800x1333, 267069 anchors P2-P6, one global NMS -> 1000 rois/image, level assignment + RoI '
+                   'extractor 14x14 crop + 2x2 max -> 7x7x256 over P2-P5, batch 64 sharded over the GPUs, detection all-gather',
+              cfg=5, image_hw=(800, 1333), batch=64, scaling='strong'))
+FPN_POST, FPN_P, FPN_C, FPN_NLEV, FPN_NSRC = 1000, 7, 256, 4, 4
+
+
+def bench_fpn(ctx, args, name):
+    """cfg3 / cfg5: proposals over the P2..P6 concatenation (base_fpn_model.py:219-225) + level assignment + FPN RoI
+    extractor (:152-161, :303-324), straight through the C ABI with preallocated outputs."""
+    torch, lib, _lib = ctx.torch, ctx.lib, ctx._lib
+    from tf_eager_object_detection_b200 import ops
+    w = FPN[name]
+    hw = w['image_hw']
+    B = w['batch'] if w['scaling'] == 'weak' else max(1, w['batch'] // ctx.world)
+    K, W = max(3, min(args.steps, args.workload_steps)), 3
+    dev = ctx.dev
+    POST, P, C, NLEV = FPN_POST, FPN_P, FPN_C, FPN_NLEV
+    ims = [syn.fpn_image(w['cfg'], ctx.rank * 100 + i, hw, with_features=False) for i in range(FPN_NSRC)]
+    n = ims[0]['anchors'].shape[0]
+    anchors = torch.as_tensor(ims[0]['anchors']).to(dev)
+    rep = (B + FPN_NSRC - 1) // FPN_NSRC
+    shapes = syn.fpn_feature_shapes(hw)[:NLEV]
+    NSTREAM = max(1, args.fpn_streams)
+    NBUF = 2
+    g = torch.Generator(device=dev); g.manual_seed(1234 + ctx.rank)
+    d_in = []
+    for k in range(NBUF):
+        order = [(i + k) % FPN_NSRC for i in range(FPN_NSRC)]
+        d_in.append(dict(
+            deltas=torch.as_tensor(np.stack([ims[i]['deltas'] for i in order])).to(dev).repeat(rep, 1, 1)[:B].contiguous(),
+            scores=torch.as_tensor(np.stack([ims[i]['scores'] for i in order])).to(dev).repeat(rep, 1)[:B].contiguous(),
+            feats=[torch.randn((B, h, wd, C), device=dev, generator=g) for h, wd in shapes]))
+    for d in d_in:
+        d['fptr'] = (ctypes.c_void_p * NLEV)(*[f.data_ptr() for f in d['feats']])
+    fh = (ctypes.c_int * NLEV)(*[s[0] for s in shapes]); fw = (ctypes.c_int * NLEV)(*[s[1] for s in shapes])
+    bi = torch.arange(B, device=dev, dtype=torch.int32).repeat_interleave(POST)
+    rec = make_records(ctx, max(K, W, NSTREAM), B, POST)
+    idx_bufs = [torch.empty((B, POST), dtype=torch.int32, device=dev) for _ in range(NSTREAM)]
+    out_bufs = [torch.empty((B * POST, P, P, C), device=dev) for _ in range(NSTREAM)]
+    lv_bufs = [(torch.empty((B * POST,), dtype=torch.int32, device=dev), torch.empty((B * POST,), dtype=torch.int32, device=dev),
+                torch.zeros((NLEV,), dtype=torch.int32, device=dev)) for _ in range(NSTREAM)]
+    params = ops.proposal_params(hw, POST, 0.7)
+    G = max(1, (K + 3) // 4)
+    pipe = None
+
+    def launch(step, pos, si):
+        din = d_in[step % NBUF]
+        lo = pos * B
+        st = ctypes.c_void_p(pipe.streams[si].cuda_stream)
+        rois = rec['boxes'][lo:lo + B]
+        _lib.check(lib.bx_proposals(pipe.handles[si], anchors.data_ptr(), din['deltas'].data_ptr(), din['scores'].data_ptr(), B,
+                                    n, ctypes.byref(params), rois.data_ptr(), idx_bufs[si].data_ptr(),
+                                    rec['counts'][lo:lo + B].data_ptr(), st))
+        lv, order, counts = lv_bufs[si]
+        _lib.check(lib.bx_fpn_roi_features(pipe.handles[si], din['fptr'], fh, fw, NLEV, 2, B, C, rois.data_ptr(), bi.data_ptr(),
+                                           B * POST, hw[0], hw[1], P, out_bufs[si].data_ptr(), lv.data_ptr(), order.data_ptr(),
+                                           counts.data_ptr(), st))
+
+    pipe = Pipeline(ctx, NSTREAM, launch, rec, G)
+    pipe.timed(NSTREAM, 0)                                   # priming (eager)
+    pipe.timed(W, 0, key=('warm', W))
+    ms = pipe.timed(K, W, key=('timed', K))
+    ms_max, ms_ranks = ctx.max_over_ranks(ms)
+    assert bool((rec['counts'][:K * B] == POST).all()), '%s: a step kept fewer than 1000 proposals' % name
+    gather_ok = verify_gather(ctx, rec, K, G) if ctx.world > 1 else None
+    _lib.check(lib.bx_profile_roi(pipe.handles[0], 1, K + 2))
+    ms_single = pipe.timed(K, W, only_stream=0)
+    buf = (ctypes.c_float * (K + 4))(); cnt = ctypes.c_int()
+    _lib.check(lib.bx_profile_read(pipe.handles[0], buf, K + 4, ctypes.byref(cnt)))
+    roi_ms = list(buf[:cnt.value])
+    _lib.check(lib.bx_profile_roi(pipe.handles[0], 0, 0))
+    ms_single_max, _ = ctx.max_over_ranks(ms_single)
+    out = None
+    if ctx.rank == 0:
+        peak, _ = hbm_peak()
+        b_prop = 36 * n + 20 * POST
+        b_roi = 4 * C * sum(h * wd for h, wd in shapes) + 16 * POST + 4 * POST * P * P * C
+        roi_avg = sum(roi_ms) / max(1, len(roi_ms))
+        value = ctx.world * K * B / (ms_max * 1e-3)
+        out = dict(workload=w['name'], scaling=w['scaling'], images_per_step_per_gpu=B, steps=K, warmup=W, streams=NSTREAM,
+                   ms_per_step=round(ms_max / K, 5), images_per_s=round(value, 1),
+                   composite_hbm_frac=round(B * (b_prop + b_roi) * K / (ms_max * 1e-3) / 1e9 / peak, 4),
+                   algorithmic_bytes_per_image=b_prop + b_roi,
+                   single_stream=dict(ms_per_step=round(ms_single_max / K, 5),
+                                      images_per_s=round(ctx.world * K * B / (ms_single_max * 1e-3), 1)),
+                   roofline=dict(bound='hbm', kernel='FPN RoI extractor launch of one batch (level assignment + pooled crop kernel)',
+                                 avg_launch_ms=round(roi_avg, 5), algorithmic_bytes_per_launch=B * b_roi,
+                                 achieved=round(B * b_roi / (roi_avg * 1e-3) / 1e9, 1) if roi_avg > 0 else None,
+                                 frac=round(B * b_roi / (roi_avg * 1e-3) / 1e9 / peak, 4) if roi_avg > 0 else None,
+                                 launches_timed=len(roi_ms), regime='single stream, CUDA events around every launch'),
+                   gather_verified=gather_ok, ms_per_rank=ms_ranks)
+    pipe.close()
+    del d_in, out_bufs, rec
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_targets(ctx, args):
+    """cfg4: anchor_target (21 546 anchors x 100 gt) + proposal_target (2000 training proposals x 100 gt), batch 16,
+    fixed-permutation sampling (anchor_target.py:29-107, proposal_target.py:32-124)."""
+    torch, lib, _lib = ctx.torch, ctx.lib, ctx._lib
+    from tf_eager_object_detection_b200 import ops
+    name = ('cfg4: training targets, anchor_target (21546 anchors x 100 gt, 256 samples) + proposal_target (2000 rois x 100 gt, '
+            '128 samples, 21 classes), fixed-permutation sampling, batch 16/GPU')
+    B, M, Kr, S, NC = 16, 100, 2000, 128, 21
+    K, W = max(3, min(args.steps, args.workload_steps)), 3
+    dev = ctx.dev
+    imgs = [syn.c4_image(4, ctx.rank * 100 + i, with_features=False) for i in range(B)]
+    anchors = torch.as_tensor(imgs[0]['anchors']).to(dev)
+    n = anchors.shape[0]
+    rng = np.random.default_rng(syn.seed_for(4, 900 + ctx.rank))
+    gts, gls = zip(*[syn.gt_boxes(rng, M, (600, 1000)) for _ in range(B)])
+    gt = torch.as_tensor(np.stack(gts)).to(dev); gl = torch.as_tensor(np.stack(gls)).to(dev)
+    perm_a = torch.as_tensor(np.stack([rng.permutation(n) for _ in range(B)]).astype(np.int32)).to(dev)
+    perm_r = torch.as_tensor(np.stack([rng.permutation(Kr) for _ in range(B)]).astype(np.int32)).to(dev)
+    deltas = torch.as_tensor(np.stack([im['deltas'] for im in imgs])).to(dev)
+    scores = torch.as_tensor(np.stack([im['scores'] for im in imgs])).to(dev)
+    rois, _, rc = ops.proposals(anchors, deltas, scores, (600, 1000), Kr)            # the 2000 training proposals (untimed)
+    torch.cuda.synchronize()
+    NSTREAM = 2
+    o = [dict(lab=torch.empty((B, n), device=dev), tg=torch.empty((B, n, 4), device=dev), iw=torch.empty((B, n, 4), device=dev),
+              ow=torch.empty((B, n, 4), device=dev), cnt=torch.empty((B, 2), dtype=torch.int32, device=dev),
+              pr=torch.empty((B, S, 4), device=dev), pl=torch.empty((B, S), dtype=torch.int32, device=dev),
+              pt=torch.empty((B, S, 4 * NC), device=dev), pi=torch.empty((B, S, 4 * NC), device=dev),
+              po=torch.empty((B, S, 4 * NC), device=dev), pk=torch.empty((B, S), dtype=torch.int32, device=dev),
+              pc=torch.empty((B, 2), dtype=torch.int32, device=dev)) for _ in range(NSTREAM)]
+    f4 = _lib.f4
+    ap = _lib.AnchorTargetParams(0.7, 0.3, 256, 128, f4((0, 0, 0, 0)), f4((1, 1, 1, 1)), 600, 1000)
+    pp = _lib.ProposalTargetParams(NC, 0.5, 0.0, S, 32, f4((0, 0, 0, 0)), f4((0.1, 0.1, 0.2, 0.2)))
+    pipe = None
+
+    def launch(step, pos, si):
+        st = ctypes.c_void_p(pipe.streams[si].cuda_stream)
+        b = o[si]
+        _lib.check(lib.bx_anchor_target(pipe.handles[si], anchors.data_ptr(), n, gt.data_ptr(), None, B, M, perm_a.data_ptr(),
+                                        ctypes.byref(ap), b['lab'].data_ptr(), b['tg'].data_ptr(), b['iw'].data_ptr(),
+                                        b['ow'].data_ptr(), b['cnt'].data_ptr(), st))
+        _lib.check(lib.bx_proposal_target(pipe.handles[si], rois.data_ptr(), rc.data_ptr(), Kr, gt.data_ptr(), gl.data_ptr(), None,
+                                          B, M, perm_r.data_ptr(), ctypes.byref(pp), b['pr'].data_ptr(), b['pl'].data_ptr(),
+                                          b['pt'].data_ptr(), b['pi'].data_ptr(), b['po'].data_ptr(), b['pk'].data_ptr(),
+                                          b['pc'].data_ptr(), st))
+
+    pipe = Pipeline(ctx, NSTREAM, launch)
+    pipe.timed(NSTREAM, 0)
+    pipe.timed(W, 0, key=('warm', W))
+    ms = pipe.timed(K, W, key=('timed', K))
+    ms_max, ms_ranks = ctx.max_over_ranks(ms)
+    ms_single = pipe.timed(K, W, only_stream=0)
+    ms_single_max, _ = ctx.max_over_ranks(ms_single)
+    assert bool((o[0]['pc'][:, 1] == 0).all()) and bool((o[0]['cnt'].sum(dim=1) == 256).all())
+    out = None
+    if ctx.rank == 0:
+        peak, _ = hbm_peak()
+        b_atgt = 16 * (n + M) + 52 * n
+        b_ptgt = 16 * (Kr + M) + 4 * M + S * (16 + 4 + 3 * 16 * NC)
+        out = dict(workload=name, scaling='weak', images_per_step_per_gpu=B, steps=K, warmup=W, streams=NSTREAM,
+                   ms_per_step=round(ms_max / K, 5), images_per_s=round(ctx.world * K * B / (ms_max * 1e-3), 1),
+                   composite_hbm_frac=round(B * (b_atgt + b_ptgt) * K / (ms_max * 1e-3) / 1e9 / peak, 4),
+                   algorithmic_bytes_per_image=b_atgt + b_ptgt,
+                   single_stream=dict(ms_per_step=round(ms_single_max / K, 5),
+                                      images_per_s=round(ctx.world * K * B / (ms_single_max * 1e-3), 1)),
+                   roofline=dict(bound='latency (7 dependent launches over 1.9 MB per image; not bandwidth-bound)',
+                                 kernel='bx_anchor_target (5 launches) + bx_proposal_target (2 launches), one batch',
+                                 avg_launch_ms=round(ms_single_max / K, 5), algorithmic_bytes_per_launch=B * (b_atgt + b_ptgt),
+                                 frac=round(B * (b_atgt + b_ptgt) * K / (ms_single_max * 1e-3) / 1e9 / peak, 4)),
+                   ms_per_rank=ms_ranks)
+    pipe.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    ctx = Ctx(args)
+    line = bench_c4(ctx, args)
+    names = ['cfg3', 'cfg5', 'cfg4'] if args.workloads == 'all' else [s for s in args.workloads.split(',') if s and s != 'none']
+    extra = {}
+    for nm in names:
+        try:
+            extra[nm] = bench_targets(ctx, args) if nm == 'cfg4' else bench_fpn(ctx, args, nm)
+        except Exception as e:                               # a secondary workload never takes the headline line down
+            extra[nm] = dict(error='%s: %s' % (type(e).__name__, str(e)[:300]))
+            ctx.torch.cuda.synchronize()
+    if ctx.rank == 0:
+        line['workloads'] = extra
+        line['details']['graph_error'] = ctx.graph_error
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=1000)
+    ap.add_argument('--steps', type=int, default=400)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--streams', type=int, default=8, help='steps are issued round-robin over this many CUDA streams')
+    ap.add_argument('--fpn-streams', type=int, default=4)
     ap.add_argument('--e2e-steps', type=int, default=20)
-    ap.add_argument('--gather-every', type=int, default=4,
-                    help='N > 1: detection records of this many consecutive steps are all-gathered together')
+    ap.add_argument('--gather-every', type=int, default=0,
+                    help='N > 1: detection records of this many consecutive steps are all-gathered together (0: K/4)')
+    ap.add_argument('--workloads', default='all', help='all | none | comma list of cfg3,cfg5,cfg4 (measured after the headline)')
+    ap.add_argument('--workload-steps', type=int, default=100, help='cap on the steps of the extra workloads')
+    ap.add_argument('--no-graph', action='store_true', help='issue the timed region eagerly instead of as one CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -192,7 +192,10 @@ int bx_pairwise_iou(bx_handle* h, const float* a, int n, const float* b, int m, 
  *      anchors [n,4] shared; gt [batch,max_gt,4] with gt_counts [batch] (NULL: all max_gt valid);
  *      perm [batch,n] int32: sampling priority per anchor replacing the reference's unseeded tf.random_shuffle
  *      (shuffle(idx) := idx sorted ascending by perm; DESIGN.md "Sampling").
- *      -> labels [batch,n] fp32 (-1/0/1), targets, in_w, out_w [batch,n,4]; counts [batch,2] = (#fg,#bg) sampled. */
+ *      -> labels [batch,n] fp32 (-1/0/1), targets, in_w, out_w [batch,n,4]; counts [batch,2] = (#fg,#bg) sampled.
+ *      An image without ground truth (max_gt == 0, gt may be NULL, or gt_counts[i] == 0) — where the reference's argmax
+ *      over an empty axis raises — is treated as max overlap 0: inside anchors are background (bx_proposal_target: every
+ *      roi is a background candidate when neg_iou_threshold <= 0). */
 typedef struct {
   float pos_iou_threshold;  /* 0.7 */
   float neg_iou_threshold;  /* 0.3 */

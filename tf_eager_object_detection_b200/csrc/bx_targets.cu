@@ -289,6 +289,8 @@ __global__ void __launch_bounds__(256) at_label_kernel(const ATArgs a) {
         if (mx < a.p.neg_iou_threshold) lab = 0;      // :67
         if (is_gt_arg) lab = 1;                       // :68
         if (mx >= a.p.pos_iou_threshold) lab = 1;     // :69
+      } else if (0.0f < a.p.neg_iou_threshold) {
+        lab = 0;   // image without ground truth (the reference's argmax over an empty axis raises): max overlap 0 -> background
       }
     }
     a.label[static_cast<size_t>(img) * a.n + i] = lab;
@@ -519,6 +521,8 @@ __global__ void __launch_bounds__(1024) proposal_target_kernel(const PTArgs a) {
       if (m > 0) {
         fg = best >= a.p.pos_iou_threshold;
         bg = (best < a.p.pos_iou_threshold) && (best >= a.p.neg_iou_threshold);
+      } else {
+        bg = (0.0f < a.p.pos_iou_threshold) && (0.0f >= a.p.neg_iou_threshold);   // no ground truth: max overlap 0
       }
     }
     if (i < pow2) {
