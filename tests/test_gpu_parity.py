@@ -1102,3 +1102,44 @@ def test_calls_run_on_the_handles_device_not_the_current_one():
     assert np.array_equal(oi[0].cpu().numpy(), idx)
     x = torch.empty(4, device='cuda')
     assert x.device.index == 0
+
+
+def test_tma_staged_extractor_matches_default_and_oracle(bx, monkeypatch):
+    """bx_roi_stage.cu (opt-in, BX_ROI_STAGE=1): the persistent TMA-staged FPN extractor — producer warp, mbarrier ring,
+    pixel-column walker — must reproduce the default kernel and the oracle bit for bit, including rois cut into several
+    strips, a pooled row too large for a stage (global taps), inverted boxes (non-monotone walker) and padded rois."""
+    from tf_eager_object_detection_b200 import _lib
+    rng = np.random.default_rng(123)
+    hw = (600, 1000)
+    shapes = syn.fpn_feature_shapes(hw)[:4]
+    B, C = 2, 128
+    feats = [rng.standard_normal((B, h, w, C), dtype=np.float32) for h, w in shapes]
+    rois = syn.random_rois(rng, 400, hw)
+    rois[:8] = np.float32([[10, 5, 40, 590], [3, 3, 990, 30], [0, 0, 999, 599], [500, 300, 500, 300],     # tall / wide / whole / point
+                           [200, 400, 100, 100], [-50, -50, 20, 20], [980, 580, 1100, 700], [300, 200, 310, 212]])   # inverted, outside
+    bi = rng.integers(0, B, 400).astype(np.int32)
+    fc = [cu(f) for f in feats]
+    monkeypatch.delenv('BX_ROI_STAGE', raising=False)
+    base, lv, order, counts = bx.fpn_roi_features(fc, cu(rois), hw, box_ind=cu(bi))
+    monkeypatch.setenv('BX_ROI_STAGE', '1')
+    for kb in ('', '12'):                                   # default stage size, and one small enough to force many strips
+        if kb:
+            monkeypatch.setenv('BX_ROI_STAGE_KB', kb)
+        got, lv2, order2, _ = bx.fpn_roi_features(fc, cu(rois), hw, box_ind=cu(bi))
+        assert torch.equal(order2, order) and torch.equal(got, base), 'stage budget %r' % kb
+    olv, _, oorder = orc.assign_levels(rois)
+    assert np.array_equal(order.cpu().numpy(), oorder)
+    got = base.cpu().numpy()
+    pos = 0
+    for l in range(4):
+        k = oorder[olv[oorder] == l + 2]
+        if k.size:
+            assert np.array_equal(got[pos:pos + k.size], orc.roi_pool_fpn(feats[l], rois[k], hw, 7, box_ind=bi[k])), l
+        pos += k.size
+    # C4 pooled extractors through the same kernel: VGG16 14x14 + max (stride norm) and RoIAlign (pad + mean)
+    feat = rng.standard_normal((1, 38, 63, 64), dtype=np.float32)
+    r2 = syn.random_rois(rng, 100, hw)
+    a = bx.roi_pool(_lib.ROI_STRIDE_NORM, _lib.POOL_MAX2, 7, cu(feat), cu(r2), stride=16.0)
+    b = bx.roi_pool(_lib.ROI_ALIGN_PAD, _lib.POOL_AVG2, 7, cu(feat), cu(r2), stride=16.0)
+    assert np.array_equal(a.cpu().numpy(), orc.roi_pool_c4(feat, r2, 16, 7, True))
+    close(b.cpu().numpy(), orc.roi_align_pad(feat, r2, 16, 7), scale=1.0)

@@ -156,13 +156,47 @@ struct __align__(16) PixRec {
   int pad[3];
 };
 
+// L2 prefetch of the feature pixels a roi will sample (its bounding box on its level: up to ~30 rows of w_f * C * 4
+// contiguous bytes in the NHWC map), one cp.async.bulk.prefetch.L2 per footprint row, issued by one warp.  The kernel is
+// bound by the latency of the compulsory DRAM misses its tap loads take in-line (ncu: long-scoreboard stalls, every
+// iteration waits for one DRAM round trip); prefetching the footprint of the roi that will run `dist` CTAs later turns
+// them into L2 hits.  Pure hint: no effect on results.  (Prefetching FOR LATER CTAs measured slower — see the launch site.)
+__device__ __forceinline__ void prefetch_footprint(const RoiArgs& a, int jp, int lane) {
+  if (jp >= a.r) return;
+  const int src = a.order ? a.order[jp] : jp;
+  const int lvl = a.level ? a.level[src] - a.level_base : 0;
+  int img = a.box_ind ? a.box_ind[src] : 0;
+  if (a.roi_counts) {
+    img = src / a.rois_per_image;
+    if ((src % a.rois_per_image) >= a.roi_counts[img]) return;
+  }
+  if (img < 0 || img >= a.b) return;
+  const int fh = a.lv[lvl].fh, fw = a.lv[lvl].fw;
+  const NormBox nb = roi_norm_box(a, a.rois[src], fh, fw);
+  const float dy = static_cast<float>(nb.dimy - 1), dx = static_cast<float>(nb.dimx - 1);
+  // conservative bounding box of the sample coordinates (un-padded map indices), clamped to the map
+  const float ya = fminf(nb.y1, nb.y2) * dy - static_cast<float>(nb.pad), yb = fmaxf(nb.y1, nb.y2) * dy - static_cast<float>(nb.pad);
+  const float xa = fminf(nb.x1, nb.x2) * dx - static_cast<float>(nb.pad), xb = fmaxf(nb.x1, nb.x2) * dx - static_cast<float>(nb.pad);
+  if (!(ya <= static_cast<float>(fh) && yb >= -1.0f && xa <= static_cast<float>(fw) && xb >= -1.0f)) return;   // also NaN
+  const int y_lo = max(static_cast<int>(floorf(fmaxf(ya, 0.0f))), 0), y_hi = min(static_cast<int>(ceilf(fminf(yb, static_cast<float>(fh - 1)))), fh - 1);
+  const int x_lo = max(static_cast<int>(floorf(fmaxf(xa, 0.0f))), 0), x_hi = min(static_cast<int>(ceilf(fminf(xb, static_cast<float>(fw - 1)))), fw - 1);
+  if (y_hi < y_lo || x_hi < x_lo) return;
+  const unsigned bytes = static_cast<unsigned>(x_hi - x_lo + 1) * static_cast<unsigned>(a.c) * 4u;
+  const float* base = a.lv[lvl].feat + (static_cast<size_t>(img) * fh * fw + x_lo) * a.c;
+  for (int y = y_lo + lane; y <= y_hi; y += 32) {
+    const float* p = base + static_cast<size_t>(y) * fw * a.c;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+  }
+}
+
 template <int POOL>
-__global__ void __launch_bounds__(256, BX_POOL2_CTAS) roi_pool2_kernel(const RoiArgs a, const float neg_zero) {
+__global__ void __launch_bounds__(256, BX_POOL2_CTAS) roi_pool2_kernel(const RoiArgs a, const float neg_zero, const int pf_dist) {
   __shared__ PixRec recs[kPool2MaxPix];
   __shared__ int s_meta[4];
   const int P = a.P, Q = a.Q;
   const int j = blockIdx.x, tid = threadIdx.x;
   const int cv = a.c >> 2;
+  if (pf_dist >= 0 && tid >= 224) prefetch_footprint(a, j + pf_dist, tid - 224);   // last warp: not a record builder (P*P <= 64)
   if (tid < P * P) {                             // one thread per output pixel builds its record (single barrier)
     const int src = a.order ? a.order[j] : j;
     const int lvl = a.level ? a.level[src] - a.level_base : 0;
@@ -463,9 +497,17 @@ int launch_roi(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
     // at roughly 0.75x the speed: not an error, but visible — bx_stats() reports the count next to bx_launch_count()
     if (!used && pool == BX_POOL_NONE && !band_pooled) h->band_fallbacks++;
   }
+  if (!used && pool != BX_POOL_NONE && !getenv("BX_ROI_NO_POOL2")) {
+    rc = roi_stage_launch(h, a, pool, st, &used);    // roi footprint staged in shared memory by TMA (bx_roi_stage.cu)
+    if (rc) return rc;
+  }
   if (!used && roi_pool2_ok(a, pool)) {
-    if (pool == BX_POOL_MAX2) roi_pool2_kernel<BX_POOL_MAX2><<<a.r, 256, 0, st>>>(a, -0.0f);
-    else roi_pool2_kernel<BX_POOL_AVG2><<<a.r, 256, 0, st>>>(a, -0.0f);
+    // L2 prefetch distance in CTAs.  Measured (cfg3 B=16 / cfg5 B=32, us): off 597 / 700, own roi (0) 578 / 653, one wave
+    // ahead (444) 625 / 830, two waves 650 / 843: only the CTA's own footprint pays.  BX_POOL2_PF overrides (-1 = off)
+    static const int pf_env = getenv("BX_POOL2_PF") ? atoi(getenv("BX_POOL2_PF")) : -2;
+    const int pf = pf_env != -2 ? pf_env : 0;
+    if (pool == BX_POOL_MAX2) roi_pool2_kernel<BX_POOL_MAX2><<<a.r, 256, 0, st>>>(a, -0.0f, pf);
+    else roi_pool2_kernel<BX_POOL_AVG2><<<a.r, 256, 0, st>>>(a, -0.0f, pf);
     BX_LAUNCH_CHECK(h);
     used = 1;
   }
@@ -492,59 +534,79 @@ __device__ __forceinline__ int roi_level(const float4 roi, int min_level, int ma
   return static_cast<int>(lv) - min_level;
 }
 
+// One CTA; thread t owns the contiguous chunk [t * chunk, (t + 1) * chunk) of the rois, so "ascending index within a
+// level" is "thread order, then position inside the thread's chunk": per level one block-wide exclusive scan of the
+// per-thread counts gives every thread the first output slot of its chunk.  Two passes over the rois (count, place), the
+// second one hitting L1; 4 scans + 3 barriers in total (the previous form walked the rois 1024 at a time with a ballot
+// round and two barriers per level and step: 45 us for 16 000 rois, now 9 us).
 __global__ void __launch_bounds__(1024) assign_levels_kernel(const float4* __restrict__ rois, int r, int min_level,
                                                              int max_level, int* __restrict__ out_level,
                                                              int* __restrict__ out_order, int* __restrict__ out_counts) {
-  __shared__ int warp_cnt[kMaxLevels][32];
-  __shared__ int base[kMaxLevels];
-  __shared__ int total[kMaxLevels];
+  __shared__ int warp_tot[kMaxLevels][32];
+  __shared__ int level_base[kMaxLevels + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nl = max_level - min_level + 1;
-  // pass 1: counts per level
-  if (tid < kMaxLevels) total[tid] = 0;
+  const int chunk = (r + 1023) / 1024;
+  const int lo = min(r, tid * chunk), hi = min(r, lo + chunk);
+  int cnt[kMaxLevels];
+#pragma unroll
+  for (int l = 0; l < kMaxLevels; ++l) cnt[l] = 0;
+  for (int i = lo; i < hi; ++i) {
+    const int lv = roi_level(rois[i], min_level, max_level);
+    if (out_level) out_level[i] = lv + min_level;
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l) cnt[l] += (lv == l) ? 1 : 0;
+  }
+  // exclusive scan of cnt[l] over the threads of the block, per level
+  int pre[kMaxLevels];
+#pragma unroll
+  for (int l = 0; l < kMaxLevels; ++l) {
+    pre[l] = 0;
+    if (l < nl) {
+      int v = cnt[l];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v += o;
+      }
+      if (lane == 31) warp_tot[l][warp] = v;
+      pre[l] = v - cnt[l];                     // exclusive prefix inside the warp
+    }
+  }
   __syncthreads();
-  for (int b0 = 0; b0 < r; b0 += 1024) {
-    const int i = b0 + tid;
-    const int lv = (i < r) ? roi_level(rois[i], min_level, max_level) : -1;
-    if (i < r && out_level) out_level[i] = lv + min_level;
+  if (warp == 0) {
     for (int l = 0; l < nl; ++l) {
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, lv == l);
-      if (lane == 0 && m) atomicAdd(&total[l], __popc(m));
+      const int t = warp_tot[l][lane];
+      int v = t;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v += o;
+      }
+      warp_tot[l][lane] = v - t;               // exclusive prefix of the warp totals
+      if (lane == 31) level_base[l + 1] = v;   // level total (prefix-summed over the levels below)
     }
   }
   __syncthreads();
   if (tid == 0) {
     int run = 0;
     for (int l = 0; l < nl; ++l) {
-      base[l] = run;
-      run += total[l];
-      if (out_counts) out_counts[l] = total[l];
+      const int tot = level_base[l + 1];
+      if (out_counts) out_counts[l] = tot;
+      level_base[l] = run;
+      run += tot;
     }
   }
   __syncthreads();
-  // pass 2: stable positions
-  for (int b0 = 0; b0 < r; b0 += 1024) {
-    const int i = b0 + tid;
-    const int lv = (i < r) ? roi_level(rois[i], min_level, max_level) : -1;
-    uint32_t my_mask = 0;
-    for (int l = 0; l < nl; ++l) {
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, lv == l);
-      if (lane == 0) warp_cnt[l][warp] = __popc(m);
-      if (lv == l) my_mask = m;
+  int pos[kMaxLevels];
+#pragma unroll
+  for (int l = 0; l < kMaxLevels; ++l) pos[l] = (l < nl) ? level_base[l] + warp_tot[l][warp] + pre[l] : 0;
+  for (int i = lo; i < hi; ++i) {
+    const int lv = roi_level(rois[i], min_level, max_level);
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l) {
+      if (lv == l) out_order[pos[l]++] = i;
     }
-    __syncthreads();
-    if (lv >= 0) {
-      int off = 0;
-      for (int w = 0; w < warp; ++w) off += warp_cnt[lv][w];
-      out_order[base[lv] + off + __popc(my_mask & ((1u << lane) - 1u))] = i;
-    }
-    __syncthreads();
-    if (tid < nl) {
-      int t = 0;
-      for (int w = 0; w < 32; ++w) t += warp_cnt[tid][w];
-      base[tid] += t;
-    }
-    __syncthreads();
   }
 }
 

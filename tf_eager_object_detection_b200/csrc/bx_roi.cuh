@@ -146,5 +146,7 @@ __device__ __forceinline__ ulonglong2 pool2(const ulonglong2 a, const ulonglong2
 
 // implemented in bx_roi_band.cu: returns BX_OK and sets *used = 1 when the band kernel handled the launch
 int roi_band_launch(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st, int* used);
+// implemented in bx_roi_stage.cu: pooled crops with the roi footprint staged in shared memory by TMA
+int roi_stage_launch(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st, int* used);
 
 }  // namespace bxroi
