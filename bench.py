@@ -649,6 +649,8 @@ def bench_fpn(ctx, args, name):
     w = FPN[name]
     hw = w['image_hw']
     B = w['batch'] if w['scaling'] == 'weak' else max(1, w['batch'] // ctx.world)
+    if args.batch_override > 0:
+        B = args.batch_override                  # experiments only: e.g. the per-GPU share of cfg5 at N = 8 on one GPU
     K, W = max(3, min(args.steps, args.workload_steps)), 3
     dev = ctx.dev
     POST, P, C, NLEV = FPN_POST, FPN_P, FPN_C, FPN_NLEV
@@ -838,6 +840,7 @@ def main():
                     help='N > 1: detection records of this many consecutive steps are all-gathered together (0: K/4)')
     ap.add_argument('--workloads', default='all', help='all | none | comma list of cfg3,cfg5,cfg4 (measured after the headline)')
     ap.add_argument('--workload-steps', type=int, default=100, help='cap on the steps of the extra workloads')
+    ap.add_argument('--batch-override', type=int, default=0, help='experiments: images per GPU and step of the FPN workloads')
     ap.add_argument('--no-graph', action='store_true', help='issue the timed region eagerly instead of as one CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':

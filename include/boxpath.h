@@ -252,6 +252,22 @@ int bx_post_ops_prediction(bx_handle* h, const float* scores, const float* delta
                            const int* roi_counts, int batch, int r, const bx_prediction_params* p, float* out_det,
                            int* out_count, void* stream);
 
+/* ---- f1, the two copies of that logic inside the reference's EVALUATION loops, which differ from post_ops_prediction in
+ *      three ways (evaluation/pascal_eval_files_utils.py:76-106, scripts/eval_coco.py:116-153):
+ *        - the rois come from im_detect, which divides them by the image's resize factor first
+ *          (faster_rcnn/base_faster_rcnn_model.py:304 `rois / img_scale`): img_scale [batch] fp32 or NULL;
+ *        - boxes are clipped to the image's own RAW size: image_sizes [batch,2] = (raw_h, raw_w) fp32 (x to [0, raw_w-1],
+ *          y to [0, raw_h-1]) or NULL (params->image_h/w for the whole batch); min_edge = the loops' min_size;
+ *        - the per-image cut: BX_CUT_TOP_K = top max_per_image by score (eval_coco.py:148, prediction.py:158);
+ *          BX_CUT_SCORE_GE = every detection with score >= the max_per_image-th largest score
+ *          (pascal_eval_files_utils.py:99-106: ties with the cut are KEPT, so an image can return more than max_per_image;
+ *          out_rows >= max_per_image is the room the caller provides, anything beyond it is dropped in score order).
+ *      out_det [batch,out_rows,6] zero padded, out_count [batch]; everything else as bx_post_ops_prediction. */
+typedef enum { BX_CUT_TOP_K = 0, BX_CUT_SCORE_GE = 1 } bx_cut_mode;
+int bx_eval_detections(bx_handle* h, const float* scores, const float* deltas, const float* rois, const int* roi_counts,
+                       const float* image_sizes, const float* img_scale, int batch, int r, const bx_prediction_params* p,
+                       int cut_mode, int out_rows, float* out_det, int* out_count, void* stream);
+
 /* ---- composite used by the benchmark and by BaseFasterRcnn.call eval (faster_rcnn/base_faster_rcnn_model.py:153,182):
  *      bx_proposals followed by bx_roi_pool(BX_ROI_STRIDE_NORM) on the kept boxes, device-resident tensors. */
 int bx_c4_proposal_roi(bx_handle* h, const float* anchors, const float* deltas, const float* scores,

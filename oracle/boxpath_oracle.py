@@ -415,6 +415,51 @@ def post_ops_prediction(roi_scores_softmax, roi_txtytwth, rois, image_shape, mea
     return bb[order], cc[order], sc[order]
 
 
+def eval_loop_detections(scores, roi_txtytwth, rois_net, img_scale, raw_h, raw_w, means=(0, 0, 0, 0), stds=(0.1, 0.1, 0.2, 0.2),
+                         score_threshold=0.05, iou_threshold=0.3, max_objects_per_class=50, max_objects_per_image=50,
+                         min_size=10, loop='voc'):
+    """The per-image body of the reference's evaluation loops.  loop='voc': evaluation/pascal_eval_files_utils.py:76-106
+    (per class: score > thr :82, decode :84-86, clip to the RAW image + min_size filter :87, NMS :89-90; per image:
+    `image_thresh = np.sort(scores)[-max]`, keep `score >= image_thresh` :98-106 — ties survive).  loop='coco':
+    scripts/eval_coco.py:127-153 (same per class; `tf.nn.top_k` :148-150).  `rois_net / img_scale` is im_detect's last
+    statement (faster_rcnn/base_faster_rcnn_model.py:304).  Returns per-class lists [(boxes [k,4], scores [k])] indexed by
+    class (entry 0 unused), restricted by the per-image cut."""
+    s = np.asarray(scores, F)
+    num_classes = s.shape[1]
+    d = np.asarray(roi_txtytwth, F).reshape(s.shape[0], num_classes, 4)
+    rois = (np.asarray(rois_net, F) / F(img_scale)).astype(F)                              # base_faster_rcnn_model.py:304
+    raw_h, raw_w = F(raw_h), F(raw_w)                                                      # tf.to_float, :77-78
+    per_class = [None] * num_classes
+    for j in range(1, num_classes):
+        inds = np.nonzero(s[:, j] > F(score_threshold))[0]                                 # :82
+        cls_scores = s[inds, j]
+        boxes = decode_bbox(rois[inds], d[inds, j, :], means, stds)                        # :84-86
+        boxes, sel = bboxes_clip_filter(boxes, 0, raw_h, raw_w, min_edge=min_size)         # :87
+        cls_scores = cls_scores[sel]
+        keep = nms_tf(boxes, cls_scores, max_objects_per_class, iou_threshold)             # :89-90
+        per_class[j] = (boxes[keep], cls_scores[keep])
+    if max_objects_per_image > 0:
+        all_scores = np.concatenate([per_class[j][1] for j in range(1, num_classes)])      # :99-100
+        if all_scores.size > max_objects_per_image:
+            if loop == 'voc':
+                thresh = np.sort(all_scores)[-max_objects_per_image]                       # :102
+                for j in range(1, num_classes):
+                    k = np.nonzero(per_class[j][1] >= thresh)[0]                           # :104-105
+                    per_class[j] = (per_class[j][0][k], per_class[j][1][k])
+            else:                                                                          # eval_coco.py:148-150
+                cls_of = np.concatenate([np.full(per_class[j][1].size, j) for j in range(1, num_classes)])
+                order = np.argsort(-all_scores, kind='stable')[:max_objects_per_image]
+                chosen = np.zeros(all_scores.size, bool); chosen[order] = True
+                pos = 0
+                for j in range(1, num_classes):
+                    n = per_class[j][1].size
+                    k = np.nonzero(chosen[pos:pos + n])[0]
+                    per_class[j] = (per_class[j][0][k], per_class[j][1][k])
+                    pos += n
+                del cls_of
+    return per_class
+
+
 # --------------------------------------------------------------------------- f3 RoI-pooling backward (w.r.t. features)
 def crop_and_resize_grad_image(image_shape, boxes, box_ind, grad_crops):
     """TF r1.13 `CropAndResizeGradImage` (the gradient TF applies for tf.image.crop_and_resize w.r.t. `image`,

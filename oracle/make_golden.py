@@ -105,6 +105,60 @@ def voc_golden():
     return out
 
 
+def eval_loop_golden():
+    """Runs the reference's own `get_prediction_files` (evaluation/pascal_eval_files_utils.py:19-122), UNMODIFIED, on the
+    numpy TF shim: a stub model returns the synthetic roi-head outputs from `im_detect` (with its final `rois / img_scale`,
+    base_faster_rcnn_model.py:304), a stub dataset module yields (img, img_scale, raw_h, raw_w).  The golden is the text of
+    the 20 VOC result files it writes.  numpy >= 1.25 raises on the reference's `dets == []` (:117) where the numpy of its
+    day returned False: the module's `np.array` is wrapped to restore that behaviour."""
+    import tempfile
+    import types
+    from oracle.voc_fixture import eval_loop_inputs
+    imgs = eval_loop_inputs()
+    fake = types.ModuleType('object_detection.dataset.eval_pascal_tf_dataset')
+    names = ['%06d' % (i + 1) for i in range(len(imgs))]
+    fake.get_dataset_by_tf_records = lambda *a, **k: ([(None, im['scale'], im['raw_h'], im['raw_w']) for im in imgs], names)
+    fake.get_dataset_by_local_file = fake.get_dataset_by_tf_records
+    sys.modules['object_detection.dataset.eval_pascal_tf_dataset'] = fake
+    import object_detection.evaluation.pascal_eval_files_utils as ref_eval
+
+    class _OldEq(np.ndarray):
+        def __eq__(self, other):
+            if isinstance(other, list) and len(other) == 0 and self.ndim == 2:
+                return False                     # "elementwise comparison failed; returning scalar" of numpy < 1.25
+            return np.ndarray.__eq__(self, other)
+        __hash__ = None
+
+    class _NpProxy:
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+        @staticmethod
+        def array(*a, **k):
+            return np.array(*a, **k).view(_OldEq)
+    ref_eval.np = _NpProxy()
+    ref_eval.tqdm = lambda it: it
+
+    class _Model:
+        def __init__(self):
+            self.i = 0
+
+        def im_detect(self, img, img_scale):
+            im = imgs[self.i]
+            self.i += 1
+            return (tf.constant(im['scores']), tf.constant(im['deltas'].reshape(300, -1)),
+                    tf.constant(im['rois']) / tf.to_float(img_scale))
+    out = {}
+    for tag, max_img in (('eval_voc', 50), ('eval_voc_nocut', 0)):
+        with tempfile.TemporaryDirectory() as d:
+            ref_eval.get_prediction_files(_Model(), dataset_type='tf', result_file_format=os.path.join(d, '{:s}.txt'),
+                                          score_threshold=0.05, iou_threshold=0.3, max_objects_per_class=50,
+                                          max_objects_per_image=max_img, min_size=10)
+            text = b''.join(open(os.path.join(d, '%s.txt' % c), 'rb').read() for c in ref_eval.class_list[1:])
+        out[tag + '_files'] = np.frombuffer(text, np.uint8).copy()
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     g = {}
@@ -250,6 +304,9 @@ def main():
 
     # ---- f4: the reference's voc_eval on a synthetic VOC tree; detection files written by the package's writer
     g.update(voc_golden())
+
+    # ---- f1, evaluation-loop form: the reference's get_prediction_files run unmodified (VOC result files as text)
+    g.update(eval_loop_golden())
 
     np.savez_compressed(os.path.join(OUT, 'reference_on_shim.npz'), **g)
     sz = os.path.getsize(os.path.join(OUT, 'reference_on_shim.npz'))

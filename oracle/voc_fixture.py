@@ -42,3 +42,17 @@ def write_voc_tree(root, names, gts, class_list):
                        % (class_list[l], d, b[0], b[1], b[2], b[3]) for b, l, d in zip(boxes, labels, difficult))
         with open(os.path.join(root, 'Annotations', n + '.xml'), 'w') as f:
             f.write('<annotation>%s</annotation>' % objs)
+
+
+def eval_loop_inputs():
+    """Three synthetic images for the evaluation-loop goldens: roi-head outputs over 300 rois in network-input pixels,
+    resize factor, raw size.  Image 3 has scores quantised to 1 decimal, so exact ties sit on the per-image cut."""
+    rng = np.random.default_rng(syn.seed_for(1, 90))
+    out = []
+    for i, (scale, (raw_h, raw_w)) in enumerate(((1.6, (375, 500)), (1.25, (480, 640)), (2.0, (300, 500)))):
+        hs, hd = syn.roi_head_outputs(rng, 300, 21)
+        if i == 2:
+            hs = np.round(hs, 1).astype(np.float32)
+        rois = syn.random_rois(rng, 300, (int(raw_h * scale), int(raw_w * scale)))
+        out.append(dict(scores=hs, deltas=hd, rois=rois, scale=np.float32(scale), raw_h=raw_h, raw_w=raw_w))
+    return out

@@ -1143,3 +1143,46 @@ def test_tma_staged_extractor_matches_default_and_oracle(bx, monkeypatch):
     b = bx.roi_pool(_lib.ROI_ALIGN_PAD, _lib.POOL_AVG2, 7, cu(feat), cu(r2), stride=16.0)
     assert np.array_equal(a.cpu().numpy(), orc.roi_pool_c4(feat, r2, 16, 7, True))
     close(b.cpu().numpy(), orc.roi_align_pad(feat, r2, 16, 7), scale=1.0)
+
+
+def test_eval_loop_detections(bx, golden):
+    """f1, evaluation-loop form (bx_eval_detections): three images of different raw size and resize factor in ONE batched
+    call — rois / img_scale, per-image clip, per-class NMS, and the VOC loop's `score >= k-th largest` cut with 26 tied
+    detections surviving on image 3 — against the oracle (sets and order exact) and against the text of the result files
+    the reference's own get_prediction_files wrote (golden), through the package's file writer."""
+    from oracle.voc_fixture import eval_loop_inputs
+    from tf_eager_object_detection_b200 import evaluation as ev
+    from tf_eager_object_detection_b200.prediction import eval_loop_detections
+    imgs = eval_loop_inputs()
+    names = ['%06d' % (i + 1) for i in range(len(imgs))]
+    scores = cu(np.stack([im['scores'] for im in imgs])); deltas = cu(np.stack([im['deltas'] for im in imgs]))
+    rois = cu(np.stack([im['rois'] for im in imgs]))
+    scale = cu(np.float32([im['scale'] for im in imgs])); raw = cu(np.float32([[im['raw_h'], im['raw_w']] for im in imgs]))
+    for loop, max_img, rows, want in (('voc', 50, 128, [50, 50, 76]), ('coco', 50, None, [50, 50, 50]), ('voc', 0, None, None)):
+        det, cnt = eval_loop_detections(scores, deltas, rois, scale, raw, score_threshold=0.05, iou_threshold=0.3,
+                                        max_objects_per_class=50, max_objects_per_image=max_img, min_size=10, loop=loop,
+                                        out_rows=rows)
+        d, c = det.cpu().numpy(), cnt.cpu().numpy()
+        if want is not None:
+            assert c.tolist() == want, (loop, c.tolist())
+        for i, im in enumerate(imgs):
+            ref = orc.eval_loop_detections(im['scores'], im['deltas'], im['rois'], im['scale'], im['raw_h'], im['raw_w'],
+                                           max_objects_per_image=max_img, loop=loop)
+            rec = d[i, :c[i]]
+            assert (d[i, c[i]:] == 0).all()
+            assert (np.diff(rec[:, 4]) <= 0).all()                                  # records in descending score order
+            for j in range(1, 21):
+                mine = rec[rec[:, 5] == j]
+                assert mine.shape[0] == ref[j][1].size, (loop, i, j)
+                assert np.array_equal(mine[:, 4], ref[j][1])                        # scores exact, NMS order within the class
+                close(mine[:, :4], ref[j][0], scale=1000.0)
+        if loop == 'voc':
+            lines = ev.voc_result_lines(names, d, c)
+            got = ''.join(''.join(lines[j]) for j in range(1, 21)).splitlines()
+            ref_lines = bytes(golden['eval_voc_files' if max_img else 'eval_voc_nocut_files']).decode().splitlines()
+            assert len(got) == len(ref_lines)
+            for x, y in zip(got, ref_lines):          # same image, same printed score; corners printed to 0.1 px: an expf ulp
+                gx, gy = x.split(), y.split()         # may move a corner across a rounding boundary, never further
+                assert gx[:2] == gy[:2] and all(abs(float(p) - float(q)) <= 0.1001 for p, q in zip(gx[2:], gy[2:])), (x, y)
+    with pytest.raises(ValueError):
+        bx.eval_detections(scores, deltas, rois, raw, scale, max_num_per_image=50, out_rows=10)     # out_rows < max_per_image

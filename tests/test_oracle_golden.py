@@ -268,3 +268,37 @@ def test_fpn_and_roialign_gradients_against_torch_autograd():
     np.testing.assert_allclose(orc.roi_align_pad(feat, rois, 16, P), out.detach().numpy(), rtol=1e-4, atol=1e-5)
     out.backward(torch.tensor(go, dtype=torch.float64))
     np.testing.assert_allclose(orc.roi_align_pad_grad(feat, rois, 16, go, P), ft.grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ f1 evaluation loops
+def _voc_lines_from_per_class(names, per_image):
+    """The reference's file format (pascal_eval_files_utils.py:109-122) from the oracle's per-class results."""
+    out = []
+    for j in range(1, 21):
+        for name, pc in zip(names, per_image):
+            boxes, scores = pc[j]
+            for k in range(boxes.shape[0]):
+                out.append('{:s} {:.3f} {:.1f} {:.1f} {:.1f} {:.1f}\n'.format(name, scores[k], boxes[k, 0] + 1, boxes[k, 1] + 1,
+                                                                          boxes[k, 2] + 1, boxes[k, 3] + 1))
+    return ''.join(out)
+
+
+def test_eval_loop_oracle_reproduces_the_reference_result_files(golden):
+    """oracle.eval_loop_detections against the text of the VOC result files the reference's own get_prediction_files wrote
+    (run unmodified on the shim by make_golden.py): per-image raw-size clip, rois / img_scale, the `>= image_thresh` cut
+    with 26 tied detections surviving on image 3, and the no-cut variant."""
+    from oracle.voc_fixture import eval_loop_inputs
+    imgs = eval_loop_inputs()
+    names = ['%06d' % (i + 1) for i in range(len(imgs))]
+    for tag, max_img in (('eval_voc', 50), ('eval_voc_nocut', 0)):
+        per_image = [orc.eval_loop_detections(im['scores'], im['deltas'], im['rois'], im['scale'], im['raw_h'], im['raw_w'],
+                                              max_objects_per_image=max_img, loop='voc') for im in imgs]
+        assert _voc_lines_from_per_class(names, per_image) == bytes(golden[tag + '_files']).decode()
+    counts = [sum(pc[j][1].size for j in range(1, 21)) for pc in per_image]
+    assert counts[0] > 50 and counts[2] > 50                                   # the no-cut run keeps everything
+    cut = [orc.eval_loop_detections(im['scores'], im['deltas'], im['rois'], im['scale'], im['raw_h'], im['raw_w'], loop='voc')
+           for im in imgs]
+    assert [sum(pc[j][1].size for j in range(1, 21)) for pc in cut] == [50, 50, 76]
+    coco = [orc.eval_loop_detections(im['scores'], im['deltas'], im['rois'], im['scale'], im['raw_h'], im['raw_w'], loop='coco')
+            for im in imgs]
+    assert [sum(pc[j][1].size for j in range(1, 21)) for pc in coco] == [50, 50, 50]

@@ -12,6 +12,7 @@ BX_OK, BX_ERR_INVALID, BX_ERR_CUDA, BX_ERR_UNSUPPORTED, BX_ERR_DLPACK = 0, -1, -
 ROI_STRIDE_NORM, ROI_IMAGE_NORM, ROI_ALIGN_PAD = 0, 1, 2
 RPN_CAFFE, RPN_PAIRS = 0, 1
 POOL_NONE, POOL_MAX2, POOL_AVG2 = 0, 1, 2
+CUT_TOP_K, CUT_SCORE_GE = 0, 1
 
 F4 = c_float * 4
 
@@ -80,6 +81,8 @@ SIGNATURES = {
     'bx_proposal_target': (c_int, [c_void_p, P, P, c_int, P, P, P, c_int, c_int, P, POINTER(ProposalTargetParams), P,
                                    P, P, P, P, P, P, c_void_p]),
     'bx_post_ops_prediction': (c_int, [c_void_p, P, P, P, P, c_int, c_int, POINTER(PredictionParams), P, P, c_void_p]),
+    'bx_eval_detections': (c_int, [c_void_p, P, P, P, P, P, P, c_int, c_int, POINTER(PredictionParams), c_int, c_int, P, P,
+                                   c_void_p]),
     'bx_c4_proposal_roi': (c_int, [c_void_p, P, P, P, P, c_int, c_int, c_int, c_int, c_int, POINTER(ProposalParams),
                                    c_float, c_int, c_int, P, P, P, P, c_void_p]),
     'bx_c4_proposal_roi_host': (c_int, [c_void_p, P, P, P, P, c_int, c_int, c_int, c_int, c_int,

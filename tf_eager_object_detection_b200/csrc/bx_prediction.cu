@@ -14,6 +14,8 @@ struct PredArgs {
   const float4* deltas;    // [B,R,C]
   const float4* rois;      // [B,R]
   const int* roi_counts;   // [B] or null
+  const float* image_sizes;  // [B,2] = (raw_h, raw_w) per image or null (codec.max_x / max_y for the whole batch)
+  const float* img_scale;    // [B] or null: rois are divided by it first (im_detect, base_faster_rcnn_model.py:304)
   int B, R, C;
   BoxCodec codec;
   float score_thr, min_edge;
@@ -29,7 +31,17 @@ __global__ void __launch_bounds__(256) prediction_prepare_kernel(const PredArgs 
     const long long br = i / fg;
     const int r = static_cast<int>(br % a.R), b = static_cast<int>(br / a.R);
     const float s = a.scores[br * a.C + c];
-    const float4 box = bx_decode_clip_one(a.rois[br], a.deltas[br * a.C + c], a.codec);
+    float4 roi = a.rois[br];
+    if (a.img_scale) {
+      const float sc = a.img_scale[b];
+      roi = make_float4(roi.x / sc, roi.y / sc, roi.z / sc, roi.w / sc);
+    }
+    BoxCodec codec = a.codec;
+    if (a.image_sizes) {           // clip box of THIS image: x to [0, raw_w - 1], y to [0, raw_h - 1] (utils/bbox_tf.py:71-74)
+      codec.max_y = a.image_sizes[2 * b] - 1.0f;
+      codec.max_x = a.image_sizes[2 * b + 1] - 1.0f;
+    }
+    const float4 box = bx_decode_clip_one(roi, a.deltas[br * a.C + c], codec);
     bool ok = s > a.score_thr;                                                               // prediction.py:135
     if (a.roi_counts) ok = ok && (r < a.roi_counts[b]);
     if (a.min_edge > 0.0f)                                                                   // utils/bbox_tf.py:80-83
@@ -46,7 +58,9 @@ struct TopkArgs {
   const int* kept_idx;       // [B*(C-1), Kc]
   const int* kept_count;     // [B*(C-1)]
   int R, C, Kc, max_per_image;
-  float* out_det;            // [B, max_per_image, 6]
+  int cut_mode;              // bx_cut_mode
+  int out_rows;              // rows of out_det per image (>= max_per_image)
+  float* out_det;            // [B, out_rows, 6]
   int* out_count;            // [B]
 };
 
@@ -78,9 +92,23 @@ __global__ void __launch_bounds__(1024) prediction_topk_kernel(const TopkArgs a)
   if ((tid & 31) == 0 && mine) atomicAdd(&s_total, mine);
   __syncthreads();
   bx_bitonic_sort<true>(comp, pow2);
-  const int keep = min(s_total, a.max_per_image);
-  float* det = a.out_det + static_cast<size_t>(b) * a.max_per_image * 6;
-  for (int t = tid; t < a.max_per_image; t += 1024) {
+  int keep = min(s_total, a.max_per_image);
+  if (a.cut_mode == BX_CUT_SCORE_GE && s_total > a.max_per_image) {
+    // evaluation/pascal_eval_files_utils.py:99-106: image_thresh = the max_per_image-th largest score, keep score >= it —
+    // every detection that TIES with the cut survives (sorted descending, so the ties follow the cut directly)
+    __shared__ int s_extra;
+    if (tid == 0) s_extra = 0;
+    __syncthreads();
+    const unsigned long long cut_key = comp[a.max_per_image - 1] >> 32;
+    int extra = 0;
+    for (int e = a.max_per_image + tid; e < s_total; e += 1024) extra += ((comp[e] >> 32) == cut_key) ? 1 : 0;
+    extra = __reduce_add_sync(0xFFFFFFFFu, extra);
+    if ((tid & 31) == 0 && extra) atomicAdd(&s_extra, extra);
+    __syncthreads();
+    keep = min(a.max_per_image + s_extra, a.out_rows);
+  }
+  float* det = a.out_det + static_cast<size_t>(b) * a.out_rows * 6;
+  for (int t = tid; t < a.out_rows; t += 1024) {
     float rec[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (t < keep) {
       const int e = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(comp[t] & 0xFFFFFFFFull));
@@ -100,17 +128,45 @@ __global__ void __launch_bounds__(1024) prediction_topk_kernel(const TopkArgs a)
 
 }  // namespace
 
+static int prediction_impl(bx_handle* h, const float* scores, const float* deltas, const float* rois,
+                           const int* roi_counts, const float* image_sizes, const float* img_scale, int batch, int r,
+                           const bx_prediction_params* p, int cut_mode, int out_rows, float* out_det, int* out_count,
+                           void* stream);
+
 extern "C" int bx_post_ops_prediction(bx_handle* h, const float* scores, const float* deltas, const float* rois,
                                       const int* roi_counts, int batch, int r, const bx_prediction_params* p,
                                       float* out_det, int* out_count, void* stream) {
   BxEnter guard(h, stream);
+  BX_REQUIRE(p, BX_ERR_INVALID, "bx_post_ops_prediction: NULL argument");
+  return prediction_impl(h, scores, deltas, rois, roi_counts, nullptr, nullptr, batch, r, p, BX_CUT_TOP_K, p->max_per_image,
+                         out_det, out_count, stream);
+}
+
+extern "C" int bx_eval_detections(bx_handle* h, const float* scores, const float* deltas, const float* rois,
+                                  const int* roi_counts, const float* image_sizes, const float* img_scale, int batch,
+                                  int r, const bx_prediction_params* p, int cut_mode, int out_rows, float* out_det,
+                                  int* out_count, void* stream) {
+  BxEnter guard(h, stream);
+  BX_REQUIRE(p, BX_ERR_INVALID, "bx_eval_detections: NULL argument");
+  BX_REQUIRE(cut_mode == BX_CUT_TOP_K || cut_mode == BX_CUT_SCORE_GE, BX_ERR_INVALID, "bx_eval_detections: bad cut_mode %d", cut_mode);
+  BX_REQUIRE(out_rows >= p->max_per_image, BX_ERR_INVALID, "bx_eval_detections: out_rows %d < max_per_image %d", out_rows,
+             p->max_per_image);
+  return prediction_impl(h, scores, deltas, rois, roi_counts, image_sizes, img_scale, batch, r, p, cut_mode, out_rows, out_det,
+                         out_count, stream);
+}
+
+static int prediction_impl(bx_handle* h, const float* scores, const float* deltas, const float* rois,
+                           const int* roi_counts, const float* image_sizes, const float* img_scale, int batch, int r,
+                           const bx_prediction_params* p, int cut_mode, int out_rows, float* out_det, int* out_count,
+                           void* stream) {
   BX_REQUIRE(h && scores && deltas && rois && p && out_det && out_count, BX_ERR_INVALID,
              "bx_post_ops_prediction: NULL argument");
   BX_REQUIRE(batch >= 0 && r >= 0 && p->num_classes >= 2, BX_ERR_INVALID, "bx_post_ops_prediction: bad size");
   BX_REQUIRE(p->max_per_class > 0 && p->max_per_image > 0, BX_ERR_INVALID, "bx_post_ops_prediction: bad limits");
   BX_REQUIRE(p->nms_iou_threshold >= 0.0f && p->nms_iou_threshold <= 1.0f, BX_ERR_INVALID,
              "bx_post_ops_prediction: iou_threshold must be in [0, 1]");
-  BX_REQUIRE(p->image_h > 0 && p->image_w > 0, BX_ERR_INVALID, "bx_post_ops_prediction: image shape must be positive");
+  BX_REQUIRE(image_sizes || (p->image_h > 0 && p->image_w > 0), BX_ERR_INVALID,
+             "bx_post_ops_prediction: image shape must be positive");
   const int fg = p->num_classes - 1;
   BX_REQUIRE(static_cast<long long>(fg) * p->max_per_class <= kMaxCand, BX_ERR_UNSUPPORTED,
              "bx_post_ops_prediction: (C-1) * max_per_class = %lld > %d", (long long)fg * p->max_per_class, kMaxCand);
@@ -139,6 +195,8 @@ extern "C" int bx_post_ops_prediction(bx_handle* h, const float* scores, const f
     a.deltas = reinterpret_cast<const float4*>(deltas);
     a.rois = reinterpret_cast<const float4*>(rois);
     a.roi_counts = roi_counts;
+    a.image_sizes = image_sizes;
+    a.img_scale = img_scale;
     a.B = batch; a.R = r; a.C = p->num_classes;
     a.codec.m0 = p->means[0]; a.codec.m1 = p->means[1]; a.codec.m2 = p->means[2]; a.codec.m3 = p->means[3];
     a.codec.s0 = p->stds[0]; a.codec.s1 = p->stds[1]; a.codec.s2 = p->stds[2]; a.codec.s3 = p->stds[3];
@@ -165,6 +223,8 @@ extern "C" int bx_post_ops_prediction(bx_handle* h, const float* scores, const f
   t.kept_idx = kept_idx;
   t.kept_count = kept_cnt;
   t.R = r; t.C = p->num_classes; t.Kc = p->max_per_class; t.max_per_image = p->max_per_image;
+  t.cut_mode = cut_mode;
+  t.out_rows = out_rows;
   t.out_det = out_det;
   t.out_count = out_count;
   int pow2 = 64;

@@ -443,6 +443,32 @@ def post_ops_prediction(scores, deltas, rois, image_shape, means=(0, 0, 0, 0), s
     return det, cnt
 
 
+def eval_detections(scores, deltas, rois, image_sizes=None, img_scale=None, image_shape=(0, 0), means=(0, 0, 0, 0),
+                    stds=(1, 1, 1, 1), max_num_per_class=50, max_num_per_image=150, nms_iou_threshold=0.3,
+                    score_threshold=0.05, min_size=10, cut=_lib.CUT_TOP_K, out_rows=None, roi_counts=None):
+    """f1, evaluation-loop form (bx_eval_detections): as post_ops_prediction, with the rois divided by `img_scale` [b]
+    first, boxes clipped to each image's own raw size `image_sizes` [b,2] = (raw_h, raw_w), and the per-image cut either
+    top-k or the VOC loop's `score >= k-th largest` (ties kept, up to `out_rows` rows).  -> (det [b,out_rows,6], count [b])."""
+    scores = to_device(scores, f32)
+    b, r, c = scores.shape
+    deltas = to_device(deltas, f32, scores.device).reshape(b, r, c, 4)
+    rois = to_device(rois, f32, scores.device)
+    dev, h, bw, st, lib = _ctx(scores)
+    rows = int(max_num_per_image if out_rows is None else out_rows)
+    p = _lib.PredictionParams(_lib.f4(means), _lib.f4(stds), int(image_shape[0]), int(image_shape[1]), int(c),
+                              int(max_num_per_class), int(max_num_per_image), float(nms_iou_threshold),
+                              float(score_threshold), float(min_size if min_size is not None else 0))
+    det, cnt = empty((b, rows, 6), f32, dev), empty((b,), i32, dev)
+    rc = bw.ptr(to_device(roi_counts, i32, scores.device), INT32, (b,)) if roi_counts is not None else None
+    isz = bw.ptr(to_device(image_sizes, f32, scores.device), FLOAT32, (b, 2)) if image_sizes is not None else None
+    isc = bw.ptr(to_device(img_scale, f32, scores.device), FLOAT32, (b,)) if img_scale is not None else None
+    _lib.check(lib.bx_eval_detections(h, bw.ptr(scores, FLOAT32, (b, r, c)) if r else 0,
+                                      bw.ptr(deltas, FLOAT32, (b, r, c, 4), 16) if r else 0,
+                                      bw.ptr(rois, FLOAT32, (b, r, 4), 16) if r else 0, rc, isz, isc, b, r, ctypes.byref(p),
+                                      int(cut), rows, bw.ptr(det, FLOAT32, (b, rows, 6)), bw.ptr(cnt, INT32, (b,)), st))
+    return det, cnt
+
+
 def c4_proposal_roi(anchors, deltas, scores, feat, image_shape, post_nms, stride=16.0, pool_size=7,
                     max_pooling_flag=False, iou_threshold=0.7, means=(0, 0, 0, 0), stds=(1, 1, 1, 1), pre_nms_top_k=0,
                     min_size=0.0, out=None):
