@@ -444,6 +444,50 @@ def verify_gather(ctx, r, nsteps, G):
     return True
 
 
+def pcie_probe(ctx, mb=256, reps=4):
+    """Host-link diagnostic for the e2e leg: pinned <-> device copy rates of rank 0 alone and of all ranks at once
+    (GB/s, CUDA events; the all-ranks figures are sums over the ranks).  Explains why the host-buffer path scales with
+    the host side of the box (PCIe switches / root ports / host memory), not with the GPUs."""
+    torch, dist = ctx.torch, ctx.dist
+    n = mb << 20
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device=ctx.dev)
+    s2 = torch.cuda.Stream(ctx.dev)
+
+    def run(h2d, d2h):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(ctx.main)
+        s2.wait_event(e0)
+        for _ in range(reps):
+            if h2d:
+                d.copy_(h, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h.copy_(d, non_blocking=True) if not h2d else h2.copy_(d2, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(s2); ctx.main.wait_event(ev)
+        e1.record(ctx.main)
+        torch.cuda.synchronize()
+        return (int(h2d) + int(d2h)) * reps * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    h2 = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d2 = torch.empty(n, dtype=torch.uint8, device=ctx.dev)
+    out = {}
+    for name, (a_, b_) in dict(h2d=(True, False), d2h=(False, True), bidir=(True, True)).items():
+        run(a_, b_)
+        ctx.barrier()
+        if ctx.rank == 0:
+            out['rank0_alone_' + name] = round(run(a_, b_), 1)
+        ctx.barrier()
+        v = run(a_, b_)
+        if ctx.world > 1:
+            t = torch.tensor([v], device=ctx.dev)
+            dist.all_reduce(t)
+            v = float(t.item())
+        out['all_ranks_' + name] = round(v, 1)
+        ctx.barrier()
+    return out
+
+
 def bench_c4(ctx, args):
     """Headline workload (cfg2)."""
     torch, lib, _lib = ctx.torch, ctx.lib, ctx._lib
@@ -568,6 +612,7 @@ def bench_c4(ctx, args):
     e2e_ms_max, e2e_ranks = ctx.max_over_ranks(max(e2e_ms, 0.0))
     e2e_value = ctx.world * e2e_steps * B / (e2e_ms_max * 1e-3)
 
+    probe = pcie_probe(ctx) if (ctx.world > 1 or args.pcie_probe) else None
     out = None
     if ctx.rank == 0:
         b_prop, b_roi = algorithmic_bytes(w, n, fh, fw)
@@ -622,7 +667,8 @@ def bench_c4(ctx, args):
                      bound='PCIe: the step moves 82 MB in and 482 MB out per 8 images; the kernels take 0.19 ms of it',
                      ms_per_rank=e2e_ranks,
                      api='ops.c4_proposal_roi_host -> bx_c4_proposal_roi_host (pinned host buffers, 2 streams)',
-                     numa=(('bound to %d CPUs (%s)' % (len(cpus), numa_how)) if cpus else numa_how)),
+                     numa=(('bound to %d CPUs (%s)' % (len(cpus), numa_how)) if cpus else numa_how),
+                     host_link_probe_gbs=probe),
             gpu_launches=gpu_launches, clocks=sampler.summary())
     pipe.close(); pipe_roi.close()
     del d_in, feat_bufs, h_outs, h_in, rec
@@ -841,6 +887,7 @@ def main():
     ap.add_argument('--workloads', default='all', help='all | none | comma list of cfg3,cfg5,cfg4 (measured after the headline)')
     ap.add_argument('--workload-steps', type=int, default=100, help='cap on the steps of the extra workloads')
     ap.add_argument('--batch-override', type=int, default=0, help='experiments: images per GPU and step of the FPN workloads')
+    ap.add_argument('--pcie-probe', action='store_true', help='N = 1: also run the host-link copy probe of the e2e block')
     ap.add_argument('--no-graph', action='store_true', help='issue the timed region eagerly instead of as one CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
