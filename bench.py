@@ -276,6 +276,7 @@ class Ctx:
                 raise SystemExit('bench.py: the process group exposes no ncclComm_t (torch without ProcessGroupNCCL._comm_ptr)')
             self.comm = ctypes.c_void_p(ptr)
         self.lib = _lib.load()
+        self.sync_buf = torch.zeros(1, device=self.dev)
         self.main = torch.cuda.current_stream(self.dev)
         self.use_graph = not args.no_graph
         self.graph_error = None
@@ -386,6 +387,11 @@ class Pipeline:
             g._bx_primed = True
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.barrier()
+        if ctx.world > 1:
+            # device-side aligned start: a tiny all-reduce queued in front of the start event completes on all ranks
+            # within microseconds of each other, so the ranks' timed regions begin together on the DEVICE and the host
+            # jitter behind the barrier (tens of microseconds, 1 - 2 % of a 20-step region) is not charged to anybody
+            ctx.dist.all_reduce(ctx.sync_buf)
         e0.record(ctx.main)
         if g is not None:
             g.replay()
@@ -508,7 +514,7 @@ def bench_c4(ctx, args):
     idx_bufs = [torch.empty((B, post), dtype=torch.int32, device=dev) for _ in range(NSTREAM)]
     feat_bufs = [torch.empty((B * post, P, P, C), device=dev) for _ in range(NSTREAM)]
     params = ops.proposal_params(w['image_hw'], post, w['iou_thr'], pre_nms_top_k=w['pre_nms'])
-    G = args.gather_every if args.gather_every > 0 else max(1, (K + 3) // 4)
+    G = args.gather_every if args.gather_every > 0 else max(K, W, NSTREAM)   # default: ONE all-gather, at the end of the region
 
     pipe = None
 
@@ -633,10 +639,10 @@ def bench_c4(ctx, args):
                          graph_error=ctx.graph_error,
                          priming='one eager step per stream (workspace allocation) and one untimed replay of the step graph '
                                  '(executable-graph upload) precede the W warm-up steps / the timed replay',
-                         parallelism=('images sharded over GPUs, no data-path collective; detection records (kept boxes + counts) of every '
-                                      '%d steps all-gathered by bx_allgather_detections on a dedicated ncclComm_t, on a communication '
-                                      'branch of the step graph no compute stream waits for; every rank verifies every rank\'s '
-                                      'gathered records' % G) if ctx.world > 1 else 'single GPU',
+                         parallelism=('images sharded over GPUs, no data-path collective; the detection records (kept boxes + counts) the '
+                                      'region accumulates are all-gathered every %d steps (K = %d: once, at the end of the region, inside '
+                                      'the timed graph) by bx_allgather_detections on a dedicated ncclComm_t, on a communication branch no '
+                                      'compute stream waits for; every rank verifies every rank\'s gathered records' % (G, K)) if ctx.world > 1 else 'single GPU',
                          gather_verified=gather_ok, ms_per_rank=ms_ranks,
                          rank_skew=round((max(ms_ranks) - min(ms_ranks)) / max(ms_ranks), 4),
                          algorithmic_bytes_per_image=b_prop + b_roi, band_launches=stats['band_launches'],
@@ -725,7 +731,7 @@ def bench_fpn(ctx, args, name):
     lv_bufs = [(torch.empty((B * POST,), dtype=torch.int32, device=dev), torch.empty((B * POST,), dtype=torch.int32, device=dev),
                 torch.zeros((NLEV,), dtype=torch.int32, device=dev)) for _ in range(NSTREAM)]
     params = ops.proposal_params(hw, POST, 0.7)
-    G = max(1, (K + 3) // 4)
+    G = max(K, W, NSTREAM)                                  # one all-gather of the region's records, at its end
     pipe = None
 
     def launch(step, pos, si):
@@ -883,7 +889,7 @@ def main():
     ap.add_argument('--fpn-streams', type=int, default=4)
     ap.add_argument('--e2e-steps', type=int, default=20)
     ap.add_argument('--gather-every', type=int, default=0,
-                    help='N > 1: detection records of this many consecutive steps are all-gathered together (0: K/4)')
+                    help='N > 1: detection records of this many consecutive steps are all-gathered together (0: all K, one gather at the end of the region)')
     ap.add_argument('--workloads', default='all', help='all | none | comma list of cfg3,cfg5,cfg4 (measured after the headline)')
     ap.add_argument('--workload-steps', type=int, default=100, help='cap on the steps of the extra workloads')
     ap.add_argument('--batch-override', type=int, default=0, help='experiments: images per GPU and step of the FPN workloads')
