@@ -347,12 +347,11 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
   const uint32_t row_bytes = static_cast<uint32_t>(fw) * (kSlice * 4);
   const uint32_t zrow_off = static_cast<uint32_t>(a.band_bytes);            // one all-zero band row after the TMA boxes
   const PlanLayout L = plan_layout(a.cap, r.Q);
-  unsigned char* tab = smem + zrow_off + ((row_bytes + 127u) & ~127u);
-  const unsigned long long* xval = reinterpret_cast<const unsigned long long*>(tab + L.off_xval);
-  const uint2* xtab = reinterpret_cast<const uint2*>(tab + L.off_xtab);
-  const uint2* ytab = reinterpret_cast<const uint2*>(tab + L.off_ytab);
-  const uint2* runs = reinterpret_cast<const uint2*>(tab + L.off_runs);
-  __shared__ uint64_t mbar;
+  // two plan-block buffers: block ch + 1 is copied in while block ch is processed (a (image, band) unit lists
+  // ~150 rois at cfg2, more than one block holds; waiting for the second block used to cost 6 % of the kernel)
+  unsigned char* tab0 = smem + zrow_off + ((row_bytes + 127u) & ~127u);
+  const uint32_t tab_step = a.n_blocks_max > 1 ? L.bytes : 0u;      // offset of the second buffer
+  __shared__ uint64_t mbar[2];
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int P = r.P, Q = r.Q, C = r.c;
@@ -373,13 +372,14 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
   const unsigned char* plan0 = a.plan + static_cast<size_t>(img * a.n_bands + band_i) * a.n_blocks_max * L.bytes;
 
   if (tid == 0) {
-    mbar_init(&mbar, 1);
-    mbar_expect_tx(&mbar, static_cast<uint32_t>(a.band_bytes) + L.bytes);
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_expect_tx(&mbar[0], static_cast<uint32_t>(a.band_bytes) + L.bytes);
     const int row0 = (img * fh + r0) * fw;
     for (int bx = 0; bx < a.nbox; ++bx)
-      tma_load_2d(smem + static_cast<size_t>(bx) * a.box_rows * (kSlice * 4), &tmap, slice * kSlice, row0 + bx * a.box_rows, &mbar);
+      tma_load_2d(smem + static_cast<size_t>(bx) * a.box_rows * (kSlice * 4), &tmap, slice * kSlice, row0 + bx * a.box_rows, &mbar[0]);
     asm volatile("griddepcontrol.wait;" ::: "memory");    // the plan kernel (previous launch in the stream) is complete
-    bulk_load(tab, plan0, L.bytes, &mbar);
+    bulk_load(tab0, plan0, L.bytes, &mbar[0]);
   }
   for (uint32_t i = tid * 16u; i < row_bytes; i += THREADS * 16u)
     *reinterpret_cast<float4*>(smem + zrow_off + i) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -397,16 +397,20 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
 
   int n_blocks = 1;
   for (int ch = 0; ch < n_blocks; ++ch) {
-    if (ch > 0) {
-      __syncthreads();                       // everyone is done with the previous plan block
-      if (tid == 0) {
-        mbar_expect_tx(&mbar, L.bytes);
-        bulk_load(tab, plan0 + static_cast<size_t>(ch) * L.bytes, L.bytes, &mbar);
-      }
-      __syncthreads();
-    }
-    mbar_wait(&mbar, static_cast<uint32_t>(ch & 1));
+    const unsigned char* tab = tab0 + (ch & 1) * tab_step;
+    mbar_wait(&mbar[ch & 1], static_cast<uint32_t>((ch >> 1) & 1));
     if (ch == 0) n_blocks = reinterpret_cast<const int*>(tab)[1];
+    if (ch + 1 < n_blocks) {                 // prefetch the next plan block into the other buffer
+      if (ch >= 1) __syncthreads();          // ... which block ch - 1 used: everyone is done with it
+      if (tid == 0) {
+        mbar_expect_tx(&mbar[(ch + 1) & 1], L.bytes);
+        bulk_load(tab0 + ((ch + 1) & 1) * tab_step, plan0 + static_cast<size_t>(ch + 1) * L.bytes, L.bytes, &mbar[(ch + 1) & 1]);
+      }
+    }
+    const unsigned long long* xval = reinterpret_cast<const unsigned long long*>(tab + L.off_xval);
+    const uint2* xtab = reinterpret_cast<const uint2*>(tab + L.off_xtab);
+    const uint2* ytab = reinterpret_cast<const uint2*>(tab + L.off_ytab);
+    const uint2* runs = reinterpret_cast<const uint2*>(tab + L.off_runs);
     if (a.dbg && tid == 0 && ch == 0) {
       unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       a.dbg[blockIdx.x * 4 + 1] = t;
@@ -634,10 +638,11 @@ bool make_band_cfg(int fh, int fw, int Q, int rois_range, size_t budget, BandCfg
   const size_t zrow = (row_bytes + 127) & ~static_cast<size_t>(127);       // the all-zero row behind the TMA boxes
   // table capacity: the rois of one image that own rows in one band — about (band height + roi height) / map height
   // of them; sized generously, overflow spills into further plan blocks handled sequentially by the same CTA
-  int cap = rois_range < 160 ? rois_range : 160;
+  // (two buffers of `cap` rois when a unit can need more than one block: the next block is prefetched)
+  int cap = rois_range < 112 ? rois_range : 112;
   if (cap < 1) cap = 1;
-  while (cap > 32 && plan_layout(cap, Q).bytes > budget / 4) cap = (cap + 1) / 2;
-  const size_t tab = plan_layout(cap, Q).bytes;
+  while (cap > 32 && 2 * plan_layout(cap, Q).bytes > budget / 3) cap = (cap + 1) / 2;
+  const size_t tab = plan_layout(cap, Q).bytes * (((rois_range + cap - 1) / cap > 1) ? 2 : 1);
   if (budget < tab + zrow + 3 * row_bytes + 256) return false;
   int max_rows_loaded = static_cast<int>((budget - tab - zrow - 256) / row_bytes);
   if (max_rows_loaded < 3) return false;                                    // map too wide for a useful band
