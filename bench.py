@@ -279,6 +279,7 @@ class Ctx:
         self.sync_buf = torch.zeros(1, device=self.dev)
         self.main = torch.cuda.current_stream(self.dev)
         self.use_graph = not args.no_graph
+        self.use_priority = bool(args.priority)
         self.graph_error = None
 
     def barrier(self):
@@ -317,6 +318,10 @@ class Pipeline:
         self.ctx, self.launch = ctx, launch
         self.streams = [torch.cuda.Stream(ctx.dev) for _ in range(n_streams)]
         self.handles = [ctx.new_handle() for _ in range(n_streams)]
+        # optional high-priority side stream per stream (+ its own handle): small latency-critical kernels (the 8-CTA proposal
+        # kernel) issued there are scheduled ahead of the queued CTAs of the bandwidth kernels of other steps
+        self.hi_streams = [torch.cuda.Stream(ctx.dev, priority=-1) for _ in range(n_streams)] if ctx.use_priority else None
+        self.hi_handles = [ctx.new_handle() for _ in range(n_streams)] if ctx.use_priority else []
         self.records = records          # dict(boxes [cap*B,k,4], counts [cap*B], B, k, out_boxes, out_counts) or None
         self.gather_every = gather_every
         self.comm_stream = torch.cuda.Stream(ctx.dev) if (records is not None and ctx.world > 1) else None
@@ -402,13 +407,14 @@ class Pipeline:
         return e0.elapsed_time(e1)
 
     def launches(self):
-        return sum(int(self.ctx.lib.bx_launch_count(h)) for h in self.handles + ([self.comm_handle] if self.comm_handle else []))
+        return sum(int(self.ctx.lib.bx_launch_count(h)) for h in self.handles + self.hi_handles + ([self.comm_handle] if self.comm_handle else []))
 
     def close(self):
         self.graphs.clear()
-        for h in self.handles + ([self.comm_handle] if self.comm_handle else []):
+        for h in self.handles + self.hi_handles + ([self.comm_handle] if self.comm_handle else []):
             self.ctx.lib.bx_destroy(h)
         self.handles = []
+        self.hi_handles = []
 
 
 def make_records(ctx, cap_steps, B, k):
@@ -521,6 +527,19 @@ def bench_c4(ctx, args):
     def launch(step, pos, si):
         din = d_in[step % NBUF]
         lo = pos * B
+        if pipe.hi_streams is not None:
+            # proposals on the stream's high-priority side stream, RoI pooling behind an event on the stream itself
+            hs, s_ = pipe.hi_streams[si], pipe.streams[si]
+            ev_in = torch.cuda.Event(); ev_in.record(s_); hs.wait_event(ev_in)        # the side stream follows the stream's order
+            _lib.check(lib.bx_proposals(pipe.hi_handles[si], anchors.data_ptr(), din['deltas'].data_ptr(), din['scores'].data_ptr(),
+                                        B, n, ctypes.byref(params), rec['boxes'][lo:lo + B].data_ptr(), idx_bufs[si].data_ptr(),
+                                        rec['counts'][lo:lo + B].data_ptr(), ctypes.c_void_p(hs.cuda_stream)))
+            ev = torch.cuda.Event(); ev.record(hs); s_.wait_event(ev)
+            _lib.check(lib.bx_roi_pool(pipe.handles[si], _lib.ROI_STRIDE_NORM, _lib.POOL_NONE, P, din['feat'].data_ptr(), B, fh, fw,
+                                       C, rec['boxes'][lo:lo + B].data_ptr(), None, rec['counts'][lo:lo + B].data_ptr(), B * post,
+                                       float(w['stride']), w['image_hw'][0], w['image_hw'][1], feat_bufs[si].data_ptr(),
+                                       ctypes.c_void_p(s_.cuda_stream)))
+            return
         _lib.check(lib.bx_c4_proposal_roi(pipe.handles[si], anchors.data_ptr(), din['deltas'].data_ptr(),
                                           din['scores'].data_ptr(), din['feat'].data_ptr(), B, n, fh, fw, C,
                                           ctypes.byref(params), float(w['stride']), P, _lib.POOL_NONE,
@@ -894,6 +913,7 @@ def main():
     ap.add_argument('--workload-steps', type=int, default=100, help='cap on the steps of the extra workloads')
     ap.add_argument('--batch-override', type=int, default=0, help='experiments: images per GPU and step of the FPN workloads')
     ap.add_argument('--pcie-probe', action='store_true', help='N = 1: also run the host-link copy probe of the e2e block')
+    ap.add_argument('--priority', type=int, default=0, help='1: proposal kernels on high-priority side streams')
     ap.add_argument('--no-graph', action='store_true', help='issue the timed region eagerly instead of as one CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -12,7 +12,7 @@ tests, fixtures or golden vectors, and TensorFlow (inferred 1.13, unpinned) is n
 here, so `nms_tf`, `crop_and_resize_tf`, `max_pool_2x2`, `avg_pool_2x2` restate the TF r1.13 CPU
 kernels from SURVEY.md Appendix B.  What IS pinned:
   * the reference's own Python control flow — `oracle/make_golden.py` executes the reference's
-    files unmodified on `oracle/tf_shim` and `tests/test_oracle_vs_reference.py` checks this module
+    files unmodified on `oracle/tf_shim` and `tests/test_oracle_golden.py` checks this module
     against those outputs (committed under `tests/golden/`);
   * `pairwise_iou` against the reference's importable numpy twin `utils/bbox_np.py:42-55`;
   * NMS / IoU / bilinear sampling against independent witnesses (torchvision.ops.nms, box_iou,

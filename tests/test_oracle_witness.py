@@ -111,7 +111,7 @@ def test_c_twin_agrees_with_numpy_oracle():
 
 
 def test_c_twin_fpn_composite_agrees_with_numpy_oracle():
-    """orc_fpn_proposal_roi (the CPU arm of bench_fpn.py) against the numpy oracle: 2 images, C = 8."""
+    """orc_fpn_proposal_roi (the FPN composite of the oracle's C twin) against the numpy oracle: 2 images, C = 8."""
     so = os.path.join(ROOT, 'oracle', 'c', 'libboxpath_ref.so')
     subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle', 'c')])
     lib = ctypes.CDLL(so)

@@ -506,6 +506,8 @@ int launch_roi(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
     // ahead (444) 625 / 830, two waves 650 / 843: only the CTA's own footprint pays.  BX_POOL2_PF overrides (-1 = off)
     static const int pf_env = getenv("BX_POOL2_PF") ? atoi(getenv("BX_POOL2_PF")) : -2;
     const int pf = pf_env != -2 ? pf_env : 0;
+    // (a two-channel-per-thread variant — half the tap registers, 4 CTAs / SM — measured SLOWER, 733 vs 563 us at cfg3
+    //  B = 16: the doubled load instructions cost more than the occupancy gains; profiles/README.md)
     if (pool == BX_POOL_MAX2) roi_pool2_kernel<BX_POOL_MAX2><<<a.r, 256, 0, st>>>(a, -0.0f, pf);
     else roi_pool2_kernel<BX_POOL_AVG2><<<a.r, 256, 0, st>>>(a, -0.0f, pf);
     BX_LAUNCH_CHECK(h);

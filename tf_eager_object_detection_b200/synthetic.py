@@ -5,7 +5,7 @@ seed = 20260000 + 100*cfg + image_index, `np.random.default_rng(seed)`.
 
 The two anchor generators restate what the reference's models feed the path with
 (`object_detection/utils/anchor_generator.py:63-81,46-60` for C4, `:137-178` for FPN);
-`tests/test_oracle_vs_reference.py` checks them against the reference's own functions.
+`oracle/make_golden.py` asserts them equal to the reference's own generators (and `tests/test_oracle_golden.py` pins the hashes).
 """
 import math
 
