@@ -313,15 +313,15 @@ class Pipeline:
     issues the steps and joins everything back — the same code eagerly (root = main stream) or under CUDA-graph capture
     (root = capturing stream; events recorded / waited inside the capture become graph edges)."""
 
-    def __init__(self, ctx, n_streams, launch, records=None, gather_every=0):
+    def __init__(self, ctx, n_streams, launch, records=None, gather_every=0, side_streams=False):
         torch = ctx.torch
         self.ctx, self.launch = ctx, launch
         self.streams = [torch.cuda.Stream(ctx.dev) for _ in range(n_streams)]
         self.handles = [ctx.new_handle() for _ in range(n_streams)]
         # optional high-priority side stream per stream (+ its own handle): small latency-critical kernels (the 8-CTA proposal
         # kernel) issued there are scheduled ahead of the queued CTAs of the bandwidth kernels of other steps
-        self.hi_streams = [torch.cuda.Stream(ctx.dev, priority=-1) for _ in range(n_streams)] if ctx.use_priority else None
-        self.hi_handles = [ctx.new_handle() for _ in range(n_streams)] if ctx.use_priority else []
+        self.hi_streams = [torch.cuda.Stream(ctx.dev, priority=-1) for _ in range(n_streams)] if side_streams else None
+        self.hi_handles = [ctx.new_handle() for _ in range(n_streams)] if side_streams else []
         self.records = records          # dict(boxes [cap*B,k,4], counts [cap*B], B, k, out_boxes, out_counts) or None
         self.gather_every = gather_every
         self.comm_stream = torch.cuda.Stream(ctx.dev) if (records is not None and ctx.world > 1) else None
@@ -344,6 +344,8 @@ class Pipeline:
     def region(self, nsteps, first, root, only_stream=None):
         torch = self.ctx.torch
         streams = self.streams if only_stream is None else [self.streams[only_stream]]
+        if self.hi_streams is not None:
+            streams = streams + (self.hi_streams if only_stream is None else [self.hi_streams[only_stream]])
         ev0 = torch.cuda.Event(); ev0.record(root)
         for s in streams:
             s.wait_event(ev0)
@@ -383,7 +385,7 @@ class Pipeline:
         self.graphs[key] = g
         return g
 
-    def timed(self, nsteps, first, key=None, only_stream=None, prime_graph=True):
+    def timed(self, nsteps, first, key=None, only_stream=None, prime_graph=True, settle=0.0):
         """Device time (ms) of the region: CUDA events on the main stream around one graph replay (or the eager issue)."""
         ctx, torch = self.ctx, self.ctx.torch
         g = self.graph(nsteps, first, key) if (key is not None and only_stream is None) else None
@@ -392,6 +394,9 @@ class Pipeline:
             g._bx_primed = True
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.barrier()
+        if settle:
+            time.sleep(settle)       # every measured region starts from an idle device (same power / clock state: a region
+            ctx.barrier()            # measured right behind another one inherits its power-cap state — sw_power_cap at K >= 200)
         if ctx.world > 1:
             # device-side aligned start: a tiny all-reduce queued in front of the start event completes on all ranks
             # within microseconds of each other, so the ranks' timed regions begin together on the DEVICE and the host
@@ -530,7 +535,8 @@ def bench_c4(ctx, args):
         if pipe.hi_streams is not None:
             # proposals on the stream's high-priority side stream, RoI pooling behind an event on the stream itself
             hs, s_ = pipe.hi_streams[si], pipe.streams[si]
-            ev_in = torch.cuda.Event(); ev_in.record(s_); hs.wait_event(ev_in)        # the side stream follows the stream's order
+            if args.priority == 1:                       # 1: the side stream follows the stream's order; 2: its own chain —
+                ev_in = torch.cuda.Event(); ev_in.record(s_); hs.wait_event(ev_in)   # proposals of step i+S overlap the RoI kernels of step i
             _lib.check(lib.bx_proposals(pipe.hi_handles[si], anchors.data_ptr(), din['deltas'].data_ptr(), din['scores'].data_ptr(),
                                         B, n, ctypes.byref(params), rec['boxes'][lo:lo + B].data_ptr(), idx_bufs[si].data_ptr(),
                                         rec['counts'][lo:lo + B].data_ptr(), ctypes.c_void_p(hs.cuda_stream)))
@@ -556,7 +562,7 @@ def bench_c4(ctx, args):
                                    B * post, float(w['stride']), w['image_hw'][0], w['image_hw'][1],
                                    feat_bufs[si].data_ptr(), ctypes.c_void_p(pipe_roi.streams[si].cuda_stream)))
 
-    pipe = Pipeline(ctx, NSTREAM, launch, rec, G)
+    pipe = Pipeline(ctx, NSTREAM, launch, rec, G, side_streams=ctx.use_priority)
     pipe_roi = Pipeline(ctx, NSTREAM, launch_roi_only)
     pipe.timed(NSTREAM, 0)                                   # priming (eager): every handle allocates its workspace
     pipe_roi.timed(NSTREAM, 0)
@@ -654,7 +660,8 @@ def bench_c4(ctx, args):
             metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=ctx.world, steps=K, warmup=W,
             ms_per_step=round(ms_max / K, 5), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
             data='synthetic', config=headline_config(w),
-            details=dict(streams=NSTREAM, issue='one CUDA-graph replay of the K steps' if g_timed is not None else 'eager launches',
+            details=dict(streams=NSTREAM, proposal_side_streams=args.priority,
+                         issue='one CUDA-graph replay of the K steps' if g_timed is not None else 'eager launches',
                          graph_error=ctx.graph_error,
                          priming='one eager step per stream (workspace allocation) and one untimed replay of the step graph '
                                  '(executable-graph upload) precede the W warm-up steps / the timed replay',
@@ -758,6 +765,8 @@ def bench_fpn(ctx, args, name):
         lo = pos * B
         st = ctypes.c_void_p(pipe.streams[si].cuda_stream)
         rois = rec['boxes'][lo:lo + B]
+        # (the proposal stage as its own chain on a side stream, which pays at cfg2, measured SLOWER here: cfg5 23.2 k vs
+        #  26.1 k images/s, cfg3 25.8 k vs 26.9 k — its six prefilter launches then compete with the extractor of the same lane)
         _lib.check(lib.bx_proposals(pipe.handles[si], anchors.data_ptr(), din['deltas'].data_ptr(), din['scores'].data_ptr(), B,
                                     n, ctypes.byref(params), rois.data_ptr(), idx_bufs[si].data_ptr(),
                                     rec['counts'][lo:lo + B].data_ptr(), st))
@@ -901,7 +910,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=400)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--streams', type=int, default=8, help='steps are issued round-robin over this many CUDA streams')
@@ -913,7 +922,7 @@ def main():
     ap.add_argument('--workload-steps', type=int, default=100, help='cap on the steps of the extra workloads')
     ap.add_argument('--batch-override', type=int, default=0, help='experiments: images per GPU and step of the FPN workloads')
     ap.add_argument('--pcie-probe', action='store_true', help='N = 1: also run the host-link copy probe of the e2e block')
-    ap.add_argument('--priority', type=int, default=0, help='1: proposal kernels on high-priority side streams')
+    ap.add_argument('--priority', type=int, default=2, help='1: proposal kernels on high-priority side streams; 2: as independent chains (proposals of a later step overlap the RoI kernels of the lane)')
     ap.add_argument('--no-graph', action='store_true', help='issue the timed region eagerly instead of as one CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
