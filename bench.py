@@ -38,7 +38,7 @@ WORKLOAD = dict(name='cfg2: ResNet-50 C4 600x1000, 21546 anchors, pre-NMS 6000 -
 METRIC = 'proposal+NMS+RoIAlign images/s'
 UNIT = 'images/s'
 FALLBACK_HBM_GBS = 6650.0
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 516283136   # profiles/r1_ncu_full_raw.csv: 92.8 MB read + 423.5 MB written by roi_band_kernel
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 517105152   # profiles/r2_ncu_band_raw.csv: 92.3 MB read + 424.8 MB written by roi_band_kernel
 
 
 def headline_config(w):

@@ -1186,3 +1186,57 @@ def test_eval_loop_detections(bx, golden):
                 assert gx[:2] == gy[:2] and all(abs(float(p) - float(q)) <= 0.1001 for p, q in zip(gx[2:], gy[2:])), (x, y)
     with pytest.raises(ValueError):
         bx.eval_detections(scores, deltas, rois, raw, scale, max_num_per_image=50, out_rows=10)     # out_rows < max_per_image
+
+
+def test_cuda_graph_capture_and_stream_ordered_workspaces(bx):
+    """The calls are capturable into a CUDA graph (what bench.py times): a capture that would have to GROW a workspace is
+    refused with NotImplementedError (BX_ERR_UNSUPPORTED), after one warm-up call (or bx_reserve) the same capture works and
+    its replay reproduces the eager result; growth itself is stream-ordered — no device-wide synchronisation — and the
+    caller's current stream / device are untouched."""
+    import ctypes
+    from tf_eager_object_detection_b200 import _lib
+    img = syn.fpn_image(3, 2, with_features=False)                       # 150 111 anchors: top-set workspace needed
+    a, d, s = cu(img['anchors']), cu(img['deltas'])[None], cu(img['scores'])[None]
+    side = torch.cuda.Stream()
+    lib = _lib.load()
+    with torch.cuda.stream(side):
+        h = _lib.handle(0, side.cuda_stream)
+        assert _lib.stats(h)['ws_bytes'] == 0
+        g = torch.cuda.CUDAGraph()
+        with pytest.raises(NotImplementedError):
+            with torch.cuda.graph(g, stream=side, capture_error_mode='thread_local'):
+                bx.proposals(a, d, s, (600, 1000), 1000)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        ob, oi, oc = bx.proposals(a, d, s, (600, 1000), 1000)            # warm-up: the workspace grows here (cudaMallocAsync)
+        assert _lib.stats(h)['ws_bytes'] > 0
+        out = [torch.empty_like(ob), torch.empty_like(oi), torch.empty_like(oc)]
+        p = bx.proposal_params((600, 1000), 1000)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side, capture_error_mode='thread_local'):
+            _lib.check(lib.bx_proposals(h, a.data_ptr(), d.data_ptr(), s.data_ptr(), 1, a.shape[0], ctypes.byref(p),
+                                        out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), ctypes.c_void_p(side.cuda_stream)))
+        for t in out:
+            t.zero_()
+        g.replay()
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], ob) and torch.equal(out[1], oi) and torch.equal(out[2], oc)
+    _, idx = orc.region_proposal(img['deltas'], img['anchors'], img['scores'], (600, 1000), 1000)
+    assert np.array_equal(out[1][0].cpu().numpy(), idx)
+    # bx_reserve sizes a fresh handle up front: the first call of that handle can then be captured directly
+    hh = ctypes.c_void_p()
+    _lib.check(lib.bx_create(0, ctypes.byref(hh)))
+    st = _lib.stats(h)
+    _lib.check(lib.bx_reserve(hh, st['ws_bytes'], st['plan_bytes'], 0, ctypes.c_void_p(side.cuda_stream)))
+    with torch.cuda.stream(side):
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, stream=side, capture_error_mode='thread_local'):
+            _lib.check(lib.bx_proposals(hh, a.data_ptr(), d.data_ptr(), s.data_ptr(), 1, a.shape[0], ctypes.byref(p),
+                                        out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), ctypes.c_void_p(side.cuda_stream)))
+        out[1].zero_()
+        g2.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out[1], oi)
+    del g2
+    _lib.check(lib.bx_destroy(hh))
