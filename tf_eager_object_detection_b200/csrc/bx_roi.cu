@@ -498,7 +498,7 @@ int launch_roi(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st) {
     if (!used && pool == BX_POOL_NONE && !band_pooled) h->band_fallbacks++;
   }
   if (!used && pool != BX_POOL_NONE && !getenv("BX_ROI_NO_POOL2")) {
-    rc = roi_stage_launch(h, a, pool, st, &used);    // roi footprint staged in shared memory by TMA (bx_roi_stage.cu)
+    rc = roi_stage_launch(h, a, pool, st, &used);    // opt-in: roi footprint staged in shared memory by TMA (bx_roi_stage.cu)
     if (rc) return rc;
   }
   if (!used && roi_pool2_ok(a, pool)) {
