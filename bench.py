@@ -680,6 +680,7 @@ def bench_c4(ctx, args):
                 single_stream=dict(ms_per_step=round(ms_single_max / K, 5),
                                    images_per_s=round(ctx.world * K * B / (ms_single_max * 1e-3), 1),
                                    composite_hbm_frac=frac(step_bytes * K, ms_single_max), streams=1,
+                                   note='one lane: one stream (plus its proposal side stream when --priority > 0), steps back to back',
                                    roi_launch_ms=round(alone_ms, 5), roi_hbm_frac=frac(roi_bytes, alone_ms),
                                    launches_timed=len(roi_ms_alone))),
             roofline=dict(bound='hbm', kernel='roi_plan_kernel + roi_band_kernel (RoI pooling of one batch)',
@@ -893,12 +894,26 @@ def run_ours(args):
     line = bench_c4(ctx, args)
     names = ['cfg3', 'cfg5', 'cfg4'] if args.workloads == 'all' else [s for s in args.workloads.split(',') if s and s != 'none']
     extra = {}
+
+    def give_up():
+        """Watchdog (every rank): the extra workloads may never take the headline line down — if they have not finished in
+        time (a rank failed inside a collective, say), rank 0 prints the headline with what is there and everybody exits."""
+        if ctx.rank == 0:
+            extra['error'] = 'extra workloads did not finish within %d s; headline line printed without them' % args.workload_timeout
+            line['workloads'] = extra
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+    watchdog = threading.Timer(args.workload_timeout, give_up)
+    watchdog.daemon = True
+    if names:
+        watchdog.start()
     for nm in names:
         try:
             extra[nm] = bench_targets(ctx, args) if nm == 'cfg4' else bench_fpn(ctx, args, nm)
         except Exception as e:                               # a secondary workload never takes the headline line down
             extra[nm] = dict(error='%s: %s' % (type(e).__name__, str(e)[:300]))
             ctx.torch.cuda.synchronize()
+    watchdog.cancel()
     if ctx.rank == 0:
         line['workloads'] = extra
         line['details']['graph_error'] = ctx.graph_error
@@ -920,6 +935,7 @@ def main():
                     help='N > 1: detection records of this many consecutive steps are all-gathered together (0: all K, one gather at the end of the region)')
     ap.add_argument('--workloads', default='all', help='all | none | comma list of cfg3,cfg5,cfg4 (measured after the headline)')
     ap.add_argument('--workload-steps', type=int, default=100, help='cap on the steps of the extra workloads')
+    ap.add_argument('--workload-timeout', type=int, default=240, help='seconds after which the extra workloads are abandoned')
     ap.add_argument('--batch-override', type=int, default=0, help='experiments: images per GPU and step of the FPN workloads')
     ap.add_argument('--pcie-probe', action='store_true', help='N = 1: also run the host-link copy probe of the e2e block')
     ap.add_argument('--priority', type=int, default=2, help='1: proposal kernels on high-priority side streams; 2: as independent chains (proposals of a later step overlap the RoI kernels of the lane)')
