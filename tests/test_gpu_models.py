@@ -182,3 +182,34 @@ def test_fpn_eval_and_training_forward():
     fg_anchors = net.predict_rpns([256, 384], gt, seed=2, device=image.device)
     assert fg_anchors.shape[1] == 4 and fg_anchors.shape[0] > 0
     assert net.predict_rois(image, gt, gl, seed=2).shape == (128, 4)
+
+
+def test_get_prediction_files_reproduces_the_reference_files(golden, tmp_path):
+    """evaluation.get_prediction_files — model.im_detect -> per-image filtering on the device -> VOC result files — fed
+    with the synthetic roi-head outputs the golden was generated from, against the text of the files the reference's own
+    get_prediction_files wrote (scores and ids identical, corners printed to 0.1 px)."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from oracle.voc_fixture import eval_loop_inputs
+    from tf_eager_object_detection_b200 import evaluation as ev
+    imgs = eval_loop_inputs()
+    cu = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()  # noqa: E731
+
+    class Model:
+        def im_detect_batched(self, i):
+            im = imgs[i]
+            return (cu(im['scores'])[None], cu(im['deltas'].reshape(300, -1))[None], cu(im['rois'])[None],
+                    torch.tensor([300], dtype=torch.int32, device='cuda'))
+    names = ['%06d' % (i + 1) for i in range(len(imgs))]
+    dataset = [(i, im['scale'], im['raw_h'], im['raw_w']) for i, im in enumerate(imgs)]
+    for tag, max_img in (('eval_voc', 50), ('eval_voc_nocut', 0)):
+        d = tmp_path / tag
+        d.mkdir()
+        rec, cnt = ev.get_prediction_files(Model(), dataset, names, str(d / '{:s}.txt'), score_threshold=0.05, iou_threshold=0.3,
+                                           max_objects_per_class=50, max_objects_per_image=max_img, min_size=10)
+        got = ''.join(open(d / ('%s.txt' % c)).read() for c in ev.PASCAL_CLASSES[1:]).splitlines()
+        ref_lines = bytes(golden[tag + '_files']).decode().splitlines()
+        assert len(got) == len(ref_lines) and (max_img == 0 or cnt.tolist() == [50, 50, 76])
+        for x, y in zip(got, ref_lines):
+            gx, gy = x.split(), y.split()
+            assert gx[:2] == gy[:2] and all(abs(float(p) - float(q)) <= 0.1001 for p, q in zip(gx[2:], gy[2:])), (x, y)

@@ -14,7 +14,7 @@ import xml.etree.ElementTree as ET
 import numpy as np
 
 __all__ = ['PASCAL_CLASSES', 'coco_category_ids', 'records_to_host', 'voc_result_lines', 'write_voc_results',
-           'coco_results', 'write_coco_results', 'voc_ap', 'voc_match', 'voc_eval', 'parse_rec']
+           'coco_results', 'write_coco_results', 'voc_ap', 'voc_match', 'voc_eval', 'parse_rec', 'get_prediction_files']
 
 PASCAL_CLASSES = ('__background__', 'aeroplane', 'bicycle', 'bird', 'boat', 'bottle', 'bus', 'car', 'cat', 'chair', 'cow',
                   'diningtable', 'dog', 'horse', 'motorbike', 'person', 'pottedplant', 'sheep', 'sofa', 'train',
@@ -180,3 +180,46 @@ def voc_eval(detpath, annopath, imagesetfile, classname, cachedir, ovthresh=0.5,
     conf = np.array([float(x[1]) for x in split])
     bb = np.array([[float(z) for z in x[2:]] for x in split])
     return voc_match(ids, conf, bb, class_recs, npos, ovthresh, use_07_metric)
+
+
+def get_prediction_files(cur_model, eval_dataset, image_sets, result_file_format='/path/to/results/{:s}.txt',
+                         score_threshold=0.0, iou_threshold=0.5, max_objects_per_class=50, max_objects_per_image=50,
+                         target_means=None, target_stds=None, min_size=10, class_list=PASCAL_CLASSES, group=None):
+    """`evaluation/pascal_eval_files_utils.py:19-122` `get_prediction_files` from the model down: for every
+    `(img, img_scale, raw_h, raw_w)` of `eval_dataset` (the reference builds it from `dataset_type` / `data_root_path`; data
+    pipelines are out of scope, so the iterable and its `image_sets` ids are passed in) run the model's `im_detect`, the
+    per-image detection filtering of the loop body (:76-106, on the device, no host synchronisation per image) and write the
+    per-class VOC result files (:109-122).  Under torch.distributed every rank passes ITS shard of the dataset
+    (`distributed.shard_bounds` order); the records are all-gathered once at the end and rank 0 writes the files for the
+    full `image_sets`.  Returns (records [n,rows,6], counts [n]) of all images (host numpy)."""
+    import torch
+    import torch.distributed as dist
+    from . import distributed as bxd
+    from .prediction import eval_loop_detections
+    num_classes = len(class_list)
+    rows = (num_classes - 1) * max_objects_per_class       # room for every tie at the per-image cut (:99-106)
+    recs, cnts = [], []
+    for img, img_scale, raw_h, raw_w in eval_dataset:
+        sm, tx, rois, roi_counts = cur_model.im_detect_batched(img)
+        dev = sm.device
+        det, cnt = eval_loop_detections(sm, tx, rois, torch.tensor([float(img_scale)], device=dev),
+                                        torch.tensor([[float(raw_h), float(raw_w)]], device=dev), target_means, target_stds,
+                                        score_threshold=score_threshold, iou_threshold=iou_threshold,
+                                        max_objects_per_class=max_objects_per_class,
+                                        max_objects_per_image=max_objects_per_image, min_size=min_size, loop='voc',
+                                        out_rows=rows, roi_counts=roi_counts)
+        recs.append(det)
+        cnts.append(cnt)
+    if recs:
+        rec, cnt = torch.cat(recs), torch.cat(cnts)
+    else:
+        rec = torch.zeros((0, rows, 6), device='cuda'); cnt = torch.zeros((0,), dtype=torch.int32, device='cuda')
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if distributed:
+        rec, cnt = bxd.allgather_detections(rec, cnt, group=group)
+    rec_h, cnt_h = records_to_host(rec, cnt)
+    if not distributed or dist.get_rank(group) == 0:
+        if len(image_sets) != rec_h.shape[0]:
+            raise ValueError('get_prediction_files: %d image ids for %d images' % (len(image_sets), rec_h.shape[0]))
+        write_voc_results(result_file_format, image_sets, rec_h, cnt_h, class_list)
+    return rec_h, cnt_h
