@@ -37,4 +37,36 @@ for name, (x, y) in dict(packed=(ra, ca), static=(rs, cs), native=(rn, cn), nati
 torch.cuda.synchronize()
 if rank == 0:
     print('allgather ok: world %d, %d images, records %s' % (world, ra.shape[0], tuple(ra.shape)), flush=True)
+
+
+# ---- evaluation.get_prediction_files over two ranks: uneven shards of the three golden images, files written by rank 0
+import tempfile
+import numpy as np
+from oracle.voc_fixture import eval_loop_inputs
+from tf_eager_object_detection_b200 import evaluation as ev
+imgs = eval_loop_inputs()
+cu = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+
+
+class _Model:
+    def im_detect_batched(self, i):
+        im = imgs[i]
+        return (cu(im['scores'])[None], cu(im['deltas'].reshape(300, -1))[None], cu(im['rois'])[None],
+                torch.tensor([300], dtype=torch.int32, device=dev))
+
+
+lo, hi = bxd.shard_bounds(len(imgs), rank, world)
+names = ['%06d' % (i + 1) for i in range(len(imgs))]
+with tempfile.TemporaryDirectory() as d:
+    rec, cnt = ev.get_prediction_files(_Model(), [(i, imgs[i]['scale'], imgs[i]['raw_h'], imgs[i]['raw_w']) for i in range(lo, hi)],
+                                       names, os.path.join(d, '{:s}.txt'), score_threshold=0.05, iou_threshold=0.3,
+                                       max_objects_per_class=50, max_objects_per_image=50, min_size=10)
+    assert cnt.tolist() == [50, 50, 76]
+    if rank == 0:
+        golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_on_shim.npz'))
+        got = ''.join(open(os.path.join(d, '%s.txt' % c)).read() for c in ev.PASCAL_CLASSES[1:]).splitlines()
+        ref = bytes(golden['eval_voc_files']).decode().splitlines()
+        assert len(got) == len(ref) and all(x.split()[:2] == y.split()[:2] for x, y in zip(got, ref))
+        print('prediction files ok: %d lines from %d ranks' % (len(got), world), flush=True)
+torch.cuda.synchronize()
 dist.destroy_process_group()

@@ -862,7 +862,8 @@ def test_native_allgather_on_two_ranks():
     out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
                           '--master-addr', '127.0.0.1', '--master-port', '29541', script], capture_output=True, text=True,
                          timeout=240)
-    assert out.returncode == 0 and 'allgather ok' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.returncode == 0 and 'allgather ok' in out.stdout and 'prediction files ok' in out.stdout, \
+        out.stdout[-2000:] + out.stderr[-2000:]
 
 
 def test_nms_long_suppression_chains_and_cluster_sweep(bx):
