@@ -1241,3 +1241,25 @@ def test_cuda_graph_capture_and_stream_ordered_workspaces(bx):
     assert torch.equal(out[1], oi)
     del g2
     _lib.check(lib.bx_destroy(hh))
+
+
+def test_persistent_band_kernel_matches_default(bx, monkeypatch):
+    """BX_ROI_BAND_PERSIST=1: the persistent, double-buffered form of the TMA band kernel (one CTA per SM, units drawn from
+    a global counter, next band + plan block prefetched) must reproduce the per-unit kernel bit for bit — plain crops at the
+    cfg2 geometry with padded rois, several plan blocks per unit, and a pooled crop through the band path."""
+    from tf_eager_object_detection_b200 import _lib
+    rng = np.random.default_rng(77)
+    B, C = 3, 96
+    feat = cu(rng.standard_normal((B, 38, 63, C), dtype=np.float32))
+    rois = np.stack([syn.random_rois(rng, 400, (600, 1000)) for _ in range(B)])
+    counts = cu(np.int32([400, 250, 0]))
+    monkeypatch.delenv('BX_ROI_BAND_PERSIST', raising=False)
+    base = bx.roi_pool(_lib.ROI_STRIDE_NORM, _lib.POOL_NONE, 7, feat, cu(rois), stride=16.0, roi_counts=counts)
+    monkeypatch.setenv('BX_ROI_BAND_PERSIST', '1')
+    got = bx.roi_pool(_lib.ROI_STRIDE_NORM, _lib.POOL_NONE, 7, feat, cu(rois), stride=16.0, roi_counts=counts)
+    assert torch.equal(got, base)
+    ref = orc.roi_pool_c4(feat[:1].cpu().numpy(), rois[0], 16, 7, False)
+    assert np.array_equal(got[:400].cpu().numpy(), ref) and (got[650:] == 0).all()
+    monkeypatch.setenv('BX_ROI_BAND_POOLED', '1')
+    pooled = bx.roi_pool(_lib.ROI_STRIDE_NORM, _lib.POOL_MAX2, 7, feat[:1], cu(rois[0]), stride=16.0)
+    assert np.array_equal(pooled.cpu().numpy(), orc.roi_pool_c4(feat[:1].cpu().numpy(), rois[0], 16, 7, True))

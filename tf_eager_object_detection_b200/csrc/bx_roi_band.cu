@@ -31,6 +31,10 @@ struct BandArgs {
   unsigned char* plan;   // [b, n_bands, n_blocks_max] plan blocks (global workspace)
   float neg_zero;        // -0.0f at run time: addend that turns fma.rn.f32x2 into an exact, non-contractible multiply
   unsigned long long* dbg;   // optional [grid,4] timestamps (globaltimer ns: start, band ready, done; smid) — BX_BAND_DEBUG
+  // persistent kernel: units beyond the first one of a CTA are drawn from *unit_counter (zeroed by the plan kernel)
+  int* unit_counter;
+  int n_units;               // b * n_slices * n_bands
+  int band_stride;           // bytes between the two band buffers (band + zero row, 128-byte aligned); 0: one buffer
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -124,6 +128,7 @@ __global__ void __launch_bounds__(kPlanThreads) roi_plan_kernel(const BandArgs a
   // programmatic dependent launch: let the band kernel start (and issue its TMA band loads) while the plan is computed;
   // it waits on griddepcontrol.wait before touching the plan
   asm volatile("griddepcontrol.launch_dependents;");
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.unit_counter) *a.unit_counter = 0;   // read behind griddepcontrol.wait only
   const RoiArgs& r = a.r;
   const int tid = threadIdx.x, lane = tid & 31;
   const int band_i = blockIdx.x % a.n_bands;
@@ -337,10 +342,191 @@ __device__ __forceinline__ void pool_acc(float4& acc, const float4 v, bool first
   else acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
 }
 
+// One plan block of one unit (image, channel slice, band): every run of output rows listed in `tab`, taps from the band staged
+// at `band` (zero row at band + a.band_bytes).  Shared by the per-unit kernel and the persistent kernel.
+template <int POOL, int THREADS>
+__device__ __forceinline__ void band_process_block(const BandArgs& a, const unsigned char* __restrict__ tab,
+                                                   const unsigned char* __restrict__ band, const float* __restrict__ feat_img,
+                                                   int slice, int g_begin, int tid) {
+  constexpr int S = (POOL == BX_POOL_NONE) ? 1 : 2;
+  const RoiArgs& r = a.r;
+  const int fw = r.lv[0].fw;
+  const int P = r.P, Q = r.Q, C = r.c;
+  const PlanLayout L = plan_layout(a.cap, Q);
+  const unsigned long long* xval = reinterpret_cast<const unsigned long long*>(tab + L.off_xval);
+  const uint2* xtab = reinterpret_cast<const uint2*>(tab + L.off_xtab);
+  const uint2* ytab = reinterpret_cast<const uint2*>(tab + L.off_ytab);
+  const uint2* runs = reinterpret_cast<const uint2*>(tab + L.off_runs);
+  const int lane = tid & 31;
+  const int q = lane & 7, sub = lane >> 3;
+  const unsigned char* band_q = band + q * 16;
+  const bool ext_zero = (r.extrapolation == 0.0f);
+  const unsigned long long nz2 = f2_splat(a.neg_zero);
+  // output pixel (first roi of the image, py 0, px 0), this unit's channel slice, this lane's 4 channels
+  float4* out_c0 = reinterpret_cast<float4*>(r.out + static_cast<size_t>(g_begin) * P * P * C + slice * kSlice + q * 4);
+  const uint32_t c4 = static_cast<uint32_t>(C) >> 2;
+  const int n_items = *reinterpret_cast<const int*>(tab);
+  // ---- one warp per run of output rows of a roi; 8 lanes (32 channels) per pixel.  Runs are sorted by descending
+  //      length in the plan and dealt round-robin to the warps.
+  for (int it = tid >> 5; it < n_items; it += THREADS / 32) {
+    const uint2 we = runs[it];
+    const int l = we.x & 0xFFF;
+    const bool zero = (we.x >> 12) & 1u;
+    const int py_begin = (we.x >> 16) & 0xFF, py_end = we.x >> 24;
+    const float ev = zero ? 0.0f : r.extrapolation;
+    const unsigned long long xv = xval[l];
+    const uint2* xrow = xtab + l * Q;
+    const uint2* yrow = ytab + l * Q;
+    // fast paths: every sample column valid, extrapolation 0 and (pooled crops) every valid sample row inside the
+    // staged band: invalid sample rows read the zero row, so no selects and no validity tests are needed
+    // (sample columns outside the map — rois clipped at the right / bottom image border end there in the C4 geometry —
+    //  read pixel 0 and are zeroed by one select per output, so they stay on the fast paths)
+    const bool fast = (ext_zero || zero) && (S == 1 || ((we.x >> 14) & 1u));
+    if (fast && S == 1) {
+      // two pixels per lane (px and px + 4) share each row's y parameters: 8 independent tap loads in flight per row
+      for (int px0 = 0; px0 < P; px0 += 8) {
+        const int pxA = px0 + sub, pxB = pxA + 4;
+        const bool actA = pxA < P, actB = pxB < P;
+        const uint2 xa = xrow[actA ? pxA : 0], xb = xrow[actB ? pxB : 0];
+        const unsigned char* a_lo = band_q + (xa.x & 0xFFFFu);
+        const unsigned char* a_hi = band_q + (xa.x >> 16);
+        const unsigned char* b_lo = band_q + (xb.x & 0xFFFFu);
+        const unsigned char* b_hi = band_q + (xb.x >> 16);
+        const unsigned long long wa2 = f2_splat(__uint_as_float(xa.y)), wb2 = f2_splat(__uint_as_float(xb.y));
+        const bool okA = (xv >> (actA ? pxA : 0)) & 1ull, okB = (xv >> (actB ? pxB : 0)) & 1ull;
+        float4* out_a = out_c0 + (we.y + static_cast<uint32_t>(pxA) * c4);
+        const bool two = px0 + 4 < P;                        // warp-uniform: is there a second group of pixels?
+        for (int py = py_begin; py < py_end; ++py) {
+          const uint2 ye = yrow[py];
+          const uint32_t ta = (ye.x & 0x3FFFu) << 4, tb = ((ye.x >> 16) & 0x3FFFu) << 4;
+          const unsigned long long wy2 = f2_splat(__uint_as_float(ye.y));
+          ulonglong2 oa = lerp2_packed(*reinterpret_cast<const ulonglong2*>(a_lo + ta),
+                                       *reinterpret_cast<const ulonglong2*>(a_hi + ta),
+                                       *reinterpret_cast<const ulonglong2*>(a_lo + tb),
+                                       *reinterpret_cast<const ulonglong2*>(a_hi + tb), wa2, wy2, nz2);
+          if (!okA) oa = make_ulonglong2(0ull, 0ull);
+          if (two) {
+            // lanes whose second pixel does not exist (px >= P) issue no loads: their 128 B would be a wasted
+            // shared-memory wavefront per tap, and this kernel is bound by the LSU data pipe
+            ulonglong2 b0 = make_ulonglong2(0ull, 0ull), b1 = b0, b2 = b0, b3 = b0;
+            if (actB) {
+              b0 = *reinterpret_cast<const ulonglong2*>(b_lo + ta);
+              b1 = *reinterpret_cast<const ulonglong2*>(b_hi + ta);
+              b2 = *reinterpret_cast<const ulonglong2*>(b_lo + tb);
+              b3 = *reinterpret_cast<const ulonglong2*>(b_hi + tb);
+            }
+            ulonglong2 ob = lerp2_packed(b0, b1, b2, b3, wb2, wy2, nz2);
+            if (!okB) ob = make_ulonglong2(0ull, 0ull);
+            if (actB) *reinterpret_cast<ulonglong2*>(out_a + 4 * c4) = ob;
+          }
+          if (actA) *reinterpret_cast<ulonglong2*>(out_a) = oa;
+          out_a += static_cast<uint32_t>(P) * c4;
+        }
+      }
+    } else if (fast) {
+      // pooled crop (2x2 samples per output pixel), packed math, max / mean in the slow path's order (sy major)
+      for (int px0 = 0; px0 < P; px0 += 4) {
+        const int px = px0 + sub;
+        const bool act = px < P;
+        const int pxc = act ? px : 0;
+        const uint2 x0 = xrow[pxc * 2], x1 = xrow[pxc * 2 + 1];
+        const unsigned char* lo0 = band_q + (x0.x & 0xFFFFu);
+        const unsigned char* hi0 = band_q + (x0.x >> 16);
+        const unsigned char* lo1 = band_q + (x1.x & 0xFFFFu);
+        const unsigned char* hi1 = band_q + (x1.x >> 16);
+        const unsigned long long w0 = f2_splat(__uint_as_float(x0.y)), w1 = f2_splat(__uint_as_float(x1.y));
+        const bool ok0 = (xv >> (pxc * 2)) & 1ull, ok1 = (xv >> (pxc * 2 + 1)) & 1ull;
+        float4* out_px = out_c0 + (we.y + static_cast<uint32_t>(px) * c4);
+        for (int py = py_begin; py < py_end; ++py) {
+          ulonglong2 acc;
+#pragma unroll
+          for (int sy = 0; sy < 2; ++sy) {
+            const uint2 ye = yrow[py * 2 + sy];
+            const uint32_t ta = (ye.x & 0x3FFFu) << 4, tb = ((ye.x >> 16) & 0x3FFFu) << 4;
+            const unsigned long long wy2 = f2_splat(__uint_as_float(ye.y));
+            ulonglong2 v0 = lerp2_packed(*reinterpret_cast<const ulonglong2*>(lo0 + ta),
+                                         *reinterpret_cast<const ulonglong2*>(hi0 + ta),
+                                         *reinterpret_cast<const ulonglong2*>(lo0 + tb),
+                                         *reinterpret_cast<const ulonglong2*>(hi0 + tb), w0, wy2, nz2);
+            ulonglong2 v1 = lerp2_packed(*reinterpret_cast<const ulonglong2*>(lo1 + ta),
+                                         *reinterpret_cast<const ulonglong2*>(hi1 + ta),
+                                         *reinterpret_cast<const ulonglong2*>(lo1 + tb),
+                                         *reinterpret_cast<const ulonglong2*>(hi1 + tb), w1, wy2, nz2);
+            if (!ok0) v0 = make_ulonglong2(0ull, 0ull);
+            if (!ok1) v1 = make_ulonglong2(0ull, 0ull);
+            if (sy == 0) acc = v0; else acc = pool2<POOL>(acc, v0);
+            acc = pool2<POOL>(acc, v1);
+          }
+          if (POOL == BX_POOL_AVG2) {
+            const unsigned long long q4 = f2_splat(0.25f);   // x / 4 == x * 0.25 exactly (power of two)
+            acc.x = f2_mul(acc.x, q4, nz2);
+            acc.y = f2_mul(acc.y, q4, nz2);
+          }
+          if (act) *reinterpret_cast<ulonglong2*>(out_px) = acc;
+          out_px += static_cast<uint32_t>(P) * c4;
+        }
+      }
+    } else {
+      for (int px0 = 0; px0 < P; px0 += 4) {
+        const int px = px0 + sub;
+        const bool act = px < P;
+        const int pxc = act ? px : 0;
+        float4* out_px = out_c0 + (we.y + static_cast<uint32_t>(px) * c4);
+        uint32_t xlo[S], xhi[S];
+        float lx[S];
+        bool xok[S];
+#pragma unroll
+        for (int sx = 0; sx < S; ++sx) {
+          const uint2 xp = xrow[pxc * S + sx];
+          xlo[sx] = xp.x & 0xFFFFu;
+          xhi[sx] = xp.x >> 16;
+          lx[sx] = __uint_as_float(xp.y);
+          xok[sx] = (xv >> (pxc * S + sx)) & 1ull;
+        }
+        for (int py = py_begin; py < py_end; ++py) {
+          float4 acc;
+#pragma unroll
+          for (int sy = 0; sy < S; ++sy) {
+            const uint2 ye = yrow[py * S + sy];
+            const bool yok = ye.x >> 31;
+            const bool inb = (ye.x >> 15) & 1u;
+            const uint32_t ya = ye.x & 0x3FFFu, yb = (ye.x >> 16) & 0x3FFFu;
+#pragma unroll
+            for (int sx = 0; sx < S; ++sx) {
+              float4 tl, tr, bl, br;
+              if (inb) {
+                const unsigned char* bt = band_q + (ya << 4);
+                const unsigned char* bb = band_q + (yb << 4);
+                tl = *reinterpret_cast<const float4*>(bt + xlo[sx]);
+                tr = *reinterpret_cast<const float4*>(bt + xhi[sx]);
+                bl = *reinterpret_cast<const float4*>(bb + xlo[sx]);
+                br = *reinterpret_cast<const float4*>(bb + xhi[sx]);
+              } else {  // sample row of a pooled pair reaching past the staged band: read it from L2
+                const float* gt = feat_img + (static_cast<size_t>(ya) * fw) * C + slice * kSlice + q * 4;
+                const float* gb = feat_img + (static_cast<size_t>(yb) * fw) * C + slice * kSlice + q * 4;
+                const size_t lo = xlo[sx] / (kSlice * 4), hi = xhi[sx] / (kSlice * 4);
+                tl = __ldg(reinterpret_cast<const float4*>(gt + lo * C));
+                tr = __ldg(reinterpret_cast<const float4*>(gt + hi * C));
+                bl = __ldg(reinterpret_cast<const float4*>(gb + lo * C));
+                br = __ldg(reinterpret_cast<const float4*>(gb + hi * C));
+              }
+              float4 v = lerp2(tl, tr, bl, br, lx[sx], __uint_as_float(ye.y));
+              if (!(yok && xok[sx])) v = make_float4(ev, ev, ev, ev);
+              pool_acc<POOL>(acc, v, sy == 0 && sx == 0);
+            }
+          }
+          if (POOL == BX_POOL_AVG2) acc = make_float4(acc.x / 4.0f, acc.y / 4.0f, acc.z / 4.0f, acc.w / 4.0f);
+          if (act) *out_px = acc;
+          out_px += static_cast<uint32_t>(P) * c4;
+        }
+      }
+    }
+  }
+}
+
 template <int POOL, int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 512) ? 2 : 1)
 roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
-  constexpr int S = (POOL == BX_POOL_NONE) ? 1 : 2;
   extern __shared__ __align__(128) unsigned char smem[];
   const RoiArgs& r = a.r;
   const int fh = r.lv[0].fh, fw = r.lv[0].fw;
@@ -387,13 +573,6 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
 
   int g_begin = 0;   // first roi of the image's range
   if (!a.scan_all && r.roi_counts) g_begin = img * r.rois_per_image;
-  const int q = lane & 7, sub = lane >> 3;
-  const unsigned char* band_q = smem + q * 16;
-  const bool ext_zero = (r.extrapolation == 0.0f);
-  const unsigned long long nz2 = f2_splat(a.neg_zero);
-  // output pixel (first roi of the image, py 0, px 0), this CTA's channel slice, this lane's 4 channels
-  float4* out_c0 = reinterpret_cast<float4*>(r.out + static_cast<size_t>(g_begin) * P * P * C + slice * kSlice + q * 4);
-  const uint32_t c4 = static_cast<uint32_t>(C) >> 2;
 
   int n_blocks = 1;
   for (int ch = 0; ch < n_blocks; ++ch) {
@@ -407,171 +586,11 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
         bulk_load(tab0 + ((ch + 1) & 1) * tab_step, plan0 + static_cast<size_t>(ch + 1) * L.bytes, L.bytes, &mbar[(ch + 1) & 1]);
       }
     }
-    const unsigned long long* xval = reinterpret_cast<const unsigned long long*>(tab + L.off_xval);
-    const uint2* xtab = reinterpret_cast<const uint2*>(tab + L.off_xtab);
-    const uint2* ytab = reinterpret_cast<const uint2*>(tab + L.off_ytab);
-    const uint2* runs = reinterpret_cast<const uint2*>(tab + L.off_runs);
     if (a.dbg && tid == 0 && ch == 0) {
       unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       a.dbg[blockIdx.x * 4 + 1] = t;
     }
-    const int n_items = *reinterpret_cast<const int*>(tab);
-    // ---- one warp per run of output rows of a roi; 8 lanes (32 channels) per pixel.  Runs are sorted by descending
-    //      length in the plan and dealt round-robin to the warps.
-    for (int it = tid >> 5; it < n_items; it += THREADS / 32) {
-      const uint2 we = runs[it];
-      const int l = we.x & 0xFFF;
-      const bool zero = (we.x >> 12) & 1u;
-      const int py_begin = (we.x >> 16) & 0xFF, py_end = we.x >> 24;
-      const float ev = zero ? 0.0f : r.extrapolation;
-      const unsigned long long xv = xval[l];
-      const uint2* xrow = xtab + l * Q;
-      const uint2* yrow = ytab + l * Q;
-      // fast paths: every sample column valid, extrapolation 0 and (pooled crops) every valid sample row inside the
-      // staged band: invalid sample rows read the zero row, so no selects and no validity tests are needed
-      // (sample columns outside the map — rois clipped at the right / bottom image border end there in the C4 geometry —
-      //  read pixel 0 and are zeroed by one select per output, so they stay on the fast paths)
-      const bool fast = (ext_zero || zero) && (S == 1 || ((we.x >> 14) & 1u));
-      if (fast && S == 1) {
-        // two pixels per lane (px and px + 4) share each row's y parameters: 8 independent tap loads in flight per row
-        for (int px0 = 0; px0 < P; px0 += 8) {
-          const int pxA = px0 + sub, pxB = pxA + 4;
-          const bool actA = pxA < P, actB = pxB < P;
-          const uint2 xa = xrow[actA ? pxA : 0], xb = xrow[actB ? pxB : 0];
-          const unsigned char* a_lo = band_q + (xa.x & 0xFFFFu);
-          const unsigned char* a_hi = band_q + (xa.x >> 16);
-          const unsigned char* b_lo = band_q + (xb.x & 0xFFFFu);
-          const unsigned char* b_hi = band_q + (xb.x >> 16);
-          const unsigned long long wa2 = f2_splat(__uint_as_float(xa.y)), wb2 = f2_splat(__uint_as_float(xb.y));
-          const bool okA = (xv >> (actA ? pxA : 0)) & 1ull, okB = (xv >> (actB ? pxB : 0)) & 1ull;
-          float4* out_a = out_c0 + (we.y + static_cast<uint32_t>(pxA) * c4);
-          const bool two = px0 + 4 < P;                        // warp-uniform: is there a second group of pixels?
-          for (int py = py_begin; py < py_end; ++py) {
-            const uint2 ye = yrow[py];
-            const uint32_t ta = (ye.x & 0x3FFFu) << 4, tb = ((ye.x >> 16) & 0x3FFFu) << 4;
-            const unsigned long long wy2 = f2_splat(__uint_as_float(ye.y));
-            ulonglong2 oa = lerp2_packed(*reinterpret_cast<const ulonglong2*>(a_lo + ta),
-                                         *reinterpret_cast<const ulonglong2*>(a_hi + ta),
-                                         *reinterpret_cast<const ulonglong2*>(a_lo + tb),
-                                         *reinterpret_cast<const ulonglong2*>(a_hi + tb), wa2, wy2, nz2);
-            if (!okA) oa = make_ulonglong2(0ull, 0ull);
-            if (two) {
-              // lanes whose second pixel does not exist (px >= P) issue no loads: their 128 B would be a wasted
-              // shared-memory wavefront per tap, and this kernel is bound by the LSU data pipe
-              ulonglong2 b0 = make_ulonglong2(0ull, 0ull), b1 = b0, b2 = b0, b3 = b0;
-              if (actB) {
-                b0 = *reinterpret_cast<const ulonglong2*>(b_lo + ta);
-                b1 = *reinterpret_cast<const ulonglong2*>(b_hi + ta);
-                b2 = *reinterpret_cast<const ulonglong2*>(b_lo + tb);
-                b3 = *reinterpret_cast<const ulonglong2*>(b_hi + tb);
-              }
-              ulonglong2 ob = lerp2_packed(b0, b1, b2, b3, wb2, wy2, nz2);
-              if (!okB) ob = make_ulonglong2(0ull, 0ull);
-              if (actB) *reinterpret_cast<ulonglong2*>(out_a + 4 * c4) = ob;
-            }
-            if (actA) *reinterpret_cast<ulonglong2*>(out_a) = oa;
-            out_a += static_cast<uint32_t>(P) * c4;
-          }
-        }
-      } else if (fast) {
-        // pooled crop (2x2 samples per output pixel), packed math, max / mean in the slow path's order (sy major)
-        for (int px0 = 0; px0 < P; px0 += 4) {
-          const int px = px0 + sub;
-          const bool act = px < P;
-          const int pxc = act ? px : 0;
-          const uint2 x0 = xrow[pxc * 2], x1 = xrow[pxc * 2 + 1];
-          const unsigned char* lo0 = band_q + (x0.x & 0xFFFFu);
-          const unsigned char* hi0 = band_q + (x0.x >> 16);
-          const unsigned char* lo1 = band_q + (x1.x & 0xFFFFu);
-          const unsigned char* hi1 = band_q + (x1.x >> 16);
-          const unsigned long long w0 = f2_splat(__uint_as_float(x0.y)), w1 = f2_splat(__uint_as_float(x1.y));
-          const bool ok0 = (xv >> (pxc * 2)) & 1ull, ok1 = (xv >> (pxc * 2 + 1)) & 1ull;
-          float4* out_px = out_c0 + (we.y + static_cast<uint32_t>(px) * c4);
-          for (int py = py_begin; py < py_end; ++py) {
-            ulonglong2 acc;
-#pragma unroll
-            for (int sy = 0; sy < 2; ++sy) {
-              const uint2 ye = yrow[py * 2 + sy];
-              const uint32_t ta = (ye.x & 0x3FFFu) << 4, tb = ((ye.x >> 16) & 0x3FFFu) << 4;
-              const unsigned long long wy2 = f2_splat(__uint_as_float(ye.y));
-              ulonglong2 v0 = lerp2_packed(*reinterpret_cast<const ulonglong2*>(lo0 + ta),
-                                           *reinterpret_cast<const ulonglong2*>(hi0 + ta),
-                                           *reinterpret_cast<const ulonglong2*>(lo0 + tb),
-                                           *reinterpret_cast<const ulonglong2*>(hi0 + tb), w0, wy2, nz2);
-              ulonglong2 v1 = lerp2_packed(*reinterpret_cast<const ulonglong2*>(lo1 + ta),
-                                           *reinterpret_cast<const ulonglong2*>(hi1 + ta),
-                                           *reinterpret_cast<const ulonglong2*>(lo1 + tb),
-                                           *reinterpret_cast<const ulonglong2*>(hi1 + tb), w1, wy2, nz2);
-              if (!ok0) v0 = make_ulonglong2(0ull, 0ull);
-              if (!ok1) v1 = make_ulonglong2(0ull, 0ull);
-              if (sy == 0) acc = v0; else acc = pool2<POOL>(acc, v0);
-              acc = pool2<POOL>(acc, v1);
-            }
-            if (POOL == BX_POOL_AVG2) {
-              const unsigned long long q4 = f2_splat(0.25f);   // x / 4 == x * 0.25 exactly (power of two)
-              acc.x = f2_mul(acc.x, q4, nz2);
-              acc.y = f2_mul(acc.y, q4, nz2);
-            }
-            if (act) *reinterpret_cast<ulonglong2*>(out_px) = acc;
-            out_px += static_cast<uint32_t>(P) * c4;
-          }
-        }
-      } else {
-        for (int px0 = 0; px0 < P; px0 += 4) {
-          const int px = px0 + sub;
-          const bool act = px < P;
-          const int pxc = act ? px : 0;
-          float4* out_px = out_c0 + (we.y + static_cast<uint32_t>(px) * c4);
-          uint32_t xlo[S], xhi[S];
-          float lx[S];
-          bool xok[S];
-#pragma unroll
-          for (int sx = 0; sx < S; ++sx) {
-            const uint2 xp = xrow[pxc * S + sx];
-            xlo[sx] = xp.x & 0xFFFFu;
-            xhi[sx] = xp.x >> 16;
-            lx[sx] = __uint_as_float(xp.y);
-            xok[sx] = (xv >> (pxc * S + sx)) & 1ull;
-          }
-          for (int py = py_begin; py < py_end; ++py) {
-            float4 acc;
-#pragma unroll
-            for (int sy = 0; sy < S; ++sy) {
-              const uint2 ye = yrow[py * S + sy];
-              const bool yok = ye.x >> 31;
-              const bool inb = (ye.x >> 15) & 1u;
-              const uint32_t ya = ye.x & 0x3FFFu, yb = (ye.x >> 16) & 0x3FFFu;
-#pragma unroll
-              for (int sx = 0; sx < S; ++sx) {
-                float4 tl, tr, bl, br;
-                if (inb) {
-                  const unsigned char* bt = band_q + (ya << 4);
-                  const unsigned char* bb = band_q + (yb << 4);
-                  tl = *reinterpret_cast<const float4*>(bt + xlo[sx]);
-                  tr = *reinterpret_cast<const float4*>(bt + xhi[sx]);
-                  bl = *reinterpret_cast<const float4*>(bb + xlo[sx]);
-                  br = *reinterpret_cast<const float4*>(bb + xhi[sx]);
-                } else {  // sample row of a pooled pair reaching past the staged band: read it from L2
-                  const float* gt = feat_img + (static_cast<size_t>(ya) * fw) * C + slice * kSlice + q * 4;
-                  const float* gb = feat_img + (static_cast<size_t>(yb) * fw) * C + slice * kSlice + q * 4;
-                  const size_t lo = xlo[sx] / (kSlice * 4), hi = xhi[sx] / (kSlice * 4);
-                  tl = __ldg(reinterpret_cast<const float4*>(gt + lo * C));
-                  tr = __ldg(reinterpret_cast<const float4*>(gt + hi * C));
-                  bl = __ldg(reinterpret_cast<const float4*>(gb + lo * C));
-                  br = __ldg(reinterpret_cast<const float4*>(gb + hi * C));
-                }
-                float4 v = lerp2(tl, tr, bl, br, lx[sx], __uint_as_float(ye.y));
-                if (!(yok && xok[sx])) v = make_float4(ev, ev, ev, ev);
-                pool_acc<POOL>(acc, v, sy == 0 && sx == 0);
-              }
-            }
-            if (POOL == BX_POOL_AVG2) acc = make_float4(acc.x / 4.0f, acc.y / 4.0f, acc.z / 4.0f, acc.w / 4.0f);
-            if (act) *out_px = acc;
-            out_px += static_cast<uint32_t>(P) * c4;
-          }
-        }
-      }
-    }
+    band_process_block<POOL, THREADS>(a, tab, smem, feat_img, slice, g_begin, tid);
   }
   if (a.dbg) {
     __syncthreads();
@@ -579,6 +598,108 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
       unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       a.dbg[blockIdx.x * 4 + 2] = t;
     }
+  }
+}
+
+// ---- persistent form: one 1024-thread CTA per SM loops over units (image, channel slice, band), heaviest bands first.
+// The per-unit kernel keeps two 512-thread CTAs on an SM so that one CTA's TMA wait overlaps the other's arithmetic, but
+// the %globaltimer timeline shows a CTA waiting 5.8 us for its band against 20.8 us of work, and the SM's two slots 90 %
+// occupied.  Here the band (and the first plan block) of the NEXT unit is copied into a second buffer while all 32 warps
+// work on the current one, so after the first unit nothing waits for TMA, and there is no wave quantisation: units are
+// drawn from a global counter (the first one is the CTA's index).  Arithmetic and results are unchanged.
+// MEASURED SLOWER than the per-unit kernel (see roi_band_launch): opt-in, kept for comparison.
+template <int POOL>
+__global__ void __launch_bounds__(1024, 1) roi_band_persist_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t band_bar[2], plan_bar[2];
+  __shared__ int s_next[2];
+  const RoiArgs& r = a.r;
+  const int fh = r.lv[0].fh, fw = r.lv[0].fw, C = r.c;
+  const uint32_t row_bytes = static_cast<uint32_t>(fw) * (kSlice * 4);
+  const uint32_t zrow_bytes = (row_bytes + 127u) & ~127u;
+  const PlanLayout L = plan_layout(a.cap, r.Q);
+  const int n_band_buf = a.band_stride ? 2 : 1;
+  unsigned char* tab0 = smem + (a.band_stride ? 2u * static_cast<uint32_t>(a.band_stride) : static_cast<uint32_t>(a.band_bytes) + zrow_bytes);
+  const int tid = threadIdx.x;
+  const int per_band = a.n_slices * r.b;
+  auto unit_of = [&](int u, int& band_i, int& slice, int& img) {
+    band_i = u / per_band;
+    const int v = u - band_i * per_band;
+    slice = v % a.n_slices;
+    img = v / a.n_slices;
+  };
+  auto issue_band = [&](int u, int buf) {       // thread 0: TMA boxes of unit u's band into band buffer `buf`
+    int band_i, slice, img;
+    unit_of(u, band_i, slice, img);
+    unsigned char* dst = smem + static_cast<size_t>(buf) * a.band_stride;
+    mbar_expect_tx(&band_bar[buf], static_cast<uint32_t>(a.band_bytes));
+    const int row0 = (img * fh + band_i * a.rows_per_band) * fw;
+    for (int bx = 0; bx < a.nbox; ++bx)
+      tma_load_2d(dst + static_cast<size_t>(bx) * a.box_rows * (kSlice * 4), &tmap, slice * kSlice, row0 + bx * a.box_rows, &band_bar[buf]);
+  };
+  auto plan_of = [&](int u) {
+    int band_i, slice, img;
+    unit_of(u, band_i, slice, img);
+    return a.plan + static_cast<size_t>(img * a.n_bands + band_i) * a.n_blocks_max * L.bytes;
+  };
+  auto issue_plan = [&](const unsigned char* src, uint32_t seq) {   // thread 0: one plan block into buffer seq & 1
+    mbar_expect_tx(&plan_bar[seq & 1u], L.bytes);
+    bulk_load(tab0 + (seq & 1u) * L.bytes, src, L.bytes, &plan_bar[seq & 1u]);
+  };
+
+  int u = blockIdx.x;                           // gridDim.x <= n_units
+  if (tid == 0) {
+    mbar_init(&band_bar[0], 1); mbar_init(&band_bar[1], 1);
+    mbar_init(&plan_bar[0], 1); mbar_init(&plan_bar[1], 1);
+    issue_band(u, 0);
+    asm volatile("griddepcontrol.wait;" ::: "memory");    // the plan kernel is complete: plan blocks and the unit counter are valid
+    issue_plan(plan_of(u), 0u);
+  }
+  // the all-zero row behind every band buffer
+  for (int bfi = 0; bfi < n_band_buf; ++bfi)
+    for (uint32_t i = tid * 16u; i < row_bytes; i += 1024u * 16u)
+      *reinterpret_cast<float4*>(smem + static_cast<size_t>(bfi) * a.band_stride + a.band_bytes + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+
+  uint32_t seq = 0;                             // plan blocks processed so far by this CTA (buffer = seq & 1)
+  for (int k = 0; u < a.n_units; ++k) {         // k-th unit of this CTA: band buffer k & 1 (0 when single-buffered)
+    const int bbuf = (n_band_buf == 2) ? (k & 1) : 0;
+    int band_i, slice, img;
+    unit_of(u, band_i, slice, img);
+    const float* feat_img = r.lv[0].feat + static_cast<size_t>(img) * fh * fw * C;
+    const unsigned char* plan0 = plan_of(u);
+    int g_begin = 0;
+    if (!a.scan_all && r.roi_counts) g_begin = img * r.rois_per_image;
+    // The next unit is drawn now and its band requested at once: the other band buffer is free, everybody is past the
+    // previous unit (the barrier that closes every unit, or the start-up barrier).  s_next is double-buffered by k: the
+    // slot written here is read behind the closing barrier of THIS unit and rewritten two units later.
+    if (tid == 0) {
+      const int nu = atomicAdd(a.unit_counter, 1) + static_cast<int>(gridDim.x);
+      s_next[k & 1] = nu;
+      if (n_band_buf == 2 && nu < a.n_units) issue_band(nu, bbuf ^ 1);
+    }
+    mbar_wait(&band_bar[bbuf], static_cast<uint32_t>(((n_band_buf == 2) ? (k >> 1) : k) & 1));
+    const unsigned char* band = smem + static_cast<size_t>(bbuf) * a.band_stride;
+    int n_blocks = 1;
+    for (int ch = 0; ch < n_blocks; ++ch, ++seq) {
+      const unsigned char* tab = tab0 + (seq & 1u) * L.bytes;
+      mbar_wait(&plan_bar[seq & 1u], (seq >> 1) & 1u);
+      if (ch == 0) n_blocks = reinterpret_cast<const int*>(tab)[1];
+      // prefetch the plan block that comes next in this CTA's sequence — the unit's next block, or block 0 of the next
+      // unit — into the other buffer, which block seq - 1 used: everyone is done with it (barrier below for ch >= 1, the
+      // closing barrier of the previous unit for ch == 0)
+      if (ch >= 1) __syncthreads();
+      if (tid == 0) {
+        const int nu = s_next[k & 1];           // thread 0's own write
+        if (ch + 1 < n_blocks) issue_plan(plan0 + static_cast<size_t>(ch + 1) * L.bytes, seq + 1u);
+        else if (nu < a.n_units) issue_plan(plan_of(nu), seq + 1u);
+      }
+      band_process_block<POOL, 1024>(a, tab, band, feat_img, slice, g_begin, tid);
+    }
+    __syncthreads();                            // closes the unit: its band buffer and last plan buffer are free, s_next is visible
+    const int nu = s_next[k & 1];
+    if (n_band_buf == 1 && tid == 0 && nu < a.n_units) issue_band(nu, 0);   // single band buffer: only now
+    u = nu;
   }
 }
 
@@ -668,6 +789,69 @@ bool make_band_cfg(int fh, int fw, int Q, int rois_range, size_t budget, BandCfg
   return c->smem <= budget;
 }
 
+// configuration of the persistent kernel: two plan buffers always (block 0 of the next unit is prefetched), two band
+// buffers when they fit (else one: wide maps), bands as tall as the room allows
+bool make_persist_cfg(int fh, int fw, int Q, int rois_range, size_t budget, BandCfg* c, int* band_stride) {
+  const size_t row_bytes = static_cast<size_t>(fw) * kSlice * 4;
+  const size_t zrow = (row_bytes + 127) & ~static_cast<size_t>(127);
+  int cap = rois_range < 112 ? rois_range : 112;
+  if (cap < 1) cap = 1;
+  while (cap > 32 && 2 * plan_layout(cap, Q).bytes > budget / 5) cap = (cap + 1) / 2;
+  const size_t tab = 2 * static_cast<size_t>(plan_layout(cap, Q).bytes);
+  if (budget < tab + zrow + 3 * row_bytes + 256) return false;
+  int bufs = 2;
+  long long room = (static_cast<long long>(budget) - static_cast<long long>(tab)) / 2 - static_cast<long long>(zrow) - 128;
+  if (room < static_cast<long long>(3 * row_bytes)) {
+    bufs = 1;
+    room = static_cast<long long>(budget) - static_cast<long long>(tab) - static_cast<long long>(zrow) - 128;
+    if (room < static_cast<long long>(3 * row_bytes)) return false;
+  }
+  int max_rows_loaded = static_cast<int>(room / static_cast<long long>(row_bytes));
+  if (max_rows_loaded > fh) max_rows_loaded = fh;
+  int rows_per_band = (max_rows_loaded >= fh) ? fh : max_rows_loaded - 1;
+  const int n_bands = (fh + rows_per_band - 1) / rows_per_band;
+  rows_per_band = (fh + n_bands - 1) / n_bands;
+  const int rows_loaded = (rows_per_band + 1 < fh) ? rows_per_band + 1 : fh;
+  const int px = rows_loaded * fw;
+  const int nbox = (px + kBoxRows - 1) / kBoxRows;
+  const int box_rows = (px + nbox - 1) / nbox;
+  c->rows_per_band = rows_per_band;
+  c->n_bands = n_bands;
+  c->nbox = nbox;
+  c->box_rows = box_rows;
+  c->band_bytes = nbox * box_rows * kSlice * 4;
+  c->cap = cap;
+  c->n_blocks_max = (rois_range + cap - 1) / cap;
+  if (c->n_blocks_max > kPlanMaxBlocks) return false;
+  if (static_cast<size_t>(c->band_bytes) + zrow > (1u << 18)) return false;        // 14-bit row offsets in 16 B units
+  if (static_cast<size_t>(c->band_bytes) >= (1u << 20)) return false;               // mbarrier tx-count limit
+  const size_t stride = (static_cast<size_t>(c->band_bytes) + zrow + 127) & ~static_cast<size_t>(127);
+  *band_stride = bufs == 2 ? static_cast<int>(stride) : 0;
+  c->smem = (bufs == 2 ? 2 * stride : static_cast<size_t>(c->band_bytes) + zrow) + tab;
+  return c->smem <= budget;
+}
+
+template <int POOL>
+int launch_band_persist(bx_handle* h, const BandArgs& a, const CUtensorMap& tmap, size_t smem, int grid, cudaStream_t st) {
+  constexpr int S = (POOL == BX_POOL_NONE) ? 1 : 2;
+  roi_plan_kernel<S><<<a.r.b * a.n_bands, kPlanThreads, 0, st>>>(a);
+  BX_LAUNCH_CHECK(h);
+  BX_CUDA(cudaFuncSetAttribute(roi_band_persist_kernel<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BX_CUDA(cudaLaunchKernelEx(&cfg, roi_band_persist_kernel<POOL>, tmap, a));
+  BX_LAUNCH_CHECK(h);
+  return BX_OK;
+}
+
 }  // namespace
 
 int roi_band_launch(bx_handle* h, const RoiArgs& ra, int pool, cudaStream_t st, int* used) {
@@ -686,8 +870,16 @@ int roi_band_launch(bx_handle* h, const RoiArgs& ra, int pool, cudaStream_t st, 
   // shared memory, else one 1024-thread CTA per SM
   BandCfg cfg;
   int threads = 512;
+  // persistent kernel: opt-in (BX_ROI_BAND_PERSIST=1, read per call).  Measured SLOWER than the per-unit kernel at cfg2 —
+  // 0.145 vs 0.133 ms alone, 0.1246 vs 0.1062 ms pipelined: with all 32 warps of the SM on one unit every plan-block and
+  // unit barrier waits for the slowest warp, which two independent 16-warp CTAs hide from each other; reserving 4 / 8 SMs for
+  // the proposal kernels of other steps gives 1 % back (profiles/README.md).  Kept as a second implementation the tests compare.
+  const char* persist_s = getenv("BX_ROI_BAND_PERSIST");
+  int band_stride = 0;
+  bool persist = (persist_s && atoi(persist_s) != 0) && !getenv("BX_BAND_DEBUG") &&
+                 make_persist_cfg(fh, fw, ra.Q, rois_range, h->smem_optin - 1024, &cfg, &band_stride);
   const char* force1 = getenv("BX_ROI_ONE_CTA");
-  if (force1 || !make_band_cfg(fh, fw, ra.Q, rois_range, (h->smem_sm - 2 * 1024) / 2 - 64, &cfg)) {
+  if (!persist && (force1 || !make_band_cfg(fh, fw, ra.Q, rois_range, (h->smem_sm - 2 * 1024) / 2 - 64, &cfg))) {
     threads = 1024;
     if (!make_band_cfg(fh, fw, ra.Q, rois_range, h->smem_optin - 1024, &cfg)) return BX_OK;
   }
@@ -703,7 +895,8 @@ int roi_band_launch(bx_handle* h, const RoiArgs& ra, int pool, cudaStream_t st, 
   BX_REQUIRE(cr == CUDA_SUCCESS, BX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
   const size_t plan_bytes = static_cast<size_t>(ra.b) * cfg.n_bands * cfg.n_blocks_max * plan_layout(cfg.cap, ra.Q).bytes;
-  int rc = bx_plan_reserve(h, plan_bytes, st);
+  const size_t counter_off = (plan_bytes + 255) & ~static_cast<size_t>(255);
+  int rc = bx_plan_reserve(h, counter_off + 256, st);
   if (rc) return rc;
 
   BandArgs a;
@@ -720,12 +913,30 @@ int roi_band_launch(bx_handle* h, const RoiArgs& ra, int pool, cudaStream_t st, 
   a.plan = static_cast<unsigned char*>(h->plan);
   a.neg_zero = -0.0f;
   a.dbg = nullptr;
+  a.unit_counter = persist ? reinterpret_cast<int*>(a.plan + counter_off) : nullptr;
+  a.n_units = ra.b * a.n_slices * a.n_bands;
+  a.band_stride = band_stride;
+  if (persist) {
+    // grid: one CTA per SM; BX_ROI_BAND_RESERVE leaves SMs to the small kernels of other steps (proposal / plan kernels)
+    const char* res_s = getenv("BX_ROI_BAND_RESERVE");
+    int grid = h->num_sms - (res_s ? atoi(res_s) : 0);
+    if (grid < 1) grid = 1;
+    if (grid > a.n_units) grid = a.n_units;
+    if (pool == BX_POOL_NONE) rc = launch_band_persist<BX_POOL_NONE>(h, a, tmap, cfg.smem, grid, st);
+    else if (pool == BX_POOL_MAX2) rc = launch_band_persist<BX_POOL_MAX2>(h, a, tmap, cfg.smem, grid, st);
+    else rc = launch_band_persist<BX_POOL_AVG2>(h, a, tmap, cfg.smem, grid, st);
+    if (rc == BX_OK) {
+      *used = 1;
+      h->band_launches++;
+    }
+    return rc;
+  }
   if (getenv("BX_BAND_DEBUG")) {   // measurement aid: per-CTA timestamps appended to the plan buffer, dumped by the caller
     const size_t grid = static_cast<size_t>(ra.b) * a.n_slices * a.n_bands;
-    rc = bx_plan_reserve(h, plan_bytes + 256 + grid * 32, st);
+    rc = bx_plan_reserve(h, counter_off + 512 + grid * 32, st);
     if (rc) return rc;
     a.plan = static_cast<unsigned char*>(h->plan);
-    a.dbg = reinterpret_cast<unsigned long long*>(a.plan + ((plan_bytes + 255) & ~static_cast<size_t>(255)));
+    a.dbg = reinterpret_cast<unsigned long long*>(a.plan + counter_off + 256);
     h->dbg_ptr = a.dbg;
     h->dbg_count = static_cast<long long>(grid);
     h->dbg_info[0] = a.n_bands; h->dbg_info[1] = a.n_slices; h->dbg_info[2] = threads; h->dbg_info[3] = (int)cfg.smem;
