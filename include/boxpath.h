@@ -148,8 +148,11 @@ int bx_proposals_rpn(bx_handle* h, const float* anchors, const float* deltas, co
 /* ---- f3 ("next" row): gradient of bx_roi_pool w.r.t. the feature map, i.e. the backward pass TF runs through
  *      tf.image.crop_and_resize (+ the 2x2 pool) when scripts/train.py:99-103 differentiates the model (the boxes are
  *      under tf.stop_gradient, model/roi_pooling.py:37,79,86).  Same arguments as bx_roi_pool; grad_out [r,P,P,c];
- *      grad_feat [b,fh,fw,c] is zeroed by the call, then accumulated with fp32 atomics (summation order, hence the
- *      last bits, vary from run to run).  feat is read only for BX_POOL_MAX2 (argmax).  c must be a multiple of 4. */
+ *      grad_feat [b,fh,fw,c] is written completely by the call.  feat is read only for BX_POOL_MAX2 (argmax).  c must
+ *      be a multiple of 4.  Two kernels: a row-owned one without atomics — every pixel's sum has one
+ *      fixed order, the result is bit-reproducible — which is the default for BX_POOL_NONE and BX_POOL_AVG2, and a
+ *      scatter kernel with fp32 atomics (last bits vary from run to run), the default for BX_POOL_MAX2 where it is the
+ *      faster one.  bx_set_deterministic(h, 1) selects the row-owned kernel for every mode. */
 int bx_roi_pool_grad(bx_handle* h, int mode, int pool, int pool_size, const float* feat, int b, int fh, int fw, int c,
                      const float* rois, const int* box_ind, const int* roi_counts, int r, float stride, int image_h,
                      int image_w, const float* grad_out, float* grad_feat, void* stream);
@@ -294,6 +297,10 @@ int bx_c4_proposal_roi_host(bx_handle* h, const float* anchors_dev, const float*
  *      `stream`. */
 int bx_allgather_detections(bx_handle* h, void* nccl_comm, const float* records, const int* counts, int b_local,
                             int kmax, int fields, int world, float* out_records, int* out_counts, void* stream);
+
+/* on != 0: calls on this handle use bit-reproducible kernels where the default one is not (today: bx_roi_pool_grad with
+ * BX_POOL_MAX2).  The Python mirror sets it from torch.are_deterministic_algorithms_enabled(). */
+int bx_set_deterministic(bx_handle* h, int on);
 
 /* number of kernels launched by this handle since creation (bench.py "gpu_launches") */
 long long bx_launch_count(const bx_handle* h);

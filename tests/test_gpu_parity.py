@@ -1263,3 +1263,76 @@ def test_persistent_band_kernel_matches_default(bx, monkeypatch):
     monkeypatch.setenv('BX_ROI_BAND_POOLED', '1')
     pooled = bx.roi_pool(_lib.ROI_STRIDE_NORM, _lib.POOL_MAX2, 7, feat[:1], cu(rois[0]), stride=16.0)
     assert np.array_equal(pooled.cpu().numpy(), orc.roi_pool_c4(feat[:1].cpu().numpy(), rois[0], 16, 7, True))
+
+
+@pytest.mark.parametrize('case', ['plain7', 'plain10_wide', 'max5', 'avg7_pad', 'counts_c96'])
+def test_roi_pool_backward_row_owned_kernel(bx, monkeypatch, case):
+    """The row-owned, atomic-free backward kernel (csrc/bx_roi_grad.cu; BX_ROI_GRAD_DETERMINISTIC=1 or
+    bx_set_deterministic): same gradients as the oracle within the fp32 tolerance, identical bits run to run, with the warps
+    of a CTA on different channel slices (SPLIT=0) and on one slice (SPLIT=1), for every extractor, pooled sizes with one and
+    two chunks of output pixels, a map wider than one 64-pixel segment, channel counts below / not a multiple of a slice,
+    and padded rois behind roi_counts.  The scatter kernel (BX_ROI_GRAD_ATOMIC=1) must agree within the same tolerance."""
+    from tf_eager_object_detection_b200 import _lib
+    rng = np.random.default_rng(hash(case) % 1000)
+    kw = {}
+    if case == 'plain7':
+        feat = rng.standard_normal((2, 38, 63, 64), dtype=np.float32); P = 7; pool = _lib.POOL_NONE; mode = _lib.ROI_STRIDE_NORM
+        rois = syn.random_rois(rng, 90, (600, 1000)); bi = rng.integers(0, 2, 90).astype(np.int32)
+        ref = orc.roi_pool_c4_grad
+        args = lambda rr, g: (feat, rr, 16, g, P, False)
+        kw = dict(stride=16.0)
+    elif case == 'plain10_wide':
+        feat = rng.standard_normal((1, 20, 150, 8), dtype=np.float32); P = 10; pool = _lib.POOL_NONE; mode = _lib.ROI_STRIDE_NORM
+        rois = syn.random_rois(rng, 70, (80, 600)); bi = np.zeros(70, np.int32)
+        ref = orc.roi_pool_c4_grad
+        args = lambda rr, g: (feat, rr, 4, g, P, False)
+        kw = dict(stride=4.0)
+    elif case == 'max5':
+        feat = rng.standard_normal((2, 25, 38, 32), dtype=np.float32); P = 5; pool = _lib.POOL_MAX2; mode = _lib.ROI_STRIDE_NORM
+        rois = syn.random_rois(rng, 60, (400, 608)); bi = rng.integers(0, 2, 60).astype(np.int32)
+        ref = orc.roi_pool_c4_grad
+        args = lambda rr, g: (feat, rr, 16, g, P, True)
+        kw = dict(stride=16.0)
+    elif case == 'avg7_pad':
+        feat = rng.standard_normal((2, 25, 38, 32), dtype=np.float32); P = 7; pool = _lib.POOL_AVG2; mode = _lib.ROI_ALIGN_PAD
+        rois = syn.random_rois(rng, 60, (400, 608)); bi = rng.integers(0, 2, 60).astype(np.int32)
+        ref = orc.roi_align_pad_grad
+        args = lambda rr, g: (feat, rr, 16, g, P)
+        kw = dict(stride=16.0)
+    else:
+        feat = rng.standard_normal((3, 38, 63, 96), dtype=np.float32); P = 7; pool = _lib.POOL_NONE; mode = _lib.ROI_STRIDE_NORM
+        rois = np.stack([syn.random_rois(rng, 40, (600, 1000)) for _ in range(3)]).reshape(-1, 4)
+        counts = np.int32([40, 0, 17])
+        bi = np.repeat(np.arange(3, dtype=np.int32), 40)
+        bi[40:80] = -1; bi[80 + 17:] = -1                            # rois behind the counts: left out of the oracle's input below
+        ref = orc.roi_pool_c4_grad
+        args = lambda rr, g: (feat, rr, 16, g, P, False)
+        kw = dict(stride=16.0, roi_counts=cu(counts))
+    g = rng.standard_normal((rois.shape[0], P, P, feat.shape[3]), dtype=np.float32)
+    keep = bi >= 0
+    want = ref(*args(rois[keep], g[keep]), box_ind=bi[keep])
+    scale = np.abs(want).max()
+    if 'roi_counts' not in kw:
+        kw['box_ind'] = cu(bi)
+    call = lambda: bx.roi_pool_grad(mode, pool, P, cu(feat), cu(rois), cu(g), **kw)
+    monkeypatch.setenv('BX_ROI_GRAD_ATOMIC', '1')
+    close(call().cpu().numpy(), want, scale=scale)
+    monkeypatch.setenv('BX_ROI_GRAD_ATOMIC', '0')
+    monkeypatch.setenv('BX_ROI_GRAD_DETERMINISTIC', '1')
+    for split in ('0', '1'):
+        monkeypatch.setenv('BX_ROI_GRAD_SPLIT', split)
+        a1, a2 = call(), call()
+        assert torch.equal(a1, a2)
+        close(a1.cpu().numpy(), want, scale=scale)
+    monkeypatch.delenv('BX_ROI_GRAD_SPLIT')
+    monkeypatch.delenv('BX_ROI_GRAD_DETERMINISTIC')
+    # torch's switch reaches the handle (bx_set_deterministic): the 2x2 max, whose default is the scatter kernel, becomes
+    # reproducible too
+    before = torch.are_deterministic_algorithms_enabled()
+    torch.use_deterministic_algorithms(True)
+    try:
+        b1, b2 = call(), call()
+    finally:
+        torch.use_deterministic_algorithms(before)
+    assert torch.equal(b1, b2)
+    close(b1.cpu().numpy(), want, scale=scale)

@@ -48,6 +48,7 @@ SIGNATURES = {
     'bx_destroy': (c_int, [c_void_p]),
     'bx_launch_count': (c_longlong, [c_void_p]),
     'bx_stats': (c_int, [c_void_p, POINTER(c_longlong), c_int]),
+    'bx_set_deterministic': (c_int, [c_void_p, c_int]),
     'bx_reserve': (c_int, [c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, c_void_p]),
     'bx_profile_roi': (c_int, [c_void_p, c_int, c_int]),
     'bx_profile_read': (c_int, [c_void_p, POINTER(c_float), c_int, POINTER(c_int)]),

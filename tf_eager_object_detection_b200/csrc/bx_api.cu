@@ -124,6 +124,12 @@ extern "C" int bx_stats(const bx_handle* h, long long* out, int n) {
   return BX_OK;
 }
 
+extern "C" int bx_set_deterministic(bx_handle* h, int on) {
+  BX_REQUIRE(h, BX_ERR_INVALID, "bx_set_deterministic: NULL handle");
+  h->deterministic = on != 0;
+  return BX_OK;
+}
+
 extern "C" long long bx_launch_count(const bx_handle* h) { return h ? h->launches : 0; }
 
 // measurement aid (not in the public header): copy the BX_BAND_DEBUG timestamps of the last band launch to the host

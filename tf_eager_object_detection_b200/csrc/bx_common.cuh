@@ -28,6 +28,7 @@ struct bx_handle {
   long long band_fallbacks;      // ... and plain-crop launches that fell back to a gather kernel (bx_stats)
   cudaStream_t last_stream;      // stream of the handle's latest call (orders workspace frees, bx_destroy)
   int last_stream_valid;
+  int deterministic;             // bx_set_deterministic: bit-reproducible kernels where the default is not (bx_roi_pool_grad)
   // optional event bracketing of the RoI-pooling kernel (bx_profile_roi)
   cudaEvent_t* prof_ev;   // 2 * prof_cap events
   int prof_cap;

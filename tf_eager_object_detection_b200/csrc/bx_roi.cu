@@ -341,13 +341,9 @@ __global__ void __launch_bounds__(256, BX_POOL2_CTAS) roi_pool2_kernel(const Roi
 //      (TF CropAndResizeGradImage: each sample scatters (1-ly)(1-lx), (1-ly)lx, ly(1-lx), ly lx times its gradient to its 4
 //      taps) composed with the gradient of the 2x2 pool (max: all of it to the first maximal sample of the window in
 //      row-major order, as TF's MaxPoolGrad; avg: a quarter to each).  The boxes get no gradient (tf.stop_gradient,
-//      roi_pooling.py:37,79,86).  One CTA per (roi, py); fp32 atomics (red.global.add.v4.f32).
-struct RoiGradArgs {
-  RoiArgs a;              // forward description; a.out is unused
-  const float* grad_out;  // [r,P,P,c]
-  float* grad_feat;       // [b,fh,fw,c], pre-zeroed
-};
-
+//      roi_pooling.py:37,79,86).  One CTA per (roi, py); fp32 atomics (red.global.add.v4.f32).  This scatter form is the
+//      fallback (crops wider than 32 samples) and the A/B partner (BX_ROI_GRAD_ATOMIC=1) of the row-owned, atomic-free
+//      kernel in bx_roi_grad.cu, which bx_roi_pool_grad uses by default.
 template <int POOL>
 __global__ void __launch_bounds__(256) roi_pool_grad_kernel(const RoiGradArgs g) {
   constexpr int S = (POOL == BX_POOL_NONE) ? 1 : 2;
@@ -692,8 +688,11 @@ extern "C" int bx_roi_pool_grad(bx_handle* h, int mode, int pool, int pool_size,
   BX_REQUIRE(c % 4 == 0 && bx_aligned(grad_feat, 16) && bx_aligned(grad_out, 16) && bx_aligned(feat, 16),
              BX_ERR_UNSUPPORTED, "bx_roi_pool_grad: channels must be a multiple of 4 and tensors 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  BX_CUDA(cudaMemsetAsync(grad_feat, 0, sizeof(float) * static_cast<size_t>(b) * fh * fw * c, st));
-  if (r == 0) return BX_OK;
+  const size_t feat_bytes = sizeof(float) * static_cast<size_t>(b) * fh * fw * c;
+  if (r == 0) {
+    BX_CUDA(cudaMemsetAsync(grad_feat, 0, feat_bytes, st));
+    return BX_OK;
+  }
   RoiGradArgs g = {};
   g.a.lv[0] = {feat, fh, fw};
   g.a.n_levels = 1;
@@ -711,6 +710,10 @@ extern "C" int bx_roi_pool_grad(bx_handle* h, int mode, int pool, int pool_size,
   g.a.extrapolation = 0.0f;
   g.grad_out = grad_out;
   g.grad_feat = grad_feat;
+  int used = 0;
+  if (int rc2 = roi_grad_rows_launch(h, g, pool, st, &used)) return rc2;   // row-owned kernel: writes every element itself
+  if (used) return BX_OK;
+  BX_CUDA(cudaMemsetAsync(grad_feat, 0, feat_bytes, st));
   const int grid = r * pool_size;
   if (pool == BX_POOL_NONE) roi_pool_grad_kernel<BX_POOL_NONE><<<grid, 256, 0, st>>>(g);
   else if (pool == BX_POOL_MAX2) roi_pool_grad_kernel<BX_POOL_MAX2><<<grid, 256, 0, st>>>(g);

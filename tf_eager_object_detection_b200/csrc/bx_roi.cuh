@@ -33,6 +33,12 @@ struct RoiArgs {
   float* out;             // [r,P,P,c]
 };
 
+struct RoiGradArgs {
+  RoiArgs a;              // forward description; a.out is unused
+  const float* grad_out;  // [r,P,P,c]
+  float* grad_feat;       // [b,fh,fw,c]
+};
+
 struct Axis {
   int lo, hi;   // tap indices (already mapped to the un-padded map)
   float lerp;
@@ -148,5 +154,8 @@ __device__ __forceinline__ ulonglong2 pool2(const ulonglong2 a, const ulonglong2
 int roi_band_launch(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st, int* used);
 // implemented in bx_roi_stage.cu: pooled crops with the roi footprint staged in shared memory by TMA
 int roi_stage_launch(bx_handle* h, const RoiArgs& a, int pool, cudaStream_t st, int* used);
+
+// implemented in bx_roi_grad.cu: row-owned, atomic-free backward; *used = 0 -> the caller runs the scatter kernel
+int roi_grad_rows_launch(bx_handle* h, const RoiGradArgs& g, int pool, cudaStream_t st, int* used);
 
 }  // namespace bxroi

@@ -227,7 +227,8 @@ def roi_pool(mode, pool, pool_size, feat, rois, stride=16.0, image_shape=(0, 0),
 
 def roi_pool_grad(mode, pool, pool_size, feat, rois, grad_out, stride=16.0, image_shape=(0, 0), box_ind=None,
                   roi_counts=None):
-    """f3: gradient of roi_pool w.r.t. feat: grad_out [r,P,P,c] -> grad_feat [b,fh,fw,c]."""
+    """f3: gradient of roi_pool w.r.t. feat: grad_out [r,P,P,c] -> grad_feat [b,fh,fw,c].  Under
+    torch.use_deterministic_algorithms(True) every mode runs on the row-owned, atomic-free kernel (bit-reproducible)."""
     feat = to_device(feat, f32)
     rois = to_device(rois, f32, feat.device).reshape(-1, 4)
     grad_out = to_device(grad_out, f32, feat.device)
@@ -235,6 +236,7 @@ def roi_pool_grad(mode, pool, pool_size, feat, rois, grad_out, stride=16.0, imag
     r = rois.shape[0]
     dev, h, bw, st, lib = _ctx(feat)
     gf = empty((b, fh, fw, c), f32, dev)
+    _lib.check(lib.bx_set_deterministic(h, int(torch.are_deterministic_algorithms_enabled())))
     bi = bw.ptr(to_device(box_ind, i32, feat.device), INT32, (r,)) if (box_ind is not None and r) else None
     rc = bw.ptr(to_device(roi_counts, i32, feat.device), INT32, (b,)) if roi_counts is not None else None
     _lib.check(lib.bx_roi_pool_grad(h, mode, pool, int(pool_size), bw.ptr(feat, FLOAT32, (b, fh, fw, c), 16), b, fh, fw, c,
