@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """bench.py — proposal + NMS + RoI pooling throughput (BASELINE.json metric) on N B200s, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workloads all|none|cfg3,cfg5,cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workloads all|none|cfg3,cfg5,cfg4,f3]
 
 A "step" = one pass of the hot path over one batch of synthetic images.  Headline workload: cfg2 of BASELINE.json
 (ResNet-50 C4, 600x1000, 21 546 anchors, pre-NMS 6000 -> post-NMS 300, crop 7x7x1024, batch 8 per GPU).  Prints ONE JSON
 line (rank 0): device-resident `value`, host-buffer `e2e`, `roofline` of the dominant kernel (RoI pooling) measured in
 the same regime as `value`, `regimes` (pipelined / single stream, structured), `cpu_baseline` (oracle C twin on the host
-cores), clocks, and `workloads` — the FPN configurations cfg3 / cfg5 and the training-target configuration cfg4 measured
-in the same run.  `--impl reference` times the CPU restatement of the reference path instead.
+cores), clocks, and `workloads` — the FPN configurations cfg3 / cfg5, the training-target configuration cfg4 and the
+RoI-pooling backward pass (f3) measured in the same run.  `--impl reference` times the CPU restatement of the reference path instead.
 
 How the timed region is issued: the K steps are captured ONCE into a CUDA graph (steps dealt round-robin over S streams,
 fork/join inside the graph; at N > 1 the all-gather of the per-image detection records runs on its own branch of the
@@ -889,10 +889,66 @@ def bench_targets(ctx, args):
     return out
 
 
+def bench_backward(ctx, args):
+    """f3: gradient of the cfg2 RoI extractor w.r.t. the feature map (what scripts/train.py:99-103 back-propagates through
+    tf.image.crop_and_resize), 8 images x 300 rois per GPU and step, grad_out [2400,7,7,1024] -> grad_feat [8,38,63,1024].
+    One stream (a call fills the device); the default kernel at this shape is the row-owned, atomic-free one, the scatter
+    kernel (BX_ROI_GRAD_ATOMIC=1, read per call) is timed beside it."""
+    torch, lib, _lib = ctx.torch, ctx.lib, ctx._lib
+    name = ('f3: RoI-pooling backward at the cfg2 shape, 8 images x 300 rois per GPU and step, grad_out [2400,7,7,1024] -> '
+            'grad_feat [8,38,63,1024] (ResNet-101 C4 map of 600x1000), one stream')
+    B, R, P, C, fh, fw = 8, 300, 7, 1024, 38, 63
+    K, W = max(3, min(args.steps, args.workload_steps)), 3
+    dev = ctx.dev
+    rng = np.random.default_rng(syn.seed_for(2, 700 + ctx.rank))
+    rois = torch.as_tensor(np.stack([syn.random_rois(rng, R, (600, 1000)) for _ in range(B)]).reshape(-1, 4)).to(dev)
+    counts = torch.full((B,), R, dtype=torch.int32, device=dev)
+    go = [torch.randn((B * R, P, P, C), device=dev) for _ in range(2)]          # 2 x 481 MB, alternated: inputs larger than L2
+    gf = torch.empty((B, fh, fw, C), device=dev)
+    pipe = None
+
+    def launch(step, pos, si):
+        _lib.check(lib.bx_roi_pool_grad(pipe.handles[si], _lib.ROI_STRIDE_NORM, _lib.POOL_NONE, P, None, B, fh, fw, C,
+                                        rois.data_ptr(), None, counts.data_ptr(), B * R, 16.0, 0, 0, go[step & 1].data_ptr(),
+                                        gf.data_ptr(), ctypes.c_void_p(pipe.streams[si].cuda_stream)))
+
+    pipe = Pipeline(ctx, 1, launch)
+    res = {}
+    for tag, env in (('row_owned', '0'), ('scatter', '1')):
+        os.environ['BX_ROI_GRAD_ATOMIC'] = env
+        pipe.timed(1, 0)
+        pipe.timed(W, 0, key=('warm', tag))
+        ms = pipe.timed(K, W, key=('timed', tag))
+        res[tag], ranks = ctx.max_over_ranks(ms)
+        if tag == 'row_owned':
+            ms_ranks = ranks
+            first = gf.clone()
+            pipe.timed(1, W + K - 1)
+            assert torch.equal(first, gf), 'row-owned backward kernel: two runs differ'
+    os.environ.pop('BX_ROI_GRAD_ATOMIC', None)
+    out = None
+    if ctx.rank == 0:
+        peak, _ = hbm_peak()
+        alg = 4 * (B * R * P * P * C + B * fh * fw * C)
+        ms = res['row_owned'] / K
+        out = dict(workload=name, scaling='weak', images_per_step_per_gpu=B, steps=K, warmup=W, streams=1,
+                   ms_per_step=round(ms, 5), images_per_s=round(ctx.world * B / (ms * 1e-3), 1),
+                   scatter_kernel_ms_per_step=round(res['scatter'] / K, 5), bit_reproducible=True,
+                   roofline=dict(bound='hbm', kernel='roi_grad_rows_kernel<NONE, 2, 4, 7, false> (1 launch per step)',
+                                 avg_launch_ms=round(ms, 5), algorithmic_bytes_per_launch=alg,
+                                 achieved=round(alg / (ms * 1e-3) / 1e9, 1), peak=peak, unit='GB/s',
+                                 frac=round(alg / (ms * 1e-3) / 1e9 / peak, 4)),
+                   ms_per_rank=ms_ranks)
+    pipe.close()
+    del go, gf
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     ctx = Ctx(args)
     line = bench_c4(ctx, args)
-    names = ['cfg3', 'cfg5', 'cfg4'] if args.workloads == 'all' else [s for s in args.workloads.split(',') if s and s != 'none']
+    names = ['cfg3', 'cfg5', 'cfg4', 'f3'] if args.workloads == 'all' else [s for s in args.workloads.split(',') if s and s != 'none']
     extra = {}
 
     def give_up():
@@ -909,7 +965,7 @@ def run_ours(args):
         watchdog.start()
     for nm in names:
         try:
-            extra[nm] = bench_targets(ctx, args) if nm == 'cfg4' else bench_fpn(ctx, args, nm)
+            extra[nm] = bench_targets(ctx, args) if nm == 'cfg4' else bench_backward(ctx, args) if nm == 'f3' else bench_fpn(ctx, args, nm)
         except Exception as e:                               # a secondary workload never takes the headline line down
             extra[nm] = dict(error='%s: %s' % (type(e).__name__, str(e)[:300]))
             ctx.torch.cuda.synchronize()
@@ -933,7 +989,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=20)
     ap.add_argument('--gather-every', type=int, default=0,
                     help='N > 1: detection records of this many consecutive steps are all-gathered together (0: all K, one gather at the end of the region)')
-    ap.add_argument('--workloads', default='all', help='all | none | comma list of cfg3,cfg5,cfg4 (measured after the headline)')
+    ap.add_argument('--workloads', default='all', help='all | none | comma list of cfg3,cfg5,cfg4,f3 (measured after the headline)')
     ap.add_argument('--workload-steps', type=int, default=100, help='cap on the steps of the extra workloads')
     ap.add_argument('--workload-timeout', type=int, default=240, help='seconds after which the extra workloads are abandoned')
     ap.add_argument('--batch-override', type=int, default=0, help='experiments: images per GPU and step of the FPN workloads')
