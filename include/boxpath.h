@@ -20,6 +20,8 @@
  *    concurrent streams.
  *  - boxes are (x1, y1, x2, y2) in image pixels, as everywhere on the reference's path.
  *  - no CPU fallback: without a CUDA device bx_create fails and nothing else can be called.
+ *  - BX_NVTX=1 in the environment (read once): every entry point that takes a handle runs inside an NVTX push/pop range
+ *    named after it, so `ncu --nvtx --nvtx-include "bx_roi_pool/"` or a timeline tool attributes kernels to calls.
  */
 #ifndef BOXPATH_H_
 #define BOXPATH_H_

@@ -70,6 +70,24 @@ def test_no_cpu_fallback():
         ops.pairwise_iou(np.zeros((2, 4), np.float32), np.zeros((2, 4), np.float32))
 
 
+def test_nvtx_ranges_are_optional_and_harmless_without_a_profiler():
+    """BX_NVTX=1 brackets every entry point with an NVTX range (header-only nvtx3: resolves its injection library
+    lazily, a no-op when no tool is attached).  No GPU needed: an argument error path runs through the guard."""
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip('libboxpath.so not built')
+    import subprocess, sys
+    code = ('from tf_eager_object_detection_b200 import _lib\n'
+            'lib = _lib.load()\n'
+            'for _ in range(3):\n'
+            '    assert lib.bx_stats(None, None, 0) == -1\n'
+            '    assert lib.bx_reserve(None, 0, 0, 0, None) != 0\n'
+            'print(lib.bx_last_error().decode())\n')
+    env = dict(os.environ, BX_NVTX='1', PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert 'NULL' in out.stdout
+
+
 def test_product_package_never_imports_the_oracle():
     pkg = os.path.join(ROOT, 'tf_eager_object_detection_b200')
     for dirpath, _, files in os.walk(pkg):

@@ -1,6 +1,9 @@
 // Handle, error reporting, workspace, DLPack validation and the composite C4 entry points of libboxpath.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "bx_common.cuh"
 #include "bx_dlpack.h"
@@ -49,7 +52,16 @@ int bx_ws_reserve(bx_handle* h, size_t bytes, cudaStream_t st) { return reserve(
 int bx_stage_reserve(bx_handle* h, size_t bytes, cudaStream_t st) { return reserve(h, &h->stage, &h->stage_bytes, bytes, st); }
 int bx_plan_reserve(bx_handle* h, size_t bytes, cudaStream_t st) { return reserve(h, &h->plan, &h->plan_bytes, bytes, st); }
 
-BxEnter::BxEnter(bx_handle* h, void* stream) : prev_(-1) {
+static bool nvtx_enabled() {
+  static const bool on = getenv("BX_NVTX") && atoi(getenv("BX_NVTX")) != 0;   // read once: ranges must pair up
+  return on;
+}
+
+BxEnter::BxEnter(bx_handle* h, void* stream, const char* fn) : prev_(-1), nvtx_(false) {
+  if (nvtx_enabled()) {
+    nvtxRangePushA(fn);
+    nvtx_ = true;
+  }
   if (!h) return;
   int cur = -1;
   if (cudaGetDevice(&cur) == cudaSuccess && cur != h->device) {
@@ -60,6 +72,7 @@ BxEnter::BxEnter(bx_handle* h, void* stream) : prev_(-1) {
 }
 BxEnter::~BxEnter() {
   if (prev_ >= 0) cudaSetDevice(prev_);
+  if (nvtx_) nvtxRangePop();
 }
 
 extern "C" int bx_version(void) { return BX_VERSION; }

@@ -46,11 +46,15 @@ int bx_plan_reserve(bx_handle* h, size_t bytes, cudaStream_t st);
 // call (kernels, memsets and allocations land on h->device whatever the caller's current device is) and restores the
 // caller's device on return; remembers the stream for stream-ordered workspace retirement.  NULL handle: no-op.
 struct BxEnter {
-  BxEnter(bx_handle* h, void* stream);
+  // `fn` = the entry point's name (the default argument is evaluated at the call site): with BX_NVTX=1 in the environment
+  // the call is bracketed by an NVTX range of that name, so ncu --nvtx --nvtx-include "bx_roi_pool/" (or an nsys timeline)
+  // attributes kernels to the C-ABI call that launched them.
+  BxEnter(bx_handle* h, void* stream, const char* fn = __builtin_FUNCTION());
   ~BxEnter();
   BxEnter(const BxEnter&) = delete;
   BxEnter& operator=(const BxEnter&) = delete;
   int prev_;
+  bool nvtx_;
 };
 int bx_internal_nms_keys(bx_handle* h, const float* boxes, const uint32_t* keys, int batch, int n, int max_out,
                          float iou_threshold, float* out_boxes, int* out_idx, int* out_count, cudaStream_t st);

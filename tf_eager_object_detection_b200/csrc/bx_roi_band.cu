@@ -539,8 +539,8 @@ roi_band_kernel(const __grid_constant__ CUtensorMap tmap, const BandArgs a) {
   const uint32_t tab_step = a.n_blocks_max > 1 ? L.bytes : 0u;      // offset of the second buffer
   __shared__ uint64_t mbar[2];
 
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int P = r.P, Q = r.Q, C = r.c;
+  const int tid = threadIdx.x;
+  const int C = r.c;
   if (a.dbg && tid == 0) {
     unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
