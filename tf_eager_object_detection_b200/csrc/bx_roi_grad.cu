@@ -156,7 +156,7 @@ __device__ __forceinline__ void add_taps(unsigned acc, const Pk<VEC> (&d)[8], co
 // and the length of a warp's entry chain is the run time): the W warps share ONE slice, take every W-th entry into private
 // copies of the row, and the copies are summed in warp order at the end — still one fixed summation order.
 template <int POOL, int VEC, int W, int KP, bool SPLIT>
-__global__ void __launch_bounds__(W * 32) roi_grad_rows_kernel(const GradRowsArgs ga) {
+__global__ void __launch_bounds__(W * 32, KP ? (VEC == 2 ? 3 : 2) : 1) roi_grad_rows_kernel(const GradRowsArgs ga) {
   constexpr int S = (POOL == BX_POOL_NONE) ? 1 : 2;
   constexpr int kThreads = W * 32;
   constexpr int kPix = 32 * VEC * 4;   // bytes per pixel of a warp's row
@@ -321,12 +321,26 @@ __global__ void __launch_bounds__(W * 32) roi_grad_rows_kernel(const GradRowsArg
           }
         }
       };
-      auto process = [&](int e, const V (&gv)[8], const CV (&cd)[8]) {
+      // one entry: route the loaded gradients to this sample row's samples (which frees the load buffer: the loads of the
+      // entry three ahead are issued into it right there, in front of the shared-memory work they overlap), then add the
+      // upper and / or lower tap row's shares
+      auto process = [&](int e, V (&gv)[8], CV (&cd)[8], int e_next) {
         const uint2 er = lds64(t_e + e * 8);
         const int hs = er.x & 0xffu, sy = (er.x >> 8) & 0xffu, p0 = (er.x >> 16) & 0xffu;
         const float ly = __uint_as_float(lds32(t_ly + (hs * Q + sy) * 4));
         const unsigned txa = t_x + (hs * Q + p0 * S) * 8;
         const int n = KP ? KP : min(8, P - p0);
+        Pk<VEC> q[S][8];
+        uint2 xe[S][8];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < N && k < n) {
+              xe[s][k] = lds64(txa + (k * S + s) * 8);
+              q[s][k] = route<POOL, VEC>(gv[k], static_cast<unsigned>(cd[k]), 2 * (sy & 1) + s);
+            }
+        issue(e_next, gv, cd);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           if (!((er.x >> (24 + half)) & 1u)) continue;
@@ -334,19 +348,15 @@ __global__ void __launch_bounds__(W * 32) roi_grad_rows_kernel(const GradRowsArg
 #pragma unroll
           for (int s = 0; s < S; ++s) {
             Pk<VEC> d[8];
-            uint2 xe[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              if (k < N && k < n) xe[k] = lds64(txa + (k * S + s) * 8);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (k < N && k < n) d[k] = pk_scale<VEC>(wy, route<POOL, VEC>(gv[k], static_cast<unsigned>(cd[k]), 2 * (sy & 1) + s));
+              if (k < N && k < n) d[k] = pk_scale<VEC>(wy, q[s][k]);
             if ((er.x >> 26) & 1u) {
-              add_taps<VEC, true, 0, N>(acc, d, xe, n);
-              add_taps<VEC, true, 1, N>(acc, d, xe, n);
+              add_taps<VEC, true, 0, N>(acc, d, xe[s], n);
+              add_taps<VEC, true, 1, N>(acc, d, xe[s], n);
             } else {
-              add_taps<VEC, false, 0, N>(acc, d, xe, n);
-              add_taps<VEC, false, 1, N>(acc, d, xe, n);
+              add_taps<VEC, false, 0, N>(acc, d, xe[s], n);
+              add_taps<VEC, false, 1, N>(acc, d, xe[s], n);
             }
           }
         }
@@ -360,16 +370,9 @@ __global__ void __launch_bounds__(W * 32) roi_grad_rows_kernel(const GradRowsArg
         issue(e0 + kStep, gb_, cb_);
         issue(e0 + 2 * kStep, gc_, cc_);
         for (int e = e0; e < n_ent; e += 3 * kStep) {
-          process(e, ga_, ca_);
-          issue(e + 3 * kStep, ga_, ca_);
-          if (e + kStep < n_ent) {
-            process(e + kStep, gb_, cb_);
-            issue(e + 4 * kStep, gb_, cb_);
-          }
-          if (e + 2 * kStep < n_ent) {
-            process(e + 2 * kStep, gc_, cc_);
-            issue(e + 5 * kStep, gc_, cc_);
-          }
+          process(e, ga_, ca_, e + 3 * kStep);
+          if (e + kStep < n_ent) process(e + kStep, gb_, cb_, e + 4 * kStep);
+          if (e + 2 * kStep < n_ent) process(e + 2 * kStep, gc_, cc_, e + 5 * kStep);
         }
       }
       __syncthreads();
