@@ -298,15 +298,15 @@ __global__ void __launch_bounds__(W * 32, KP ? (VEC == 2 ? 3 : 2) : 1) roi_grad_
       // the gradient rows of the next three entries are in flight while one entry is added: a warp walks its entries one
       // after the other (they may touch the same pixels), and few warps fit beside their rows in shared memory, so the
       // DRAM round trip of a row has to overlap the work on the rows before it
-      auto issue = [&](int e, V (&g)[8], CV (&c)[8]) {
+      auto issue = [&](int e, V (&g)[8], CV (&c)[8], uint2& er) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           V z = {};
           g[k] = z;
           c[k] = 0;
         }
+        if (e < n_ent) er = lds64(t_e + e * 8);   // kept in registers until the entry is processed
         if (e < n_ent && ch_ok) {
-          const uint2 er = lds64(t_e + e * 8);
           const int n = KP ? KP : min(8, P - static_cast<int>((er.x >> 16) & 0xffu));
           const float* gp = go_lane + static_cast<size_t>(er.y) * cstride;
           const unsigned char* cp = code_lane + static_cast<size_t>(er.y) * cstride;
@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(W * 32, KP ? (VEC == 2 ? 3 : 2) : 1) roi_grad_
       // one entry: route the loaded gradients to this sample row's samples (which frees the load buffer: the loads of the
       // entry three ahead are issued into it right there, in front of the shared-memory work they overlap), then add the
       // upper and / or lower tap row's shares
-      auto process = [&](int e, V (&gv)[8], CV (&cd)[8], int e_next) {
-        const uint2 er = lds64(t_e + e * 8);
+      auto process = [&](uint2& er_buf, V (&gv)[8], CV (&cd)[8], int e_next) {
+        const uint2 er = er_buf;
         const int hs = er.x & 0xffu, sy = (er.x >> 8) & 0xffu, p0 = (er.x >> 16) & 0xffu;
         const float ly = __uint_as_float(lds32(t_ly + (hs * Q + sy) * 4));
         const unsigned txa = t_x + (hs * Q + p0 * S) * 8;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(W * 32, KP ? (VEC == 2 ? 3 : 2) : 1) roi_grad_
               xe[s][k] = lds64(txa + (k * S + s) * 8);
               q[s][k] = route<POOL, VEC>(gv[k], static_cast<unsigned>(cd[k]), 2 * (sy & 1) + s);
             }
-        issue(e_next, gv, cd);
+        issue(e_next, gv, cd, er_buf);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           if (!((er.x >> (24 + half)) & 1u)) continue;
@@ -366,13 +366,14 @@ __global__ void __launch_bounds__(W * 32, KP ? (VEC == 2 ? 3 : 2) : 1) roi_grad_
         CV ca_[8], cb_[8], cc_[8];
         constexpr int kStep = SPLIT ? W : 1;
         const int e0 = SPLIT ? warp : 0;
-        issue(e0, ga_, ca_);
-        issue(e0 + kStep, gb_, cb_);
-        issue(e0 + 2 * kStep, gc_, cc_);
+        uint2 ea_ = make_uint2(0, 0), eb_ = ea_, ec_ = ea_;
+        issue(e0, ga_, ca_, ea_);
+        issue(e0 + kStep, gb_, cb_, eb_);
+        issue(e0 + 2 * kStep, gc_, cc_, ec_);
         for (int e = e0; e < n_ent; e += 3 * kStep) {
-          process(e, ga_, ca_, e + 3 * kStep);
-          if (e + kStep < n_ent) process(e + kStep, gb_, cb_, e + 4 * kStep);
-          if (e + 2 * kStep < n_ent) process(e + 2 * kStep, gc_, cc_, e + 5 * kStep);
+          process(ea_, ga_, ca_, e + 3 * kStep);
+          if (e + kStep < n_ent) process(eb_, gb_, cb_, e + 4 * kStep);
+          if (e + 2 * kStep < n_ent) process(ec_, gc_, cc_, e + 5 * kStep);
         }
       }
       __syncthreads();
