@@ -71,6 +71,7 @@ struct ProposalArgs {
   // order, `src_idx` maps its positions back to anchors, boxes / deltas keep the full stride `src_stride`
   const int* src_idx;     // [batch,n] or null
   int src_stride;         // anchors per image in deltas / boxes when src_idx is set
+  int first_chunk;        // candidates of the first select / sort / sweep round; 0: smallest power of two >= the quota
   const int* topset_info; // [batch,4] (threshold lo, m, n_valid_full, fallback flag) or null
   int* flag_out;          // &info[0][3]: set to 1 when the compacted list ran dry before the quota was met
   const int* run_flag;    // fallback launch: images whose flag is 0 return immediately
@@ -380,9 +381,12 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   int consumed = 0;
   int tile_seq = 0;                        // tiles announced to the helpers so far (double-buffer parity)
 
-  // first round: a chunk about 1.5x the quota (NMS usually fills it from there); later rounds take full chunks
+  // first round: the smallest power of two (>= 512) that can fill the quota; later rounds take full chunks.  Measured
+  // (profiles/README.md): at quota 1000 a first chunk of 1024 beats 2048 by 15 - 18 % (sorting and decoding twice the quota
+  // costs more than the second round it sometimes saves); at quota 300, 512 beats 256 and 1024.
   int round_cap = 512;
-  while (round_cap < kChunk && round_cap < a.post_nms + (a.post_nms >> 1)) round_cap <<= 1;
+  while (round_cap < kChunk && round_cap < a.post_nms) round_cap <<= 1;
+  if (a.first_chunk > 0) round_cap = min(a.first_chunk, kChunk);
   while (consumed < limit && sh->kept < a.post_nms) {
     const int want = min(round_cap, limit - consumed);
     round_cap = kChunk;
@@ -985,6 +989,7 @@ size_t proposals_smem_bytes(int n, bool cache, int tile) {
 static int launch_proposals_kernel(bx_handle* h, ProposalArgs& a, int batch, cudaStream_t st) {
   const bool cache = a.n <= kKeyCacheMax;
   a.cache_keys = cache ? 1 : 0;
+  if (const char* fc = getenv("BX_PROP_FIRST_CHUNK")) a.first_chunk = atoi(fc);   // A/B switch, read per call
   const size_t smem64 = proposals_smem_bytes(a.n, cache, 64);
   BX_REQUIRE(smem64 <= h->smem_optin, BX_ERR_UNSUPPORTED, "proposals: %zu B shared memory > device limit %zu", smem64,
              h->smem_optin);
