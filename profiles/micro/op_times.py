@@ -88,7 +88,7 @@ lg = torch.randn((8, 38 * 63, 18), device=dev)
 rows.append(('f2 proposals_rpn  B=8 raw logits 6000->300 (softmax fused)', t(lambda: ops.proposals_rpn(anchors, deltas, lg, _lib.RPN_CAFFE, 9, (600, 1000), 300, pre_nms_top_k=6000)), 8 * (40 * 21546 + 20 * 300)))
 rows.append(('f2 generate_anchors FPN 800x1333 (267069 anchors)', t(lambda: __import__('tf_eager_object_detection_b200.anchor_generator', fromlist=['x']).make_fpn_anchors((800, 1333))), 16 * 267069))
 go = torch.randn((2400, 7, 7, 1024), device=dev)
-rows.append(('f3 roi_pool_grad 7x7x1024 R=2400 -> [8,38,63,1024]', t(lambda: ops.roi_pool_grad(_lib.ROI_STRIDE_NORM, _lib.POOL_NONE, 7, feat, ob.reshape(-1, 4), go, roi_counts=oc), n=10), 4 * 2400 * 49 * 1024 + 2 * 8 * 4 * 1024 * 38 * 63))
+rows.append(('f3 roi_pool_grad 7x7x1024 R=2400 -> [8,38,63,1024]', t(lambda: ops.roi_pool_grad(_lib.ROI_STRIDE_NORM, _lib.POOL_NONE, 7, feat, ob.reshape(-1, 4), go, roi_counts=oc), n=10), 4 * 2400 * 49 * 1024 + 8 * 4 * 1024 * 38 * 63))   # grad_out read + grad_feat written once (no memset)
 gfp = [torch.randn((1, h, w, 256), device=dev) for (h, w) in syn.fpn_feature_shapes((600, 1000))[:1]]
 lab = torch.randint(-1, 2, (16 * 21546,), device=dev).float()
 lg2 = torch.randn((16 * 21546, 2), device=dev)
