@@ -1336,3 +1336,51 @@ def test_roi_pool_backward_row_owned_kernel(bx, monkeypatch, case):
         torch.use_deterministic_algorithms(before)
     assert torch.equal(b1, b2)
     close(b1.cpu().numpy(), want, scale=scale)
+
+
+def test_roi_pool_backward_kernels_agree_on_random_shapes(bx, monkeypatch):
+    """Randomised cross-check of the two backward kernels (and the oracle on the smaller cases): pooled sizes 1..12, all three
+    extractors, 4..100 channels, maps up to 90 x 150 (up to three 64-pixel segments), boxes that are inverted, degenerate,
+    partly or wholly outside the image, images without rois."""
+    from tf_eager_object_detection_b200 import _lib
+    rng = np.random.default_rng(20260)
+    for trial in range(24):
+        P = int(rng.integers(1, 13))
+        pool = int(rng.integers(0, 3))
+        mode = [_lib.ROI_STRIDE_NORM, _lib.ROI_IMAGE_NORM, _lib.ROI_ALIGN_PAD][int(rng.integers(0, 3))]
+        if P == 1 and pool == _lib.POOL_NONE and mode == _lib.ROI_ALIGN_PAD:
+            P = 2
+        b = int(rng.integers(1, 4))
+        fh, fw = int(rng.integers(3, 91)), int(rng.integers(3, 151))
+        c = 4 * int(rng.integers(1, 26))
+        stride = float(rng.choice([4.0, 8.0, 16.0]))
+        H, W = int(fh * stride), int(fw * stride)
+        r = int(rng.integers(1, 60))
+        rois = syn.random_rois(rng, r, (H, W)).astype(np.float32)
+        k = rng.integers(0, 6, r)
+        rois[k == 1] = rois[k == 1][:, [2, 3, 0, 1]]                      # inverted
+        rois[k == 2, 2:] = rois[k == 2, :2]                               # zero size
+        rois[k == 3] += np.float32([W, H, W, H]) * np.float32(0.6)        # partly / wholly outside
+        rois[k == 4] -= np.float32([W, H, W, H]) * np.float32(0.4)
+        bi = rng.integers(0, b, r).astype(np.int32)
+        if b > 1:
+            bi[bi == b - 1] = 0                                           # the last image has no rois
+        feat = rng.standard_normal((b, fh, fw, c), dtype=np.float32)
+        g = rng.standard_normal((r, P, P, c), dtype=np.float32)
+        kw = dict(stride=stride, image_shape=(H, W), box_ind=cu(bi))
+        call = lambda: bx.roi_pool_grad(mode, pool, P, cu(feat), cu(rois), cu(g), **kw)
+        monkeypatch.setenv('BX_ROI_GRAD_ATOMIC', '1')
+        ref = call()
+        monkeypatch.setenv('BX_ROI_GRAD_ATOMIC', '0')
+        monkeypatch.setenv('BX_ROI_GRAD_DETERMINISTIC', '1')
+        monkeypatch.setenv('BX_ROI_GRAD_SPLIT', str(trial & 1))
+        a1, a2 = call(), call()
+        monkeypatch.delenv('BX_ROI_GRAD_DETERMINISTIC')
+        monkeypatch.delenv('BX_ROI_GRAD_SPLIT')
+        tag = 'trial %d: P=%d pool=%d mode=%d b=%d map=%dx%d c=%d r=%d' % (trial, P, pool, mode, b, fh, fw, c, r)
+        assert torch.equal(a1, a2), tag
+        scale = max(float(ref.abs().max()), 1e-6)
+        assert float((a1 - ref).abs().max()) <= 2e-5 * scale, tag
+        if mode == _lib.ROI_STRIDE_NORM and pool != _lib.POOL_AVG2 and trial % 3 == 0:
+            want = orc.roi_pool_c4_grad(feat, rois, stride, g, P, pool == _lib.POOL_MAX2, box_ind=bi)
+            close(a1.cpu().numpy(), want, scale=max(np.abs(want).max(), 1e-6))
