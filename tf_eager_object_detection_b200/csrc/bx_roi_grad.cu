@@ -524,7 +524,7 @@ int roi_grad_rows_launch(bx_handle* h, const RoiGradArgs& g, int pool, cudaStrea
   // few rows: the warps of a CTA share one channel slice and split its entries (BX_ROI_GRAD_SPLIT=0/1 overrides)
   const int slices = (a.c + 32 * vec - 1) / (32 * vec);
   const long long rows = static_cast<long long>(a.b) * fh * ga.n_xseg;
-  bool split = rows * ((slices + warps - 1) / warps) < 4LL * h->num_sms;
+  bool split = rows * ((slices + warps - 1) / warps) < 3LL * h->num_sms;   // less than one CTA per resident slot (3 per SM)
   // default = the faster kernel as measured: the scatter kernel for the 2x2 max and for problems this small
   if (!deterministic && (pool == BX_POOL_MAX2 || split)) return BX_OK;
   if (const char* s = getenv("BX_ROI_GRAD_SPLIT")) split = atoi(s) != 0;
