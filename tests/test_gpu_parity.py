@@ -1243,6 +1243,22 @@ def test_cuda_graph_capture_and_stream_ordered_workspaces(bx):
     _lib.check(lib.bx_destroy(hh))
 
 
+def test_band_height_does_not_change_the_crops(bx, monkeypatch):
+    """BX_ROI_BAND_ROWS caps the feature rows a band owns (measurement switch): more, shorter bands — every roi split over
+    more (image, band) units, more halo rows — must give the same bits."""
+    from tf_eager_object_detection_b200 import _lib
+    rng = np.random.default_rng(78)
+    feat = cu(rng.standard_normal((2, 38, 63, 64), dtype=np.float32))
+    rois = np.stack([syn.random_rois(rng, 300, (600, 1000)) for _ in range(2)])
+    counts = cu(np.int32([300, 123]))
+    monkeypatch.delenv('BX_ROI_BAND_ROWS', raising=False)
+    base = bx.roi_pool(_lib.ROI_STRIDE_NORM, _lib.POOL_NONE, 7, feat, cu(rois), stride=16.0, roi_counts=counts)
+    for rows in ('2', '5', '8'):
+        monkeypatch.setenv('BX_ROI_BAND_ROWS', rows)
+        got = bx.roi_pool(_lib.ROI_STRIDE_NORM, _lib.POOL_NONE, 7, feat, cu(rois), stride=16.0, roi_counts=counts)
+        assert torch.equal(got, base), rows
+
+
 def test_persistent_band_kernel_matches_default(bx, monkeypatch):
     """BX_ROI_BAND_PERSIST=1: the persistent, double-buffered form of the TMA band kernel (one CTA per SM, units drawn from
     a global counter, next band + plan block prefetched) must reproduce the per-unit kernel bit for bit — plain crops at the

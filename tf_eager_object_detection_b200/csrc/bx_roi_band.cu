@@ -768,6 +768,10 @@ bool make_band_cfg(int fh, int fw, int Q, int rois_range, size_t budget, BandCfg
   int max_rows_loaded = static_cast<int>((budget - tab - zrow - 256) / row_bytes);
   if (max_rows_loaded < 3) return false;                                    // map too wide for a useful band
   if (max_rows_loaded > fh) max_rows_loaded = fh;
+  if (const char* e = getenv("BX_ROI_BAND_ROWS")) {   // measurement switch: cap on the rows a band owns
+    const int cap_rows = atoi(e);
+    if (cap_rows >= 2 && cap_rows + 1 < max_rows_loaded) max_rows_loaded = cap_rows + 1;
+  }
   int rows_per_band = (max_rows_loaded >= fh) ? fh : max_rows_loaded - 1;
   const int n_bands = (fh + rows_per_band - 1) / rows_per_band;
   rows_per_band = (fh + n_bands - 1) / n_bands;
