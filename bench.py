@@ -984,7 +984,7 @@ def main():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--streams', type=int, default=8, help='steps are issued round-robin over this many CUDA streams')
+    ap.add_argument('--streams', type=int, default=16, help='steps are issued round-robin over this many CUDA streams')
     ap.add_argument('--fpn-streams', type=int, default=4)
     ap.add_argument('--e2e-steps', type=int, default=20)
     ap.add_argument('--gather-every', type=int, default=0,
