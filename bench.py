@@ -837,7 +837,7 @@ def bench_targets(ctx, args):
     scores = torch.as_tensor(np.stack([im['scores'] for im in imgs])).to(dev)
     rois, _, rc = ops.proposals(anchors, deltas, scores, (600, 1000), Kr)            # the 2000 training proposals (untimed)
     torch.cuda.synchronize()
-    NSTREAM = 2
+    NSTREAM = max(1, args.target_streams)
     o = [dict(lab=torch.empty((B, n), device=dev), tg=torch.empty((B, n, 4), device=dev), iw=torch.empty((B, n, 4), device=dev),
               ow=torch.empty((B, n, 4), device=dev), cnt=torch.empty((B, 2), dtype=torch.int32, device=dev),
               pr=torch.empty((B, S, 4), device=dev), pl=torch.empty((B, S), dtype=torch.int32, device=dev),
@@ -986,6 +986,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--streams', type=int, default=16, help='steps are issued round-robin over this many CUDA streams')
     ap.add_argument('--fpn-streams', type=int, default=4)
+    ap.add_argument('--target-streams', type=int, default=8, help='streams of the cfg4 (training targets) workload')
     ap.add_argument('--e2e-steps', type=int, default=20)
     ap.add_argument('--gather-every', type=int, default=0,
                     help='N > 1: detection records of this many consecutive steps are all-gathered together (0: all K, one gather at the end of the region)')
