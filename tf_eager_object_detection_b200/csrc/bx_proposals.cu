@@ -25,6 +25,7 @@ namespace {
 
 constexpr int kThreads = 1024;
 constexpr int kChunk = 2048;        // candidates sorted + swept per round
+constexpr int kMaxClusterRanks = 16; // CTAs of one image's cluster in the cluster sweep (16 = non-portable size, BX_NMS_CLUSTER=16)
 constexpr int kBins = 2048;         // histogram bins per select level
 static_assert(kBins == 2 * kThreads, "the select scan gives every thread two bins");
 constexpr int kMaxPost = 2048;      // kept-box list capacity (post_nms limit)
@@ -163,7 +164,7 @@ struct Shared {
   alignas(16) ClusterCmd cc;
   int p_valid, p_kept;    // leader: result of the previous tile (copied into cc for the next one)
   uint64_t p_keepmask[2];
-  uint64_t sup_part[8][2];  // partial suppression masks pushed by the helpers
+  uint64_t sup_part[kMaxClusterRanks][2];  // partial suppression masks pushed by the helpers
   uint64_t mb_tile;       // helpers: "tile pushed" (1 arrival per tile, from the leader)
   uint64_t mb_part;       // leader: "partial masks delivered" (cs - 1 arrivals per tile)
 };
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
           sh->cc.p_keepmask[1] = sh->p_keepmask[1];
         }
       }
-      if (cs > 1 && tid < 16) sh->sup_part[tid >> 1][tid & 1] = 0ull;
+      if (cs > 1 && tid < 2 * kMaxClusterRanks) sh->sup_part[tid >> 1][tid & 1] = 0ull;
       if (tid >= 128 && tid < 128 + TILE) { // normalised corners + area of the tile's candidates, masks cleared
         const int c = tid - 128;
         const float4 nb = normalise(cand_box[t0 + min(c, tn - 1)]);
@@ -546,17 +547,18 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
       __syncthreads();
       if (cs > 1) {
         // push the tile's boxes and the command block into every helper's shared memory, then signal A
-        const int n_push = TILE * (static_cast<int>(cs) - 1);                   // <= 896
-        if (tid < n_push) {
-          const uint32_t helper = 1u + static_cast<uint32_t>(tid) / TILE;
-          const int c = tid % TILE;
+        const int n_push = TILE * (static_cast<int>(cs) - 1);                   // 896 at 8 CTAs, 1920 at 16
+        for (int i = tid; i < n_push; i += kThreads) {
+          const uint32_t helper = 1u + static_cast<uint32_t>(i) / TILE;
+          const int c = i % TILE;
           if (c < tn) {
             const float4 b = cand_box[t0 + c];
             dsmem_st_v4(dsmem_addr(&cand_box[(tile_seq & 1) * TILE + c], helper),
                         make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
           }
-        } else if (tid >= 960 && tid < 960 + 3 * (static_cast<int>(cs) - 1)) {
-          const int e = tid - 960, part = e % 3;
+        }
+        if (tid >= kThreads - 64 && tid < kThreads - 64 + 3 * (static_cast<int>(cs) - 1)) {   // the last two warps: 3 x 16 B per helper
+          const int e = tid - (kThreads - 64), part = e % 3;
           const uint32_t helper = 1u + static_cast<uint32_t>(e / 3);
           const uint4* src = reinterpret_cast<const uint4*>(&sh->cc) + part;
           dsmem_st_v4(dsmem_addr(src, helper), *src);
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
         uint64_t rem0 = sh->sup[0], rem1 = sh->sup[1];
         if (cs > 1) {
 #pragma unroll
-          for (int r = 1; r < 8; ++r) { rem0 |= sh->sup_part[r][0]; rem1 |= sh->sup_part[r][1]; }
+          for (int r = 1; r < kMaxClusterRanks; ++r) { rem0 |= sh->sup_part[r][0]; rem1 |= sh->sup_part[r][1]; }
         }
         rem0 |= ~below_w0(tn);
         rem1 |= ~below_w1(tn);
@@ -682,8 +684,8 @@ __global__ void __launch_bounds__(kThreads, 1) proposals_kernel(const ProposalAr
   if (cs > 1) {                              // release the helpers; stay until they have read the command
     if (tid == 0) sh->cc.cmd = 2;
     __syncthreads();
-    if (tid >= 960 && tid < 960 + 3 * (static_cast<int>(cs) - 1)) {
-      const int e = tid - 960, part = e % 3;
+    if (tid >= kThreads - 64 && tid < kThreads - 64 + 3 * (static_cast<int>(cs) - 1)) {
+      const int e = tid - (kThreads - 64), part = e % 3;
       const uint4* src = reinterpret_cast<const uint4*>(&sh->cc) + part;
       dsmem_st_v4(dsmem_addr(src, 1u + static_cast<uint32_t>(e / 3)), *src);
     }
@@ -1004,9 +1006,10 @@ static int launch_proposals_kernel(bx_handle* h, ProposalArgs& a, int batch, cud
   static const int cs_env = getenv("BX_NMS_CLUSTER") ? atoi(getenv("BX_NMS_CLUSTER")) : 0;   // A/B switch
   const size_t smem128 = proposals_smem_bytes(a.n, cache, 128);
   int cs = (a.post_nms >= 512 && smem128 <= h->smem_optin) ? 8 : 1;
-  if (cs_env > 0) cs = cs_env > 8 ? 8 : cs_env;
+  if (cs_env > 0) cs = cs_env > kMaxClusterRanks ? kMaxClusterRanks : cs_env;
   if (cs > 1 && smem128 > h->smem_optin) cs = 1;
   if (cs > 1) BX_CUDA(cudaFuncSetAttribute(proposals_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128));
+  if (cs > 8) BX_CUDA(cudaFuncSetAttribute(proposals_kernel<true, 128>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   for (; cs > 1; cs >>= 1) {               // largest cluster size whose clusters are all co-resident (one wave)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(batch * cs);
